@@ -1,0 +1,100 @@
+"""ctypes loader for libatomorph_b200.so (the C-ABI of include/amx.h and include/amx_morph.h).
+
+There is NO fallback: if the shared object is missing or a CUDA device is absent, calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatomorph_b200.so")
+
+AMX_OK = 0
+STATUS = {0: "AMX_OK", 1: "AMX_ERR_CUDA", 2: "AMX_ERR_ARG", 3: "AMX_ERR_STATE", 4: "AMX_ERR_NOMEM", 5: "AMX_ERR_BUSY"}
+
+_lib = None
+
+
+class AmxError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library (once).  Raises if it has not been built -- never falls back to CPU code."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AmxError("libatomorph_b200.so is not built: run `python -m atomorph_b200.build` "
+                       "(there is no CPU fallback for the morph pipeline)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32, f64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_double
+    P = C.POINTER
+
+    def sig(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig("amx_create", i32, P(vp), i32)
+    sig("amx_destroy", None, vp)
+    sig("amx_last_error", C.c_char_p, vp)
+    sig("amx_version", C.c_char_p)
+    sig("amx_set_stream", i32, vp, vp)
+    sig("amx_device_sync", i32, vp)
+    sig("amx_set_param", i32, vp, i32, f64)
+    sig("amx_get_param", f64, vp, i32)
+    sig("amx_reset", i32, vp)
+    sig("amx_set_canvas", i32, vp, u32, u32, u32, u32, vp)
+    sig("amx_set_frame_count", i32, vp, u32, vp)
+    sig("amx_upload_frame", i32, vp, u32, vp, vp, vp)
+    sig("amx_upload_frame_device", i32, vp, u32, vp, vp, vp)
+    sig("amx_download_fetch", i32, vp, u32, vp)
+    sig("amx_download_stored", i32, vp, u32, vp)
+    sig("amx_step", i32, vp, u64)
+    sig("amx_next_state", i32, vp)
+    sig("amx_get_state", C.c_uint, vp)
+    sig("amx_get_energy", f64, vp)
+    sig("amx_blobify", i32, vp)
+    sig("amx_blob_count", i32, vp, u32, P(u32))
+    sig("amx_export_blobs", i32, vp, u32, vp, vp, vp)
+    sig("amx_import_blobs", i32, vp, u32, u32, vp, vp, vp)
+    sig("amx_match_init", i32, vp)
+    sig("amx_match_rounds", i32, vp, u64)
+    sig("amx_match_energy", i32, vp, P(f64))
+    sig("amx_init_chains", i32, vp)
+    sig("amx_chain_count", i32, vp, P(u32))
+    sig("amx_chain_info", i32, vp, u32, vp)
+    sig("amx_export_chain", i32, vp, u32, vp)
+    sig("amx_import_chains", i32, vp, u32, vp, vp, vp, u32, vp)
+    sig("amx_table_device_ptr", i32, vp, u32, P(vp), P(u64))
+    sig("amx_swap_rounds", i32, vp, i32, i32, u64, vp)
+    sig("amx_swap_stats", i32, vp, vp)
+    sig("amx_cost", i32, vp, P(f64))
+    sig("amx_render_prepare", i32, vp)
+    sig("amx_render", i32, vp, vp, u32, vp, i32)
+    sig("amx_render_blob", i32, vp, u32, f64, u64, vp, vp, P(C.c_int64), P(u64))
+    sig("amx_background", i32, vp, f64, vp, i32)
+    sig("amx_fluid_create", i32, vp, u32, u32, u32)
+    sig("amx_fluid_set_particles", i32, vp, u32, vp)
+    sig("amx_fluid_get_particles", i32, vp, u32, vp)
+    sig("amx_fluid_step", i32, vp, u64, f64, f64)
+    sig("amx_fluid_get_nodes", i32, vp, vp)
+    sig("amx_launch_count", u64, vp)
+    sig("amx_timer_start", i32, vp)
+    sig("amx_timer_stop", i32, vp, P(C.c_float))
+    _lib = L
+    return L
+
+
+# every symbol include/amx.h declares (checked by tests/test_abi.py without a GPU)
+AMX_SYMBOLS = [
+    "amx_create", "amx_destroy", "amx_last_error", "amx_version", "amx_set_stream", "amx_device_sync",
+    "amx_set_param", "amx_get_param", "amx_reset", "amx_set_canvas", "amx_set_frame_count", "amx_upload_frame",
+    "amx_upload_frame_device", "amx_download_fetch", "amx_download_stored", "amx_step", "amx_next_state",
+    "amx_get_state", "amx_get_energy", "amx_blobify", "amx_blob_count", "amx_export_blobs", "amx_import_blobs",
+    "amx_match_init", "amx_match_rounds", "amx_match_energy", "amx_init_chains", "amx_chain_count",
+    "amx_chain_info", "amx_export_chain", "amx_import_chains", "amx_table_device_ptr", "amx_swap_rounds",
+    "amx_swap_stats", "amx_cost", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_background",
+    "amx_fluid_create", "amx_fluid_set_particles", "amx_fluid_get_particles", "amx_fluid_step",
+    "amx_fluid_get_nodes", "amx_launch_count", "amx_timer_start", "amx_timer_stop",
+]

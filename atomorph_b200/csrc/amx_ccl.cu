@@ -1,0 +1,269 @@
+/*
+ * amx_ccl.cu -- K2: blob segmentation and blob statistics (SURVEY.md row a-B1).
+ *
+ * Reference: thread::blobify_frame (thread.cpp:225-412) -- stochastic agglomerative region
+ * merging, one merge per step.  With the library defaults (blob_threshold = 1.0,
+ * blob_max_size = SIZE_MAX, blob_min_size = 1, blob_number = 1) every pair of 4-adjacent
+ * pixels ends in the same blob, i.e. the final partition is exactly the set of 4-connected
+ * components of the presence mask (measured).  That deterministic regime is
+ * what is bit-exact here; for blob_threshold < 1 adjacent pixels are joined when their STORED
+ * colours are within the threshold (color_distance, color.h:17-24) -- a deterministic stand-in
+ * for the reference's RNG-dependent merge order, compared statistically only.
+ *
+ * Algorithm: lock-free union-find on the pixel grid (label = smaller root wins through
+ * atomicMin), then path compression; the root of a component is its smallest canvas index
+ * (= smallest xy2pos, the canonical label of SURVEY.md M2).  Statistics are exact integer
+ * sums (count, x, y, r, g, b, a) reduced per warp with __match_any_sync before one atomic per
+ * distinct root, then divided in double -- the reference reaches the same means through a
+ * chain of pairwise weighted averages (thread.cpp:348-357).
+ *
+ * Blob vector order: ascending canonical label (the reference's order is an RNG shuffle).
+ * Algorithmic bytes: ~16 B per canvas position per key frame.
+ */
+#include <algorithm>
+#include <cub/cub.cuh>
+#include "amx_engine.h"
+
+namespace amx {
+
+__device__ __forceinline__ uint32_t uf_find(const uint32_t *lab, uint32_t i) {
+    uint32_t p = lab[i];
+    while (p != i) { i = p; p = lab[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t *lab, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find(lab, a);
+        b = uf_find(lab, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }     // a > b: hang a under b
+        uint32_t old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;                                           // somebody else re-rooted a meanwhile
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_init(const uint8_t *__restrict__ present, uint32_t *__restrict__ lab, size_t n) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lab[i] = present[i] ? (uint32_t) i : 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_merge(const uint8_t *__restrict__ present, const uint32_t *__restrict__ stored, uint32_t *__restrict__ lab, uint32_t cw, uint32_t ch,
+            int use_threshold, double threshold) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t) cw * ch || !present[i]) return;
+    uint32_t x = (uint32_t) (i % cw), y = (uint32_t) (i / cw);
+    if (x > 0 && present[i - 1] && (!use_threshold || color_distance(stored[i], stored[i - 1]) <= threshold)) uf_union(lab, (uint32_t) i, (uint32_t) i - 1);
+    if (y > 0 && present[i - cw] && (!use_threshold || color_distance(stored[i], stored[i - cw]) <= threshold)) uf_union(lab, (uint32_t) i, (uint32_t) (i - cw));
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_compress(uint32_t *__restrict__ lab, size_t n, uint32_t *__restrict__ root_flag) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t l = lab[i];
+    if (l == 0xffffffffu) { root_flag[i] = 0; return; }
+    uint32_t r = uf_find(lab, (uint32_t) i);
+    lab[i] = r;
+    root_flag[i] = (r == (uint32_t) i) ? 1u : 0u;
+}
+
+// label[i] = rank of the root (blob index); accumulate exact integer statistics per blob
+__global__ void __launch_bounds__(256)
+k_ccl_stats(const uint32_t *__restrict__ lab, const uint32_t *__restrict__ root_rank, const uint32_t *__restrict__ stored,
+            int32_t *__restrict__ label, uint32_t cw, size_t n, unsigned long long *__restrict__ sums /* [nblobs][8] */) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t r = 0xffffffffu;
+    if (i < n) r = lab[i];
+    int32_t b = -1;
+    if (r != 0xffffffffu) b = (int32_t) root_rank[r];
+    if (i < n) label[i] = b;
+    unsigned active = __ballot_sync(0xffffffffu, b >= 0);
+    if (b < 0) return;
+    unsigned peers = __match_any_sync(active, b);
+    unsigned lane = threadIdx.x & 31;
+    unsigned leader = __ffs(peers) - 1;
+    uint32_t c = stored[i];
+    unsigned long long v[7] = {1ull, (unsigned long long) (i % cw), (unsigned long long) (i / cw), c_r(c), c_g(c), c_b(c), c_a(c)};
+    // reduce within the peer group (small loops over set bits; groups are usually the whole warp)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned long long s = 0;
+        unsigned m = peers;
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            s += __shfl_sync(peers, v[k], src);
+        }
+        if (lane == leader) atomicAdd(&sums[(size_t) b * 8 + k], s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_iota_keys(const int32_t *__restrict__ label, unsigned long long *__restrict__ keys, size_t n) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t b = label[i];
+    keys[i] = b < 0 ? 0xffffffffffffffffull : (((unsigned long long) (uint32_t) b << 32) | (unsigned long long) i);
+}
+__global__ void __launch_bounds__(256)
+k_keys_to_pix(const unsigned long long *__restrict__ keys, uint32_t *__restrict__ pix, size_t npix) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) pix[i] = (uint32_t) (keys[i] & 0xffffffffull);
+}
+
+// per-blob pixel lists (ascending position inside a blob) from the label image: radix sort of (blob, index) keys
+int engine_build_blob_pixels(Engine *E, uint32_t index) {
+    FrameDev &f = E->frames[index];
+    size_t n = E->canvas();
+    dev_free(f.blob_pix); f.blob_pix = nullptr;
+    f.blob_pix_off.assign(f.blobs.size() + 1, 0);
+    for (size_t b = 0; b < f.blobs.size(); ++b) f.blob_pix_off[b + 1] = f.blob_pix_off[b] + f.blobs[b].size;
+    uint64_t npix = f.blob_pix_off.back();
+    if (npix == 0) return AMX_OK;
+    unsigned long long *k_in = nullptr, *k_out = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    if (!dev_alloc(E, (void **) &k_in, n * 8, "sort keys") || !dev_alloc(E, (void **) &k_out, n * 8, "sort keys")) { dev_free(k_in); return AMX_ERR_NOMEM; }
+    k_iota_keys<<<div_up(n, 256), 256, 0, E->stream>>>(f.label, k_in, n);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k_in, k_out, (int) n, 0, 64, E->stream);
+    if (!dev_alloc(E, &tmp, tmp_bytes, "sort tmp")) { dev_free(k_in); dev_free(k_out); return AMX_ERR_NOMEM; }
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k_in, k_out, (int) n, 0, 64, E->stream);
+    int rc = AMX_OK;
+    if (!dev_alloc(E, (void **) &f.blob_pix, npix * 4, "blob_pix")) rc = AMX_ERR_NOMEM;
+    else k_keys_to_pix<<<div_up(npix, 256), 256, 0, E->stream>>>(k_out, f.blob_pix, npix);
+    E->launches += 3;
+    if (E->fail(cudaStreamSynchronize(E->stream), "blob pixels") || E->check("blob pixels")) rc = AMX_ERR_CUDA;
+    dev_free(k_in); dev_free(k_out); dev_free(tmp);
+    return rc;
+}
+
+static int blobify_frame(Engine *E, uint32_t index) {
+    FrameDev &f = E->frames[index];
+    size_t n = E->canvas();
+    f.blobs.clear();
+    dev_free(f.blob_pix); f.blob_pix = nullptr; f.blob_pix_off.clear();
+    if (f.pixel_count == 0) { cudaMemsetAsync(f.label, 0xff, n * 4, E->stream); return AMX_OK; }
+    uint32_t *lab = nullptr, *flag = nullptr, *rank = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    unsigned long long *sums = nullptr;
+    int rc = AMX_OK;
+    if (!dev_alloc(E, (void **) &lab, n * 4, "ccl lab") || !dev_alloc(E, (void **) &flag, n * 4, "ccl flag") || !dev_alloc(E, (void **) &rank, n * 4, "ccl rank")) rc = AMX_ERR_NOMEM;
+    if (rc == AMX_OK) {
+        bool use_thr = E->p.blob_threshold < 1.0;
+        k_ccl_init<<<div_up(n, 256), 256, 0, E->stream>>>(f.present, lab, n);
+        if (E->p.blob_max_size > 1)
+            k_ccl_merge<<<div_up(n, 256), 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold);
+        k_ccl_compress<<<div_up(n, 256), 256, 0, E->stream>>>(lab, n, flag);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, rank, (int) n, E->stream);
+        if (!dev_alloc(E, &tmp, tmp_bytes, "scan tmp")) rc = AMX_ERR_NOMEM;
+    }
+    uint32_t nblobs = 0;
+    if (rc == AMX_OK) {
+        cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, (int) n, E->stream);
+        uint32_t last_rank = 0, last_flag = 0;
+        cudaMemcpyAsync(&last_rank, rank + n - 1, 4, cudaMemcpyDeviceToHost, E->stream);
+        cudaMemcpyAsync(&last_flag, flag + n - 1, 4, cudaMemcpyDeviceToHost, E->stream);
+        if (E->fail(cudaStreamSynchronize(E->stream), "ccl")) rc = AMX_ERR_CUDA;
+        nblobs = last_rank + last_flag;
+        E->launches += 4;
+    }
+    if (rc == AMX_OK && !dev_alloc(E, (void **) &sums, (size_t) std::max(nblobs, 1u) * 64, "ccl sums")) rc = AMX_ERR_NOMEM;
+    if (rc == AMX_OK) {
+        cudaMemsetAsync(sums, 0, (size_t) std::max(nblobs, 1u) * 64, E->stream);
+        k_ccl_stats<<<div_up(n, 256), 256, 0, E->stream>>>(lab, rank, f.stored, f.label, E->cw, n, sums);
+        E->launches++;
+        std::vector<unsigned long long> hs((size_t) nblobs * 8);
+        if (nblobs) cudaMemcpyAsync(hs.data(), sums, hs.size() * 8, cudaMemcpyDeviceToHost, E->stream);
+        if (E->fail(cudaStreamSynchronize(E->stream), "ccl stats") || E->check("ccl stats")) rc = AMX_ERR_CUDA;
+        else {
+            f.blobs.resize(nblobs);
+            for (uint32_t b = 0; b < nblobs; ++b) {
+                const unsigned long long *s = &hs[(size_t) b * 8];
+                BlobHost &bl = f.blobs[b];
+                double cnt = (double) s[0];
+                bl.size = s[0];
+                bl.group = b;
+                bl.stats[0] = (double) s[1] / cnt;
+                bl.stats[1] = (double) s[2] / cnt;
+                for (int k = 0; k < 4; ++k) bl.stats[2 + k] = ((double) s[3 + k] / cnt) / 255.0;
+            }
+        }
+    }
+    dev_free(lab); dev_free(flag); dev_free(rank); dev_free(tmp); dev_free(sums);
+    if (rc == AMX_OK) rc = engine_build_blob_pixels(E, index);
+    return rc;
+}
+
+int engine_blobify(Engine *E) {
+    for (uint32_t i = 0; i < E->frames.size(); ++i) {
+        int rc = blobify_frame(E, i);
+        if (rc != AMX_OK) return rc;
+    }
+    return AMX_OK;
+}
+
+} // namespace amx
+
+using namespace amx;
+extern "C" {
+
+int amx_blobify(amx_ctx *ctx) {
+    if (!ctx) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    int rc = engine_blobify(&ctx->e);
+    if (rc == AMX_OK && ctx->e.state == ST_BLOB_DETECTION) ctx->e.state = ST_BLOB_UNIFICATION;
+    return rc;
+}
+
+int amx_blob_count(amx_ctx *ctx, uint32_t index, uint32_t *count) {
+    if (!ctx || !count || index >= ctx->e.frames.size()) return AMX_ERR_ARG;
+    *count = (uint32_t) ctx->e.frames[index].blobs.size();
+    return AMX_OK;
+}
+
+int amx_export_blobs(amx_ctx *ctx, uint32_t index, int32_t *labels_out, double *stats_out, uint64_t *meta_out) {
+    if (!ctx || index >= ctx->e.frames.size()) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    FrameDev &f = E->frames[index];
+    if (labels_out) {
+        if (E->fail(cudaMemcpyAsync(labels_out, f.label, E->canvas() * 4, cudaMemcpyDeviceToHost, E->stream), "labels D2H") ||
+            E->fail(cudaStreamSynchronize(E->stream), "labels"))
+            return AMX_ERR_CUDA;
+    }
+    for (size_t b = 0; b < f.blobs.size(); ++b) {
+        if (stats_out) for (int k = 0; k < 6; ++k) stats_out[6 * b + k] = f.blobs[b].stats[k];
+        if (meta_out) { meta_out[2 * b] = f.blobs[b].group; meta_out[2 * b + 1] = f.blobs[b].size; }
+    }
+    return AMX_OK;
+}
+
+int amx_import_blobs(amx_ctx *ctx, uint32_t index, uint32_t nblobs, const int32_t *labels, const double *stats, const uint64_t *groups) {
+    if (!ctx || index >= ctx->e.frames.size() || (nblobs && (!stats || !groups))) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    FrameDev &f = E->frames[index];
+    size_t n = E->canvas();
+    f.blobs.assign(nblobs, BlobHost());
+    for (uint32_t b = 0; b < nblobs; ++b) {
+        for (int k = 0; k < 6; ++k) f.blobs[b].stats[k] = stats[6 * b + k];
+        f.blobs[b].group = groups[b];
+        f.blobs[b].size = 0;
+    }
+    if (labels) {
+        for (size_t i = 0; i < n; ++i) if (labels[i] >= 0 && (uint32_t) labels[i] < nblobs) f.blobs[labels[i]].size++;
+        if (E->fail(cudaMemcpyAsync(f.label, labels, n * 4, cudaMemcpyHostToDevice, E->stream), "labels H2D") ||
+            E->fail(cudaStreamSynchronize(E->stream), "labels"))
+            return AMX_ERR_CUDA;
+    } else cudaMemsetAsync(f.label, 0xff, n * 4, E->stream);
+    dev_free(f.blob_pix); f.blob_pix = nullptr; f.blob_pix_off.clear();
+    E->render_ready = false;
+    return labels ? engine_build_blob_pixels(E, index) : AMX_OK;
+}
+
+}

@@ -1,0 +1,385 @@
+/*
+ * amx_fluid.cu -- K5: the Material-Point-Method liquid step (SURVEY.md row a-F, M3).
+ *
+ * Reference: FluidModel::step (fluidmodel.cpp:165-580; Grant Kot's MPM with atomorph's
+ * customisations: inactive particles, colour diffusion through nodes, attractor, freedom
+ * radius).  The reference walks particles serially and scatters into AoS nodes; here every
+ * pass is one kernel over particles (SoA doubles) or nodes (SoA doubles), scatters are double
+ * atomicAdd into the 3x3 quadratic B-spline stencil, so node sums differ from the reference only
+ * by summation order (<< 1e-5 relative).  The node colour, a strength-weighted running mean in
+ * the reference (fluidmodel.cpp:234-244), is kept as sum(w*c) and sum(w): the G2P pass only ever
+ * uses mean*weight (fluidmodel.cpp:463-469), which is that sum.
+ *
+ * Passes per step (algorithmic bytes: Np*(120 read + 64 written) + Ng*2*104, section 8d):
+ *   clear grid | P2G mass/gradients/colour | pressure+wall forces -> node acceleration |
+ *   node a/=m | particle velocity update + momentum scatter | node v/=m | G2P gather + move
+ *
+ * Wall clamping uses the counter-based RNG where the reference calls rand() (fluidmodel.cpp:553-566).
+ */
+#include "amx_engine.h"
+
+namespace amx {
+
+enum { PF_X, PF_Y, PF_U, PF_V, PF_GX, PF_GY, PF_FREE, PF_RI, PF_GI, PF_BI, PF_AI, PF_R, PF_G, PF_B, PF_A, PF_STRENGTH, PF_COUNT };
+enum { NF_M, NF_D, NF_GX, NF_GY, NF_U, NF_V, NF_AX, NF_AY, NF_R, NF_G, NF_B, NF_A, NF_W, NF_COUNT };
+
+struct Fluid {
+    uint32_t gx = 0, gy = 0, n = 0;
+    double *pf = nullptr;        // [PF_COUNT][n]
+    uint8_t *active = nullptr, *mature = nullptr, *owner = nullptr;
+    double *aux = nullptr;       // [3][n] frame_key, source_pos, destination_pos (driver bookkeeping)
+    double *nf = nullptr;        // [NF_COUNT][gx*gy]
+    uint64_t step_counter = 0;
+};
+
+struct PW { int cx, cy; double px[3], py[3], gx[3], gy[3]; };
+
+__device__ __forceinline__ void particle_weights(double x, double y, PW &w) {
+    // fluidmodel.cpp:195-218
+    w.cx = (int) (x - 0.5);
+    w.cy = (int) (y - 0.5);
+    double t = (double) (unsigned) w.cx - x;
+    w.px[0] = (0.5 * t * t + 1.5 * t + 1.125); w.gx[0] = (t + 1.5);
+    t += 1.0;
+    w.px[1] = (-t * t + 0.75); w.gx[1] = (-2.0 * t);
+    t += 1.0;
+    w.px[2] = (0.5 * t * t - 1.5 * t + 1.125); w.gx[2] = (t - 1.5);
+    t = (double) (unsigned) w.cy - y;
+    w.py[0] = (0.5 * t * t + 1.5 * t + 1.125); w.gy[0] = (t + 1.5);
+    t += 1.0;
+    w.py[1] = (-t * t + 0.75); w.gy[1] = (-2.0 * t);
+    t += 1.0;
+    w.py[2] = (0.5 * t * t - 1.5 * t + 1.125); w.gy[2] = (t - 1.5);
+}
+
+#define PFI(k) pf[(size_t) (k) * n + i]
+#define NODE(k, idx) nf[(size_t) (k) * ng + (idx)]
+
+__global__ void __launch_bounds__(128)
+k_fluid_p2g(const double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
+            double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !active[i]) return;
+    size_t ng = (size_t) gsx * gsy;
+    PW w;
+    particle_weights(PFI(PF_X), PFI(PF_Y), w);
+    double strength = PFI(PF_STRENGTH);
+    bool colour = mature[i] && strength > 0.0;
+    double r = PFI(PF_R), g = PFI(PF_G), b = PFI(PF_B), a = PFI(PF_A);
+    for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) {
+            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
+            if (nx >= gsx || ny >= gsy) continue;
+            size_t idx = (size_t) ny * gsx + nx;
+            double phi = w.px[ii] * w.py[jj];
+            atomicAdd(&NODE(NF_M, idx), phi * 1.0);
+            atomicAdd(&NODE(NF_D, idx), phi);
+            atomicAdd(&NODE(NF_GX, idx), w.gx[ii] * w.py[jj]);
+            atomicAdd(&NODE(NF_GY, idx), w.px[ii] * w.gy[jj]);
+            if (colour) {
+                atomicAdd(&NODE(NF_R, idx), strength * r);
+                atomicAdd(&NODE(NF_G, idx), strength * g);
+                atomicAdd(&NODE(NF_B, idx), strength * b);
+                atomicAdd(&NODE(NF_A, idx), strength * a);
+                atomicAdd(&NODE(NF_W, idx), strength);
+            }
+        }
+}
+
+__global__ void __launch_bounds__(128)
+k_fluid_forces(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !active[i]) return;
+    size_t ng = (size_t) gsx * gsy;
+    double x = PFI(PF_X), y = PFI(PF_Y);
+    PW w;
+    particle_weights(x, y, w);
+    // fluidmodel.cpp:275-317 cubic density interpolant from the 4 corner nodes
+    uint32_t cx = (uint32_t) (int) x, cy = (uint32_t) (int) y;
+    uint32_t cxi = cx + 1, cyi = cy + 1;
+    auto ld = [&](int k, uint32_t ix, uint32_t iy) -> double { return (ix < gsx && iy < gsy) ? NODE(k, (size_t) iy * gsx + ix) : 0.0; };
+    double n01d = ld(NF_D, cx, cy), n01gx = ld(NF_GX, cx, cy), n01gy = ld(NF_GY, cx, cy);
+    double n02d = ld(NF_D, cx, cyi), n02gx = ld(NF_GX, cx, cyi), n02gy = ld(NF_GY, cx, cyi);
+    double n11d = ld(NF_D, cxi, cy), n11gx = ld(NF_GX, cxi, cy), n11gy = ld(NF_GY, cxi, cy);
+    double n12d = ld(NF_D, cxi, cyi), n12gx = ld(NF_GX, cxi, cyi), n12gy = ld(NF_GY, cxi, cyi);
+    double pdx = n11d - n01d, pdy = n02d - n01d;
+    double C20 = 3.0 * pdx - n11gx - 2.0 * n01gx;
+    double C02 = 3.0 * pdy - n02gy - 2.0 * n01gy;
+    double C30 = -2.0 * pdx + n11gx + n01gx;
+    double C03 = -2.0 * pdy + n02gy + n01gy;
+    double csum1 = n01d + n01gy + C02 + C03;
+    double csum2 = n01d + n01gx + C20 + C30;
+    double C21 = 3.0 * n12d - 2.0 * n02gx - n12gx - 3.0 * csum1 - C20;
+    double C31 = -2.0 * n12d + n02gx + n12gx + 2.0 * csum1 - C30;
+    double C12 = 3.0 * n12d - 2.0 * n11gy - n12gy - 3.0 * csum2 - C02;
+    double C13 = -2.0 * n12d + n11gy + n12gy + 2.0 * csum2 - C03;
+    double C11 = n02gx - C13 - C12 - n01gx;
+    double u = x - (double) cx, u2 = u * u, u3 = u * u2;
+    double v = y - (double) cy, v2 = v * v, v3 = v * v2;
+    double density = n01d + n01gx * u + n01gy * v + C20 * u2 + C02 * v2 + C30 * u3 + C03 * v3 + C21 * u2 * v + C31 * u3 * v +
+                     C12 * u * v2 + C13 * u * v3 + C11 * u * v;
+    double pressure = density - 1.0;
+    if (pressure > 2.0) pressure = 2.0;
+    double fx = 0.0, fy = 0.0;
+    if (x < 4.0) fx += 1.0 * (4.0 - x);
+    else if (x > (double) (gsx - 5)) fx += 1.0 * ((double) (gsx - 5) - x);
+    if (y < 4.0) fy += 1.0 * (4.0 - y);
+    else if (y > (double) (gsy - 5)) fy += 1.0 * ((double) (gsy - 5) - y);
+    for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) {
+            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
+            if (nx >= gsx || ny >= gsy) continue;
+            size_t idx = (size_t) ny * gsx + nx;
+            double phi = w.px[ii] * w.py[jj];
+            atomicAdd(&NODE(NF_AX, idx), -((w.gx[ii] * w.py[jj]) * pressure) + fx * phi);
+            atomicAdd(&NODE(NF_AY, idx), -((w.px[ii] * w.gy[jj]) * pressure) + fy * phi);
+        }
+}
+
+__global__ void __launch_bounds__(256) k_fluid_node_div(double *__restrict__ nf, size_t ng, int ka, int kb) {
+    size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ng) return;
+    double m = NODE(NF_M, idx);
+    if (m > 0.0) { NODE(ka, idx) /= m; NODE(kb, idx) /= m; }
+}
+
+// attractor pull, shared by the velocity and the move pass (fluidmodel.cpp:385-413 / 505-548)
+__device__ __forceinline__ void pull_towards(double x1, double y1, double x2, double y2, double a, double *ox, double *oy) {
+    double A = fabs(y1 - y2), B = fabs(x1 - x2);
+    double C = sqrt(A * A + B * B);
+    if (a >= C) a = C;
+    *ox = 0.0; *oy = 0.0;
+    if (B <= 0.0) {
+        if (y2 <= y1) *oy -= a; else *oy += a;
+    } else if (C > 0.0) {
+        double dx = (a * B) / C;
+        double dy = (A * dx) / B;
+        if (x1 <= x2) *ox += dx; else *ox -= dx;
+        if (y1 <= y2) *oy += dy; else *oy -= dy;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_fluid_velocity(double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
+                 double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !active[i]) return;
+    size_t ng = (size_t) gsx * gsy;
+    double x = PFI(PF_X), y = PFI(PF_Y);
+    PW w;
+    particle_weights(x, y, w);
+    double cax, cay;
+    pull_towards(x, y, PFI(PF_GX), PFI(PF_GY), 0.03, &cax, &cay);
+    double u = PFI(PF_U), v = PFI(PF_V);
+    for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) {
+            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
+            double ax = 0.0, ay = 0.0;
+            if (nx < gsx && ny < gsy) { size_t idx = (size_t) ny * gsx + nx; ax = NODE(NF_AX, idx); ay = NODE(NF_AY, idx); }
+            double phi = w.px[ii] * w.py[jj];
+            u += phi * (ax + cax);
+            v += phi * (ay + cay);
+        }
+    PFI(PF_U) = u;
+    PFI(PF_V) = v;
+    double mu = 1.0 * u, mv = 1.0 * v;
+    if (!mature[i]) { mu *= 0.0; mv *= 0.0; }
+    for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) {
+            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
+            if (nx >= gsx || ny >= gsy) continue;
+            size_t idx = (size_t) ny * gsx + nx;
+            double phi = w.px[ii] * w.py[jj];
+            atomicAdd(&NODE(NF_U, idx), phi * mu);
+            atomicAdd(&NODE(NF_V, idx), phi * mv);
+        }
+}
+
+__global__ void __launch_bounds__(128)
+k_fluid_g2p(double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
+            const double *__restrict__ nf, uint32_t gsx, uint32_t gsy, double steps_left, double freedom_radius, uint64_t seed, uint64_t stepno) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !active[i]) return;
+    size_t ng = (size_t) gsx * gsy;
+    double x = PFI(PF_X), y = PFI(PF_Y);
+    PW w;
+    particle_weights(x, y, w);
+    double gu = 0.0, gv = 0.0, nR = 0.0, nG = 0.0, nB = 0.0, nA = 0.0, weight = 0.0;
+    for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) {
+            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
+            if (nx >= gsx || ny >= gsy) continue;
+            size_t idx = (size_t) ny * gsx + nx;
+            double phi = w.px[ii] * w.py[jj];
+            gu += phi * NODE(NF_U, idx);
+            gv += phi * NODE(NF_V, idx);
+            double nw = NODE(NF_W, idx);
+            if (nw > 0.0) { weight += nw; nR += NODE(NF_R, idx); nG += NODE(NF_G, idx); nB += NODE(NF_B, idx); nA += NODE(NF_A, idx); }
+        }
+    if (weight > 0.0) {          // fluidmodel.cpp:476-498
+        nR /= weight; nG /= weight; nB /= weight; nA /= weight;
+        if (!mature[i]) { PFI(PF_R) = nR; PFI(PF_G) = nG; PFI(PF_B) = nB; PFI(PF_A) = nA; }
+        else {
+            double wr = fabs(nR - PFI(PF_RI)), wg = fabs(nG - PFI(PF_GI)), wb = fabs(nB - PFI(PF_BI)), wa = fabs(nA - PFI(PF_AI));
+            PFI(PF_R) = (1.0 - wr) * PFI(PF_R) + wr * nR;
+            PFI(PF_G) = (1.0 - wg) * PFI(PF_G) + wg * nG;
+            PFI(PF_B) = (1.0 - wb) * PFI(PF_B) + wb * nB;
+            PFI(PF_A) = (1.0 - wa) * PFI(PF_A) + wa * nA;
+        }
+    }
+    x += gu; y += gv;
+    {   // freedom radius pull (fluidmodel.cpp:505-548)
+        double x2 = PFI(PF_GX), y2 = PFI(PF_GY);
+        double A = fabs(y - y2), B = fabs(x - x2);
+        double C = sqrt(A * A + B * B);
+        double r = freedom_radius * PFI(PF_FREE);
+        if (C > r) {
+            double mx, my;
+            pull_towards(x, y, x2, y2, C - r, &mx, &my);
+            double ww = 1.0 / (steps_left + 1.0);
+            x += mx * ww; y += my * ww;
+        }
+    }
+    double u = PFI(PF_U), v = PFI(PF_V);
+    u += gu - u; v += gv - v;
+    uint64_t rr = rng64(seed, 0xf1u + stepno, i);
+    double j1 = (double) (rr & 0x7fffffffu) / 2147483647.0 * 0.01, j2 = (double) ((rr >> 32) & 0x7fffffffu) / 2147483647.0 * 0.01;
+    if (x < 1.0) { x = 1.0 + j1; u = 0.0; }
+    else if (x > (double) (gsx - 2)) { x = (double) (gsx - 2) - j1; u = 0.0; }
+    if (y < 1.0) { y = 1.0 + j2; v = 0.0; }
+    else if (y > (double) (gsy - 2)) { y = (double) (gsy - 2) - j2; v = 0.0; }
+    PFI(PF_X) = x; PFI(PF_Y) = y; PFI(PF_U) = u; PFI(PF_V) = v;
+}
+
+void engine_fluid_free(Engine *E) {
+    if (!E->fluid) return;
+    Fluid *F = E->fluid;
+    dev_free(F->pf); dev_free(F->active); dev_free(F->mature); dev_free(F->owner); dev_free(F->aux); dev_free(F->nf);
+    delete F;
+    E->fluid = nullptr;
+}
+
+static int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
+    Fluid *F = E->fluid;
+    size_t ng = (size_t) F->gx * F->gy;
+    uint32_t n = F->n;
+    cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream);
+    if (n) {
+        k_fluid_p2g<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy);
+        k_fluid_forces<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, n, F->nf, F->gx, F->gy);
+        k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_AX, NF_AY);
+        k_fluid_velocity<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy);
+        k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_U, NF_V);
+        k_fluid_g2p<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy, (double) steps_left, freedom_radius,
+                                                          E->p.seed, F->step_counter++);
+        E->launches += 6;
+    }
+    return E->check("fluid step") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+} // namespace amx
+
+using namespace amx;
+extern "C" {
+
+int amx_fluid_create(amx_ctx *ctx, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle_count) {
+    if (!ctx || gsize_x < 8 || gsize_y < 8) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    engine_fluid_free(E);
+    Fluid *F = new Fluid();
+    F->gx = gsize_x; F->gy = gsize_y; F->n = particle_count;
+    size_t ng = (size_t) gsize_x * gsize_y, n = particle_count;
+    E->fluid = F;
+    if (!dev_alloc(E, (void **) &F->pf, n * PF_COUNT * 8, "fluid particles") || !dev_alloc(E, (void **) &F->active, n, "fluid active") ||
+        !dev_alloc(E, (void **) &F->mature, n, "fluid mature") || !dev_alloc(E, (void **) &F->owner, n, "fluid owner") ||
+        !dev_alloc(E, (void **) &F->aux, n * 3 * 8, "fluid aux") || !dev_alloc(E, (void **) &F->nf, ng * NF_COUNT * 8, "fluid nodes")) {
+        engine_fluid_free(E);
+        return AMX_ERR_NOMEM;
+    }
+    cudaMemsetAsync(F->pf, 0, n * PF_COUNT * 8 + 0, E->stream);
+    cudaMemsetAsync(F->active, 0, n, E->stream);
+    cudaMemsetAsync(F->mature, 0, n, E->stream);
+    cudaMemsetAsync(F->owner, 0, n, E->stream);
+    cudaMemsetAsync(F->aux, 0, n * 3 * 8, E->stream);
+    cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream);
+    return E->fail(cudaStreamSynchronize(E->stream), "fluid create") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+// record field -> SoA slot
+static const int rec2pf[17] = {PF_X, PF_Y, PF_U, PF_V, PF_GX, PF_GY, PF_FREE, -1, -1, PF_RI, PF_GI, PF_BI, PF_AI, PF_R, PF_G, PF_B, PF_A};
+
+int amx_fluid_set_particles(amx_ctx *ctx, uint32_t n, const double *rec) {
+    if (!ctx || !ctx->e.fluid || !rec || n != ctx->e.fluid->n) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    Fluid *F = E->fluid;
+    std::vector<double> soa((size_t) n * PF_COUNT), aux((size_t) n * 3);
+    std::vector<uint8_t> act(n), mat(n), own(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const double *r = rec + (size_t) i * AMX_FP_STRIDE;
+        for (int k = 0; k < 17; ++k) if (rec2pf[k] >= 0) soa[(size_t) rec2pf[k] * n + i] = r[k];
+        soa[(size_t) PF_STRENGTH * n + i] = r[17];
+        act[i] = r[7] != 0.0; mat[i] = r[8] != 0.0; own[i] = r[18] != 0.0;
+        aux[i] = r[19]; aux[(size_t) n + i] = r[20]; aux[(size_t) 2 * n + i] = r[21];
+    }
+    cudaMemcpyAsync(F->pf, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice, E->stream);
+    cudaMemcpyAsync(F->active, act.data(), n, cudaMemcpyHostToDevice, E->stream);
+    cudaMemcpyAsync(F->mature, mat.data(), n, cudaMemcpyHostToDevice, E->stream);
+    cudaMemcpyAsync(F->owner, own.data(), n, cudaMemcpyHostToDevice, E->stream);
+    cudaMemcpyAsync(F->aux, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, E->stream);
+    return E->fail(cudaStreamSynchronize(E->stream), "fluid set") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+int amx_fluid_get_particles(amx_ctx *ctx, uint32_t n, double *rec) {
+    if (!ctx || !ctx->e.fluid || !rec || n != ctx->e.fluid->n) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    Fluid *F = E->fluid;
+    std::vector<double> soa((size_t) n * PF_COUNT), aux((size_t) n * 3);
+    std::vector<uint8_t> act(n), mat(n), own(n);
+    cudaMemcpyAsync(soa.data(), F->pf, soa.size() * 8, cudaMemcpyDeviceToHost, E->stream);
+    cudaMemcpyAsync(act.data(), F->active, n, cudaMemcpyDeviceToHost, E->stream);
+    cudaMemcpyAsync(mat.data(), F->mature, n, cudaMemcpyDeviceToHost, E->stream);
+    cudaMemcpyAsync(own.data(), F->owner, n, cudaMemcpyDeviceToHost, E->stream);
+    cudaMemcpyAsync(aux.data(), F->aux, aux.size() * 8, cudaMemcpyDeviceToHost, E->stream);
+    if (E->fail(cudaStreamSynchronize(E->stream), "fluid get")) return AMX_ERR_CUDA;
+    for (uint32_t i = 0; i < n; ++i) {
+        double *r = rec + (size_t) i * AMX_FP_STRIDE;
+        for (int k = 0; k < 17; ++k) if (rec2pf[k] >= 0) r[k] = soa[(size_t) rec2pf[k] * n + i];
+        r[17] = soa[(size_t) PF_STRENGTH * n + i];
+        r[7] = act[i]; r[8] = mat[i]; r[18] = own[i];
+        r[19] = aux[i]; r[20] = aux[(size_t) n + i]; r[21] = aux[(size_t) 2 * n + i];
+        double x = r[0], y = r[1];
+        r[22] = (double) (unsigned) (int) (x - 0.5); r[23] = (double) (unsigned) (int) (y - 0.5);
+    }
+    return AMX_OK;
+}
+
+int amx_fluid_step(amx_ctx *ctx, uint64_t steps_left, double freedom_radius, double t) {
+    (void) t;   // morph_time is unused by the reference step as well (fluidmodel.cpp:165)
+    if (!ctx || !ctx->e.fluid) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    return fluid_step(&ctx->e, steps_left, freedom_radius);
+}
+
+int amx_fluid_get_nodes(amx_ctx *ctx, double *out) {
+    if (!ctx || !ctx->e.fluid || !out) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    Fluid *F = E->fluid;
+    size_t ng = (size_t) F->gx * F->gy;
+    std::vector<double> soa(ng * NF_COUNT);
+    if (E->fail(cudaMemcpyAsync(soa.data(), F->nf, soa.size() * 8, cudaMemcpyDeviceToHost, E->stream), "nodes D2H") ||
+        E->fail(cudaStreamSynchronize(E->stream), "nodes"))
+        return AMX_ERR_CUDA;
+    for (size_t idx = 0; idx < ng; ++idx) {
+        double *o = out + idx * 13;
+        for (int k = 0; k < 13; ++k) o[k] = soa[(size_t) k * ng + idx];
+        double w = o[12];
+        if (w > 0.0) { o[8] /= w; o[9] /= w; o[10] /= w; o[11] /= w; }   // report the running mean like the reference node
+    }
+    return AMX_OK;
+}
+
+}

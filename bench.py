@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- atom-swap proposals/s + morph frames/s at 1024^2 RGBA (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 1024] [--frames 64]
+
+Workload (BASELINE.json configs[1]): synthetic 1024x1024 RGBA, 2 key frames (full square -> disc),
+1 048 576 atoms, spline motion + cosine fading, 64 output frames.
+
+One STEP = one pass of the hot path over one batch:
+    render phase : the 64 output frames of the morph (k_splat / k_resolve / k_composite per frame)
+    swap phase   : SWAP_ROUNDS rounds of disjoint pair-swap proposals on the 1M-atom chain
+Both phases are timed separately with CUDA events on the engine's stream, inputs resident in HBM.
+`value` is the render throughput (frames/s); the swap throughput and its roofline are reported in
+the `swap` object of the same JSON line.  `e2e` is the same frames/s measured through the C-ABI with
+HOST buffers: per step the trajectory table is uploaded (H2D), the frames are rendered and copied
+back (D2H) inside the timed region.
+
+N > 1 (torchrun): output frames are sharded by frame range, swap rounds by atom range; the timed
+region is bracketed by a barrier and the time is the max over ranks (weak scaling: every rank
+renders `--frames` frames and proposes SWAP_ROUNDS rounds on its slice).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWAP_ROUNDS = 64          # rounds per step; one round = W/2 proposals on a power-of-two chain
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def build_reference(size, seed_images, chains, blobs_per_frame, params):
+    from oracle import amref
+    m = amref.RefMorph(**params)
+    for k, im in enumerate(seed_images):
+        m.add_image(k, im)
+    m.set_resolution(size, size)
+    for k, blobs in enumerate(blobs_per_frame):
+        m.import_blobs(k, blobs)
+    for c in chains:
+        m.import_chain(c["key"], c["words"], c["max_surface"])
+    m.finish_import()
+    return m
+
+
+def reference_tables(size, images):
+    """Chain table + blobs for the reference arm WITHOUT the GPU: the single-blob C2 scene has a closed
+    form (row-major ranks; duplicates follow init_morph's rule with a numpy shuffle)."""
+    rng = np.random.default_rng(4321)
+    cols = []
+    blobs = []
+    W = 0
+    for im in images:
+        W = max(W, int((im[..., 3] != 0).sum()))
+    for im in images:
+        ys, xs = np.nonzero(im[..., 3] != 0)
+        words = xs.astype(np.uint64) | (ys.astype(np.uint64) << np.uint64(16)) | (np.uint64(3) << np.uint64(48))
+        n = len(words)
+        if n < W:
+            perm = rng.permutation(n)
+            src = perm[np.arange(n, W) % n]
+            fr = rng.integers(0, 256, size=(W - n, 2)).astype(np.uint64)
+            dup = (words[src] & np.uint64(0xffffffff)) | (fr[:, 0] << np.uint64(32)) | (fr[:, 1] << np.uint64(40)) | (np.uint64(1) << np.uint64(48))
+            words = np.concatenate([words, dup])
+        cols.append(words)
+        c = im[ys, xs].astype(np.float64) / 255.0
+        blobs.append([dict(group=0, stats=np.array([xs.mean(), ys.mean(), c[:, 0].mean(), c[:, 1].mean(), c[:, 2].mean(), c[:, 3].mean()]),
+                           surface=(ys.astype(np.uint64) * np.uint64(65536) + xs.astype(np.uint64)))])
+    return [dict(key=0, words=np.stack(cols), max_surface=W)], blobs
+
+
+def cpu_reference_numbers(m, frames, frame_budget_s=25.0, morph_steps=16):
+    """Times the reference's own CPU path: get_pixels(t) on one thread (the reference renderer is
+    single-threaded) and thread::morph() with all host threads."""
+    from oracle import amref
+    cores = amref.hardware_concurrency()
+    # render: frames until the budget is used (at least one)
+    t_used, n = 0.0, 0
+    while n < frames and (n == 0 or t_used < frame_budget_s):
+        dt, _ = m.time_render(n / float(frames))
+        t_used += dt
+        n += 1
+    fps = n / t_used
+    m.set(threads=cores, cycle_length=100000)
+    m.sync()
+    dt = m.time_morph_steps(morph_steps)
+    pps = morph_steps * max(1, cores) * 100000 / dt
+    m.sync()
+    return dict(fps=fps, frames=n, render_s=t_used, pps=pps, cores=int(cores), morph_s=dt)
+
+
+def run_reference(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    from atomorph_b200 import scenes
+    from oracle import amref
+    params = dict(seed=1, motion=amref.SPLINE, fading=amref.COSINE)
+    images = scenes.square_to_disc(args.size)
+    chains, blobs = reference_tables(args.size, images)
+    m = build_reference(args.size, images, chains, blobs, params)
+    cores = amref.hardware_concurrency()
+    # swap leg (all host threads)
+    m.set(threads=cores, cycle_length=100000)
+    m.sync()
+    sw = m.time_morph_steps(16)
+    pps = 16 * max(1, cores) * 100000 / sw
+    m.sync()
+    # render leg: each step = ONE frame of the 64-frame morph (bounded sample; ~10-15 s per frame)
+    warm = min(args.warmup, 1)
+    for i in range(warm):
+        m.time_render(0.5)
+    t = 0.0
+    for i in range(args.steps):
+        dt, _ = m.time_render((i % args.frames) / float(args.frames))
+        t += dt
+    fps = args.steps / t
+    line = {
+        "impl": "reference", "metric": "morph frames/s at %d^2 RGBA (swap proposals/s in 'swap')" % args.size,
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+        "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 synthetic %dx%d RGBA, 2 key frames, %d atoms, spline+cosine, %d frames" %
+                   (args.size, args.size, chains[0]["words"].shape[1], args.frames), "step": "one frame (bounded sample)"},
+        "swap": {"value": pps, "unit": "proposals/s", "cores": int(cores)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                         "sample": "%d single frames of the %d-frame morph via am::morph::get_pixels (single-threaded renderer); "
+                                   "swap: 16 morph steps x %d threads x 100000 proposals" % (args.steps, args.frames, cores)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    from atomorph_b200 import engine as eng
+    from atomorph_b200 import scenes
+
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peak, peak_kind = measured_peak()
+
+    size, F = args.size, args.frames
+    params = dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=100000)
+    images = scenes.square_to_disc(size)
+    e = eng.Engine(local_rank, **params)
+    stream = torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    e.load_images(images)
+    e.step(8)                                     # blobify -> unify -> match -> init chains (all on device)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    info = e.chains() if size <= 256 else None
+    A = e.table_device_ptr(0)[1]
+    P = size * size
+    e.swap_rounds(256, want_stats=False)          # leave the trivial initial table behind
+    e.render_prepare()
+
+    # weak scaling: rank r renders frames [r*F, (r+1)*F) of an (F*world)-frame morph
+    total_frames = F * world
+    times = np.array([(rank * F + f) / float(total_frames) for f in range(F)])
+    out = torch.empty((F, size, size), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def render_step():
+        e.render_into(times, out.data_ptr(), True)
+
+    def swap_step():
+        e.swap_rounds(SWAP_ROUNDS, want_stats=False)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()                          # L2 flush between timed iterations (outside the event pair)
+            torch.cuda.synchronize()
+            e.timer_start()
+            fn()
+            tot += e.timer_stop()
+        barrier()
+        return tot
+
+    sampler = ClockSampler(local_rank)
+    launches0 = e.launch_count()
+    sampler.start()
+    ms_render = timed(render_step, args.steps, args.warmup)
+    st0 = e.swap_stats()
+    ms_swap = timed(swap_step, args.steps, args.warmup)
+    st1 = e.swap_stats()
+    clocks = sampler.stop()
+    launches = e.launch_count() - launches0
+    proposals = int(st1[0] - st0[0]) * args.steps // (args.steps + args.warmup)
+
+    # e2e through the C-ABI with host buffers: upload the table (H2D), render, copy frames back (D2H)
+    chain_words = e.chains()
+    host_out = torch.empty((F, size, size), dtype=torch.int32).pin_memory()
+    h2d = sum(c["words"].nbytes for c in chain_words)
+    d2h = F * P * 4
+
+    def e2e_step():
+        e.import_chains(chain_words)
+        e.render_into(times, host_out.data_ptr(), False)
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    s_e2e = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_render, ms_swap, s_e2e, float(proposals)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_render, ms_swap, s_e2e = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        proposals = int(tsum[3])
+    fps = world * F * args.steps / (ms_render / 1000.0)
+    pps = proposals / (ms_swap / 1000.0)
+    fps_e2e = world * F * e2e_steps / s_e2e
+
+    render_bytes = A * 24 + P * 4                  # linear or h <= 3 -> 24 B/atom + 4 B/pixel
+    swap_bytes = 32                                # h = 2: 4 distinct key points per proposal
+    r_ach = render_bytes * (F * args.steps) / (ms_render / 1000.0) / 1e9
+    s_ach = swap_bytes * (proposals / world) / (ms_swap / 1000.0) / 1e9
+
+    line = {
+        "metric": "morph frames/s at %d^2 RGBA (swap proposals/s in 'swap')" % size,
+        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_render / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 synthetic %dx%d RGBA, 2 key frames, %d atoms, spline+cosine, %d frames per GPU" % (size, size, A, F),
+                   "l2": "256 MB buffer written between timed steps", "step": "render %d frames; swap: %d rounds" % (F, SWAP_ROUNDS),
+                   "parallelism": "frame-range x%d" % world},
+        "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None,
+                     "peak_kind": peak_kind, "kernel": "k_splat+k_resolve+k_composite (per frame)",
+                     "bytes_per_unit": render_bytes, "unit_name": "frame"},
+        "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps, "rounds_per_step": SWAP_ROUNDS,
+                 "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
+                              "traffic": None, "kernel": "k_swap_single", "bytes_per_unit": swap_bytes, "unit_name": "proposal",
+                              "note": "16 MiB table is L2-resident: algorithmic GB/s may exceed DRAM GB/s"}},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import amref
+            if amref.available():
+                blobs = []
+                for i in range(len(images)):
+                    ys, xs = np.nonzero(images[i][..., 3] != 0)
+                    labels, stats, meta = e.export_blobs(i)
+                    blobs.append([dict(group=int(meta[0, 0]), stats=stats[0],
+                                       surface=(ys.astype(np.uint64) * np.uint64(65536) + xs.astype(np.uint64)))])
+                m = build_reference(size, images, chain_words, blobs, dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE))
+                cpu = cpu_reference_numbers(m, F)
+                line["cpu_baseline"] = {"value": cpu["fps"], "unit": "frames/s", "cores": 1, "kind": "reference",
+                                        "sample": "%d of %d frames via am::morph::get_pixels on the same chain table (single-threaded renderer, %.1f s)"
+                                                  % (cpu["frames"], F, cpu["render_s"]),
+                                        "swap": {"value": cpu["pps"], "unit": "proposals/s", "cores": cpu["cores"],
+                                                 "sample": "16 thread::morph steps x %d threads x 100000 proposals (%.1f s)" % (cpu["cores"], cpu["morph_s"])}}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        except Exception as ex:  # the baseline must never take the GPU line down
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

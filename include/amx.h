@@ -1,0 +1,149 @@
+/*
+ * amx.h -- C-ABI of libatomorph_b200.so: the sm_100a device engine underneath the am::morph
+ * facade (include/atomorph/morph.h).  Plain C types, caller-owned host buffers, int status
+ * codes, no exceptions, NO CPU FALLBACK: every entry point needs a CUDA device and fails with
+ * AMX_ERR_CUDA when there is none.
+ *
+ * Each entry point names the reference interface it replaces (file:line under the reference
+ * tree 1Hyena/atomorph).  A cgo / JNI / ctypes binding for this path would bind exactly these
+ * symbols; INTEGRATION.md shows the stubs.
+ *
+ * Conventions
+ *   - colours are packed little-endian  r | g<<8 | b<<16 | a<<24  (am::color, color.h:7-12)
+ *   - key points are u64 words  x | y<<16 | x_fract<<32 | y_fract<<40 | flags<<48
+ *     (am::point, atomorph.h:275-284); chain tables are COLUMN-major: word[j*width + x] is
+ *     atom x at key frame j  (the reference's points[x][j], atomorph.h:286-298)
+ *   - images are row-major, `canvas_w * canvas_h` for key-frame data, `width * height` for
+ *     rendered output
+ *   - frame INDEX = rank of the frame key in ascending key order (am::frame::index)
+ */
+#ifndef AMX_H
+#define AMX_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "amx_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amx_ctx amx_ctx;
+
+enum amx_status {
+    AMX_OK = 0,
+    AMX_ERR_CUDA = 1,      /* no device / CUDA runtime error (see amx_last_error)        */
+    AMX_ERR_ARG = 2,       /* bad argument                                                */
+    AMX_ERR_STATE = 3,     /* call not valid in the current pipeline state                */
+    AMX_ERR_NOMEM = 4,     /* device or host allocation failed                            */
+    AMX_ERR_BUSY = 5
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* replaces am::morph::morph() / ~morph() / clear()  (morph.cpp:9-50) on the device side    */
+int  amx_create(amx_ctx **out, int device);
+void amx_destroy(amx_ctx *ctx);
+const char *amx_last_error(amx_ctx *ctx);
+const char *amx_version(void);                                   /* am::get_version, atomorph.cpp:1013 */
+/* Use an externally owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream. */
+int  amx_set_stream(amx_ctx *ctx, void *cuda_stream);
+int  amx_device_sync(amx_ctx *ctx);
+
+/* ---- parameters: one id per setter, morph.h:52-76, pushed like synchronize() morph.cpp:105-120 */
+int  amx_set_param(amx_ctx *ctx, int id, double value);
+double amx_get_param(amx_ctx *ctx, int id);
+
+/* ---- ingest (row a-I): replaces the worker-side set_frame, thread.cpp:89-111, and the
+ *      RGB->HSP store / HSP->RGB fetch round trip of add_pixel / get_pixel (morph.cpp:298-301, 378-392).
+ * amx_reset drops frames, blobs, chains (thread::clear, thread.cpp:36-81).
+ * amx_set_canvas: width/height = set_resolution (morph.cpp:1517-1520); canvas covers every pixel
+ * position; bbox = bbox_x1,y1,x2,y2 (morph.cpp:313-316).
+ * amx_upload_frame: rgba = RAW input colours (as passed to add_pixel), present[i] != 0 where a
+ * pixel was added; means = the facade's running means x,y,r,g,b,a (morph.cpp:318-334). */
+int  amx_reset(amx_ctx *ctx);
+int  amx_set_canvas(amx_ctx *ctx, uint32_t width, uint32_t height, uint32_t canvas_w, uint32_t canvas_h, const uint16_t bbox[4]);
+int  amx_set_frame_count(amx_ctx *ctx, uint32_t nframes, const uint64_t *keys);
+int  amx_upload_frame(amx_ctx *ctx, uint32_t index, const uint32_t *rgba, const uint8_t *present, const double means[6]);
+/* device pointer variant (inputs already resident in HBM) */
+int  amx_upload_frame_device(amx_ctx *ctx, uint32_t index, const uint32_t *d_rgba, const uint8_t *d_present, const double means[6]);
+/* fetch colours after the store/fetch round trip (am::morph::get_pixel for every canvas position) */
+int  amx_download_fetch(amx_ctx *ctx, uint32_t index, uint32_t *rgba_out);
+int  amx_download_stored(amx_ctx *ctx, uint32_t index, uint32_t *rgba_out);
+
+/* ---- pipeline state machine (row a-B..a-M): replaces thread::step, thread.cpp:139-171 ------- */
+/* nsteps reference-equivalent steps: blob detection completes in one step; one matching step =
+ * one parallel round of disjoint blob swaps; one morphing step = max(1,threads)*cycle_length atom
+ * swap proposals on one chain, chains served round-robin (thread.cpp:1043-1064). */
+int  amx_step(amx_ctx *ctx, uint64_t nsteps);
+int  amx_next_state(amx_ctx *ctx);                               /* thread::next_state, thread.h:17 */
+unsigned amx_get_state(amx_ctx *ctx);                            /* thread::get_state            */
+double amx_get_energy(amx_ctx *ctx);                             /* thread::get_energy, thread.cpp:1176-1185 (true cost, not the reference's uninitialised sum) */
+
+/* ---- K2 blob segmentation (row a-B1): thread::blobify_frame, thread.cpp:225-412 ------------- */
+int  amx_blobify(amx_ctx *ctx);
+int  amx_blob_count(amx_ctx *ctx, uint32_t index, uint32_t *count);
+/* labels_out[canvas] = blob index in the frame's blob vector (-1 = no pixel);
+ * stats_out[6*b..] = x,y,r,g,b,a ; meta_out[2*b..] = group, size */
+int  amx_export_blobs(amx_ctx *ctx, uint32_t index, int32_t *labels_out, double *stats_out, uint64_t *meta_out);
+int  amx_import_blobs(amx_ctx *ctx, uint32_t index, uint32_t nblobs, const int32_t *labels, const double *stats, const uint64_t *groups);
+
+/* ---- K3 blob matching (row a-B3): thread::match, thread.cpp:598-738; blob_distance 1151-1174 -- */
+int  amx_match_init(amx_ctx *ctx);
+int  amx_match_rounds(amx_ctx *ctx, uint64_t rounds);
+int  amx_match_energy(amx_ctx *ctx, double *energy);             /* thread::get_energy(blob***), thread.cpp:1087-1107 */
+
+/* ---- K4 chain build (row a-C): thread::init_morph, thread.cpp:740-891 ------------------------ */
+int  amx_init_chains(amx_ctx *ctx);
+int  amx_chain_count(amx_ctx *ctx, uint32_t *count);
+/* info4 = key(group), width, height, max_surface */
+int  amx_chain_info(amx_ctx *ctx, uint32_t chain, uint64_t info4[4]);
+int  amx_export_chain(amx_ctx *ctx, uint32_t chain, uint64_t *words_out);
+/* Replace ALL chains: keys[n], widths[n], max_surface[n], height, words = chains concatenated, each column-major */
+int  amx_import_chains(amx_ctx *ctx, uint32_t nchains, const uint64_t *keys, const uint64_t *widths,
+                       const uint64_t *max_surface, uint32_t height, const uint64_t *words);
+/* device access for collectives (NCCL all-gather of table columns): pointer to column j of the
+ * concatenated table (total_atoms words) */
+int  amx_table_device_ptr(amx_ctx *ctx, uint32_t column, void **d_ptr, uint64_t *total_atoms);
+
+/* ---- K1 pair-swap optimal transport (row a-M): morph_asynch, thread.cpp:990-1041 -------------- */
+/* `rounds` rounds of disjoint pairings on column `column` (or a counter-RNG chosen column when
+ * column < 0) of chain `chain` (or all chains when chain < 0).  stats3 += proposals, accepted, gain. */
+int  amx_swap_rounds(amx_ctx *ctx, int32_t chain, int32_t column, uint64_t rounds, uint64_t stats3[3]);
+int  amx_swap_stats(amx_ctx *ctx, uint64_t stats3[3]);           /* cumulative since init / import  */
+int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_energy(chain*), thread.cpp:1109-1125, summed over chains */
+
+/* ---- K6 renderer (row a-R): morph::get_pixels / draw_atoms, morph.cpp:452-678, 1302-1421 ------- */
+/* Refresh the per-atom render inputs from the chain table (the device analogue of the chain /
+ * spline mirror of synchronize(), morph.cpp:174-205). */
+int  amx_render_prepare(amx_ctx *ctx);
+/* n frames at times t[i] -> out[i*width*height ...] packed RGBA.  out_is_device: out is a device pointer. */
+int  amx_render(amx_ctx *ctx, const double *times, uint32_t n, uint32_t *out, int out_is_device);
+/* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
+ * returns count via *n (pixels in reference emission order), -1 in *n when the blob index is out of range */
+int  amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_t *xy_out, uint32_t *rgba_out, int64_t *n, uint64_t *group);
+/* background cross-dissolve image at time t (morph::get_background for every pixel, morph.cpp:1431-1465) */
+int  amx_background(amx_ctx *ctx, double t, uint32_t *out, int out_is_device);
+
+/* ---- K5 fluid (row a-F): FluidModel::step, fluidmodel.cpp:165-580 ------------------------------ */
+/* particle record = AMX_FP_STRIDE doubles:
+ * 0 x 1 y 2 u 3 v 4 gravity_x 5 gravity_y 6 freedom_r 7 active 8 mature 9 R 10 G 11 B 12 A 13 r 14 g 15 b 16 a
+ * 17 strength 18 source_owner 19 frame_key 20 source_pos 21 destination_pos 22 cx 23 cy */
+#define AMX_FP_STRIDE 24
+int  amx_fluid_create(amx_ctx *ctx, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle_count);
+int  amx_fluid_set_particles(amx_ctx *ctx, uint32_t n, const double *records);
+int  amx_fluid_get_particles(amx_ctx *ctx, uint32_t n, double *records);
+int  amx_fluid_step(amx_ctx *ctx, uint64_t steps_left, double freedom_radius, double t);
+/* node record = 13 doubles m d gx gy u v ax ay r g b a weight ; out[(j*gsize_x+i)*13+k] */
+int  amx_fluid_get_nodes(amx_ctx *ctx, double *out);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+/* number of kernels this context launched since creation (bench.py "gpu_launches") */
+uint64_t amx_launch_count(amx_ctx *ctx);
+/* bracket a region with CUDA events on the engine's stream; amx_timer_stop returns milliseconds */
+int  amx_timer_start(amx_ctx *ctx);
+int  amx_timer_stop(amx_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

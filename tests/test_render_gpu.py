@@ -1,0 +1,69 @@
+"""K6 parity: rendered frames vs the reference run on the same inputs, fed the reference's own
+correspondence / trajectory tables (SURVEY.md row a-R).  Bar: <= 1 LSB per 8-bit channel, and the
+differing pixels (exact .5 ties of the double sums) stay a small fraction."""
+import numpy as np
+import pytest
+
+from atomorph_b200 import engine as eng
+from atomorph_b200 import scenes
+from helpers import build_ref, diff_stats, engine_from_ref
+
+pytestmark = pytest.mark.gpu
+
+TIMES = [0.0, 0.1, 0.25, 1.0 / 3.0, 0.5, 0.61, 0.75, 0.999]
+
+CASES = [
+    # name, scene, params
+    ("linear_linear_k2", lambda: scenes.ellipses(48, 2, seed=7), dict(motion=eng.LINEAR, fading=eng.LINEAR)),
+    ("spline_cosine_k2_d2", lambda: scenes.ellipses(48, 2, seed=8), dict(motion=eng.SPLINE, fading=eng.COSINE, density=2)),
+    ("spline_cosine_k4", lambda: scenes.ellipses(48, 4, seed=9), dict(motion=eng.SPLINE, fading=eng.COSINE)),
+    ("linear_perlin_k3", lambda: scenes.ellipses(40, 3, seed=10, alpha_noise=True), dict(motion=eng.LINEAR, fading=eng.PERLIN)),
+    ("spline_perlin_feather", lambda: scenes.ellipses(40, 3, seed=11), dict(motion=eng.SPLINE, fading=eng.PERLIN, feather=3)),
+    ("none_none_rgb", lambda: scenes.ellipses(32, 2, seed=12), dict(motion=eng.NONE, fading=eng.NONE, blob_delimiter=eng.RGB)),
+    ("cloud_bg", lambda: scenes.random_cloud(40, 3, seed=3), dict(motion=eng.LINEAR, fading=eng.COSINE, keep_background=1, feather=2, density=2)),
+    ("cloud_bg_perlin", lambda: scenes.random_cloud(32, 2, seed=4), dict(motion=eng.SPLINE, fading=eng.PERLIN, keep_background=1)),
+]
+
+
+@pytest.mark.parametrize("name,scene,params", CASES, ids=[c[0] for c in CASES])
+def test_render_matches_reference(reflib, name, scene, params):
+    images = scene()
+    m = build_ref(reflib, images, seed=1, **params)
+    m.set(cycle_length=500)
+    m.sync()
+    m.iterate(40)          # some matching so the table is not the trivial initial one
+    m.sync()
+    e = engine_from_ref(m, images, seed=1, **params)
+    assert abs(e.cost() - m.true_cost()) == 0
+    total = ndiff = 0
+    for t in TIMES:
+        ref = m.render(t)
+        got = e.render([t])[0]
+        n, mx = diff_stats(ref, got)
+        assert mx <= 1, "%s t=%g: channel diff %d" % (name, t, mx)
+        ndiff += n
+        total += ref.size
+    assert ndiff <= 0.01 * total, "%s: %d of %d pixels differ" % (name, ndiff, total)
+
+
+def test_render_multi_blob_order_and_show_blobs(reflib):
+    images = scenes.rect_blobs(64, 12, frames=2, seed=5, min_side=4, max_side=14)
+    for show in (eng.TEXTURE, eng.AVERAGE, eng.DISTINCT):
+        params = dict(motion=eng.LINEAR, fading=eng.LINEAR, show_blobs=show, feather=1)
+        m = build_ref(reflib, images, seed=2, match_steps=200, **params)
+        e = engine_from_ref(m, images, seed=2, **params)
+        for t in (0.0, 0.3, 0.5, 0.8):
+            n, mx = diff_stats(m.render(t), e.render([t])[0])
+            assert mx <= 1
+            assert n <= 0.01 * 64 * 64
+
+
+def test_batch_equals_single(reflib):
+    images = scenes.ellipses(32, 2, seed=21)
+    params = dict(motion=eng.SPLINE, fading=eng.COSINE)
+    m = build_ref(reflib, images, seed=1, **params)
+    e = engine_from_ref(m, images, seed=1, **params)
+    ts = [m.get_time(f, 16) for f in range(16)]
+    batch = e.render(ts)
+    for i, t in enumerate(ts):
+        assert np.array_equal(batch[i], e.render([t])[0])

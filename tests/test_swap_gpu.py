@@ -1,0 +1,75 @@
+"""K1 parity: the parallel pair-swap matcher against the reference's serial stochastic matcher
+(SURVEY.md row a-M).  The serial RNG stream cannot be reproduced in parallel, so the criterion is
+the transport cost (recomputed from the table, reference metric point_distance)."""
+import numpy as np
+import pytest
+
+from atomorph_b200 import engine as eng
+from atomorph_b200 import scenes
+from helpers import build_ref, engine_from_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows_are_permutation(before, after):
+    for j in range(before.shape[0]):
+        if not np.array_equal(np.sort(before[j]), np.sort(after[j])):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("frames", [2, 4])
+def test_cost_reaches_reference(reflib, frames):
+    images = scenes.ellipses(40, frames, seed=30 + frames)
+    m = build_ref(reflib, images, seed=1)
+    e = engine_from_ref(m, images, seed=1)
+    before = e.chains()[0]["words"].copy()
+    W = before.shape[1]
+    c0 = e.cost()
+    assert c0 == m.true_cost()
+    # reference: 2000 proposals per atom
+    m.set(cycle_length=W)
+    m.sync()
+    m.iterate(2000)
+    m.sync()
+    c_ref = m.true_cost()
+    # engine: same number of proposals
+    st0 = e.swap_stats()
+    rounds = 0
+    while int(e.swap_stats()[0] - st0[0]) < 2000 * W:
+        e.swap_rounds(200)
+        rounds += 200
+        assert rounds < 200000
+    st = e.swap_stats()
+    c_gpu = e.cost()
+    after = e.chains()[0]["words"]
+    assert _rows_are_permutation(before, after), "a swap round lost or duplicated a key point"
+    # the gain bookkeeping is exact integer arithmetic
+    assert c0 - c_gpu == float(int(st[2] - st0[2]))
+    assert c_gpu <= 1.01 * c_ref, (c_gpu, c_ref)
+
+
+def test_step_counts_proposals(reflib):
+    images = scenes.ellipses(32, 2, seed=40)
+    m = build_ref(reflib, images, seed=1)
+    e = engine_from_ref(m, images, seed=1, threads=0, cycle_length=5000)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    st0 = e.swap_stats()
+    e.step(10)
+    st = e.swap_stats()
+    assert int(st[0] - st0[0]) >= 10 * 5000
+    assert int(st[0] - st0[0]) <= 10 * 5000 + 2 * e.chains()[0]["width"]
+
+
+def test_multi_chain_sweep(reflib):
+    images = scenes.rect_blobs(64, 10, frames=2, seed=6, min_side=5, max_side=14)
+    m = build_ref(reflib, images, seed=3, match_steps=100)
+    e = engine_from_ref(m, images, seed=3)
+    befores = [c["words"].copy() for c in e.chains()]
+    c0 = e.cost()
+    assert c0 == m.true_cost()
+    e.swap_rounds(500)
+    c1 = e.cost()
+    assert c1 <= c0
+    for b, a in zip(befores, e.chains()):
+        assert _rows_are_permutation(b, a["words"])
