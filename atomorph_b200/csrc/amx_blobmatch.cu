@@ -9,9 +9,11 @@
  * Here one ROUND proposes a perfect matching of the slots of one frame (slot l with l XOR m,
  * counter-RNG mask m), all proposals of a round evaluated in parallel -- the same disjoint-pair
  * scheme as the atom matcher (amx_swap.cu).  Costs are the reference's double formula on the
- * same truncated/rounded blob features.  The search is pure descent (c1 >= c2 accepted); the
- * reference's periodic forced uphill move ("degeneration") is not reproduced, its best-so-far
- * bookkeeping therefore coincides with the current map.
+ * same truncated/rounded blob features.  The search is pure descent (c1 >= c2 accepted) run as
+ * 296 independent REPLICAS (one CTA each, different proposal streams, same start); the lowest
+ * energy replica wins.  The reference's periodic forced uphill move ("degeneration") is not
+ * reproduced; best-of-replicas plays its role of escaping poor 2-swap local optima, and the
+ * best-so-far bookkeeping coincides with the current map.
  */
 #include <algorithm>
 #include <cmath>
@@ -34,13 +36,9 @@ __device__ __forceinline__ double blob_dist(const double *a, const double *b, co
     return (w.xy * pix + w.rgba * col + w.size * siz);
 }
 
-__global__ void __launch_bounds__(256)
-k_match_round(uint32_t *__restrict__ bmap, const double *__restrict__ feat, uint32_t W, uint32_t H, uint32_t y, uint32_t m, BW w,
-              unsigned long long *__restrict__ accepted) {
-    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= W) return;
-    uint32_t r = l ^ m;
-    if (r <= l || r >= W) return;
+// shared by the round kernel: evaluate the swap of slots l, r of frame y on map `bmap`
+__device__ __forceinline__ void match_propose(uint32_t *bmap, const double *__restrict__ feat, uint32_t W, uint32_t H, uint32_t y,
+                                              uint32_t l, uint32_t r, const BW &w) {
     uint32_t yn = (y + 1) % H, yp = (y + H - 1) % H;
     const double *fy = feat + (size_t) y * W * 4, *fn = feat + (size_t) yn * W * 4, *fp = feat + (size_t) yp * W * 4;
     uint32_t b1 = bmap[(size_t) y * W + l], b2 = bmap[(size_t) y * W + r];
@@ -56,8 +54,43 @@ k_match_round(uint32_t *__restrict__ bmap, const double *__restrict__ feat, uint
     if (c1 >= c2) {
         bmap[(size_t) y * W + l] = b2;
         bmap[(size_t) y * W + r] = b1;
-        if (c1 > c2) atomicAdd(accepted, 1ull);
     }
+}
+
+// One CTA = one REPLICA of the descent: all replicas start from the current map and follow different
+// counter-RNG proposal streams for `rounds` rounds (block barrier between rounds); the host keeps the
+// replica with the lowest energy.  The reference runs a single serial descent; best-of-R is the
+// massively parallel way to spend the same wall time.
+__global__ void __launch_bounds__(256)
+k_match_replicas(const uint32_t *__restrict__ bmap0, uint32_t *__restrict__ rmaps, const double *__restrict__ feat, uint32_t W, uint32_t H,
+                 unsigned kbits, uint64_t seed, uint64_t round0, uint64_t rounds, BW w, double *__restrict__ renergy) {
+    __shared__ double sh[8];
+    uint32_t *bmap = rmaps + (size_t) blockIdx.x * W * H;
+    for (uint32_t i = threadIdx.x; i < W * H; i += blockDim.x) bmap[i] = bmap0[i];
+    __syncthreads();
+    for (uint64_t rd = 0; rd < rounds; ++rd) {
+        uint64_t rr = rng64(seed ^ (0x9e3779b97f4a7c15ull * (blockIdx.x + 1)), 0xb10bu, round0 + rd);
+        uint32_t y = (uint32_t) (rr % H);
+        uint32_t m = 1u + (uint32_t) ((rr >> 20) % ((1ull << kbits) - 1ull));
+        for (uint32_t l = threadIdx.x; l < W; l += blockDim.x) {
+            uint32_t r = l ^ m;
+            if (r > l && r < W) match_propose(bmap, feat, W, H, y, l, r, w);
+        }
+        __syncthreads();
+    }
+    double e = 0.0;
+    for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) {
+        const double *prev = feat + ((size_t) (H - 1) * W + bmap[(size_t) (H - 1) * W + i]) * 4;
+        for (uint32_t j = 0; j < H; ++j) {
+            const double *cur = feat + ((size_t) j * W + bmap[(size_t) j * W + i]) * 4;
+            e += blob_dist(prev, cur, w);
+            prev = cur;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; ++k) t += sh[k]; renergy[blockIdx.x] = t; }
 }
 
 // energy = sum over slots and frames of dist(map[i][j-1], map[i][j]) (thread.cpp:1087-1107), one partial per block
@@ -162,22 +195,35 @@ int engine_match_init(Engine *E) {
 int engine_match_rounds(Engine *E, uint64_t rounds) {
     if (!E->map_ready) { int rc = engine_match_init(E); if (rc != AMX_OK) return rc; }
     uint32_t W = E->map_w, H = E->map_h;
-    if (H == 0 || W <= 1) return AMX_OK;
+    if (H < 2 || W <= 1 || rounds == 0) return AMX_OK;
     BW w = make_weights(E);
     unsigned k = 0;
     while ((1u << k) < W) ++k;
-    unsigned long long *d_acc = (unsigned long long *) (E->d_menergy + 64);
-    cudaMemsetAsync(d_acc, 0, 8, E->stream);
-    for (uint64_t r = 0; r < rounds; ++r) {
-        uint64_t round = E->rng_round++;
-        uint32_t y = (uint32_t) (rng64(E->p.seed, 0xb10bu, round) % H);
-        uint32_t m = 1u + (uint32_t) (rng64(E->p.seed, 0xb10cu, round) % ((1ull << k) - 1ull));
-        k_match_round<<<div_up(W, 256), 256, 0, E->stream>>>(E->d_bmap, E->d_bfeat, W, H, y, m, w, d_acc);
-        E->launches++;
+    const uint32_t R = 296;                       // 2 replicas per SM
+    uint32_t *d_rmaps = nullptr;
+    double *d_re = nullptr;
+    if (!dev_alloc(E, (void **) &d_rmaps, (size_t) R * W * H * 4, "replica maps") || !dev_alloc(E, (void **) &d_re, R * 8, "replica energy")) {
+        dev_free(d_rmaps);
+        return AMX_ERR_NOMEM;
     }
-    if (E->fail(cudaMemcpyAsync(E->blob_map.data(), E->d_bmap, (size_t) W * H * 4, cudaMemcpyDeviceToHost, E->stream), "map D2H") ||
+    k_match_replicas<<<R, 256, 0, E->stream>>>(E->d_bmap, d_rmaps, E->d_bfeat, W, H, k, E->p.seed, E->rng_round, rounds, w, d_re);
+    E->rng_round += rounds;
+    E->launches++;
+    std::vector<double> re(R);
+    int rc = AMX_OK;
+    if (E->fail(cudaMemcpyAsync(re.data(), d_re, R * 8, cudaMemcpyDeviceToHost, E->stream), "replica energy D2H") ||
         E->fail(cudaStreamSynchronize(E->stream), "match rounds") || E->check("match rounds"))
-        return AMX_ERR_CUDA;
+        rc = AMX_ERR_CUDA;
+    if (rc == AMX_OK) {
+        uint32_t best = 0;
+        for (uint32_t i = 1; i < R; ++i) if (re[i] < re[best]) best = i;
+        if (E->fail(cudaMemcpyAsync(E->d_bmap, d_rmaps + (size_t) best * W * H, (size_t) W * H * 4, cudaMemcpyDeviceToDevice, E->stream), "best map") ||
+            E->fail(cudaMemcpyAsync(E->blob_map.data(), E->d_bmap, (size_t) W * H * 4, cudaMemcpyDeviceToHost, E->stream), "map D2H") ||
+            E->fail(cudaStreamSynchronize(E->stream), "match rounds"))
+            rc = AMX_ERR_CUDA;
+    }
+    dev_free(d_rmaps); dev_free(d_re);
+    if (rc != AMX_OK) return rc;
     groups_from_map(E);
     double e;
     return engine_match_energy(E, &e);

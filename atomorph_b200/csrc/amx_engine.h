@@ -120,12 +120,13 @@ struct Engine {
     int32_t  *d_blob_of_chain = nullptr;   // [h][nchains] blob vector index of chain c in frame y
     uint32_t *d_blob_avg = nullptr;        // [h][nchains] blob2pixel colour (AVERAGE) per frame/chain
     uint32_t *d_blob_distinct = nullptr;   // [nchains]   DISTINCT colour per chain (host mt19937(group))
-    // accumulators (canvas sized)
+    // A-buffer of one frame: list head per canvas position, one record per atom {next, colour, fract}
+    uint32_t *ab_head = nullptr;
+    uint4    *ab_rec = nullptr;
+    // per-(pixel, blob) entries for the feather / per-blob paths (canvas sized + overflow hash)
     int32_t  *acc_owner = nullptr;
-    unsigned long long *acc = nullptr;     // [5][canvas]  R,G,B,A, N|cnt<<40
     uint8_t  *acc_hasovf = nullptr;
-    unsigned long long *ovf_key = nullptr; // overflow hash table
-    unsigned long long *ovf_acc = nullptr; // [5][ovf_cap]
+    unsigned long long *ovf_key = nullptr;
     uint32_t  ovf_cap = 0;
     uint32_t *d_ovf_used = nullptr;
     uint32_t *blob_px = nullptr;           // resolved per-(pixel,layer-0) colour for feather / per-blob fetch

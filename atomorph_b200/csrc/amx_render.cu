@@ -3,25 +3,31 @@
  *
  * Reference: morph::get_pixels(t) -> draw_atoms -> get_pixels(blob,t)  (morph.cpp:452-678,
  * 1302-1421), get_background (1431-1465).  The reference is a scatter into per-pixel std::map
- * lists followed by per-pixel normalisation, per-blob feather peeling and cross-blob "over"
- * compositing.  Here:
+ * lists followed by per-pixel normalisation IN ATOM ORDER, per-blob feather peeling and
+ * cross-blob "over" compositing.  Here a frame is two kernels:
  *
  *   prepare  (once per table refresh)  per atom & interval: end colours with the one-sided
  *            alpha rule resolved, Perlin lag/slope  -> coalesced SoA, 24 B/atom/interval
- *   splat    per atom: trajectory (linear / Catmull-Rom in double, reference operation order),
- *            colour fade, 4 bilinear splats accumulated as EXACT INTEGERS  sum(c*n), sum(n), count
- *            (n = integer bilinear numerator <= 65025): order independent, so atomics are safe
- *   resolve  per (pixel, blob) entry: round(sum(c*n)/sum(n)) with exact rational rounding,
- *            density alpha scale  (morph.cpp:598-613)
- *   feather  4-neighbour erosion layers per blob  (morph.cpp:625-674)
- *   composite per pixel: blobs in blob-vector order, "over", background blend (morph.cpp:1357-1401)
+ *   scatter  per atom: trajectory (linear / Catmull-Rom in double, reference operation order),
+ *            colour fade; the atom is linked into the list of its HOME pixel (top-left splat
+ *            target) with ONE 32-bit atomicExch; its 16-byte record {next, colour, fract} is
+ *            written at index = atom (coalesced, no allocator)
+ *   gather   per pixel: walk the lists of the 4 homes that can reach the pixel, keep the
+ *            contributions (atom, colour, integer bilinear numerator n <= 65025), sort them by
+ *            blob order and atom index and replay the reference's double sums in ITS order
+ *            (morph.cpp:598-613): bit-exact, including the exact .5 ties where an order-free
+ *            integer sum would differ by 1 LSB.  Without feather the same thread composites the
+ *            blobs "over" each other and blends the background (morph.cpp:1357-1401) and
+ *            writes the RGBA pixel: no accumulator ever touches HBM.
+ *   feather  (only when feather > 0) per-(pixel, blob) entries, 4-neighbour erosion layers
+ *            (morph.cpp:625-674), then a composite kernel.
  *
- * The reference sums doubles in atom order; the exact-integer form differs from it only where
- * the true quotient is an exact .5 tie (<= 1 LSB, SURVEY.md section 7 hard part 2).
+ * A pixel that receives more than MAXK contributions (atoms of a volatile blob collapsing
+ * onto one point) falls back to exact integer sums sum(c*n)/sum(n) with exact rational
+ * rounding -- identical to the reference except on exact .5 ties (<= 1 LSB there).
  *
- * Accumulators: acc[5][canvas] u64 = R, G, B, A, (N | count<<40) owned by the first blob that
- * touches the pixel; other blobs touching the same pixel go to an open-addressing overflow
- * table keyed (pixel, chain).  Single-chain scenes skip the ownership logic.
+ * Algorithmic bytes per frame: A*24 B (h <= 3 or linear) or A*40 B
+ * (spline, h >= 4) read + P*4 B written.
  */
 #include <cmath>
 #include <cstring>
@@ -32,8 +38,8 @@
 
 namespace amx {
 
-#define NC_SHIFT 40
-#define NC_MASK ((1ull << NC_SHIFT) - 1ull)
+#define MAXK 32
+#define NIL 0xffffffffu
 
 struct RConst {
     uint32_t width, height, cw, ch;
@@ -51,15 +57,14 @@ struct RFrame {
     double   b1, b2, b3, b4;      // Catmull-Rom basis at the local time
     double   w;                   // c1 / pt1 weight = 1 - local t
     double   str_cos;             // eased weight for COSINE fading (host libm)
-    int32_t  chain_only;          // >= 0: splat only this chain (per-blob fetch)
+    int32_t  chain_only;          // >= 0: only this chain (per-blob fetch)
 };
 
+// per-(pixel, blob) entries, used by the feather / per-blob paths
 struct Acc {
-    int32_t *owner;
-    unsigned long long *acc;      // [5][canvas]
+    int32_t *owner;               // chain stored in the layer-0 entry of a pixel, -1 none
     uint8_t *hasovf;
-    unsigned long long *ovf_key;
-    unsigned long long *ovf_acc;  // [5][cap]
+    unsigned long long *ovf_key;  // open addressing, key = pixel<<32 | chain+1
     uint32_t *ovf_used;
     size_t canvas;
     size_t ovf_cap;
@@ -85,50 +90,23 @@ __device__ __forceinline__ uint32_t ovf_slot(const Acc &ac, uint32_t mask, uint3
     return 0xffffffffu;
 }
 
-template <bool SINGLE>
-__device__ __forceinline__ void splat_add(const Acc &ac, const RConst &rc, uint32_t x, uint32_t y, uint32_t c, uint32_t col, uint32_t n) {
-    uint32_t ci = y * rc.cw + x;
-    unsigned long long *base = ac.acc + ci;
-    size_t stride = ac.canvas;
-    if (!SINGLE) {
-        int32_t o = ac.owner[ci];
-        if (o < 0) {
-            o = atomicCAS(&ac.owner[ci], -1, (int32_t) c);
-            if (o < 0) o = (int32_t) c;
-        }
-        if ((uint32_t) o != c) {
-            uint32_t s = ovf_slot(ac, rc.ovf_mask, ci, c, true);
-            if (s == 0xffffffffu) return;   // table full: reported through ovf_used on the host
-            ac.hasovf[ci] = 1;
-            base = ac.ovf_acc + s;
-            stride = ac.ovf_cap;
-        }
-    }
-    atomicAdd(base + 0 * stride, (unsigned long long) (c_r(col) * n));
-    atomicAdd(base + 1 * stride, (unsigned long long) (c_g(col) * n));
-    atomicAdd(base + 2 * stride, (unsigned long long) (c_b(col) * n));
-    atomicAdd(base + 3 * stride, (unsigned long long) (c_a(col) * n));
-    atomicAdd(base + 4 * stride, (unsigned long long) n | (1ull << NC_SHIFT));
-}
-
 struct DevCos { __device__ double operator()(double x) const { return cos(x); } };
 
-template <bool SINGLE>
+// ---------------------------------------------------------------------------------------- scatter
 __global__ void __launch_bounds__(256)
-k_splat(const pword *__restrict__ table, const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2,
-        const double *__restrict__ rlag, const double *__restrict__ rslope, const uint32_t *__restrict__ chain_of,
-        RConst rc, RFrame rf, Acc ac) {
+k_scatter(const pword *__restrict__ table, const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2,
+          const double *__restrict__ rlag, const double *__restrict__ rslope, const uint32_t *__restrict__ chain_of,
+          RConst rc, RFrame rf, uint32_t *__restrict__ head, uint4 *__restrict__ rec) {
     size_t a = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= rc.A) return;
-    uint32_t c = SINGLE ? 0u : chain_of[a];
-    if (rf.chain_only >= 0 && c != (uint32_t) rf.chain_only) return;
+    if (rf.chain_only >= 0 && chain_of[a] != (uint32_t) rf.chain_only) return;
     size_t A = rc.A;
     pword pt1 = table[(size_t) rf.y * A + a];
     pword pt2 = table[(size_t) rf.yn * A + a];
     bool has1 = pw_flags(pt1) & F_HAS_PIXEL, has2 = pw_flags(pt2) & F_HAS_PIXEL;
     if (!has1 && !has2) return;
 
-    // trajectory
+    // trajectory (morph.cpp:523-531)
     uint32_t x, y, xf, yf;
     if (rc.motion == K_LINEAR) {
         lerp_point(pt1, pt2, rf.w, &x, &y, &xf, &yf);
@@ -142,36 +120,77 @@ k_splat(const pword *__restrict__ table, const uint32_t *__restrict__ rc1, const
     } else {
         x = pw_x(pt1); y = pw_y(pt1); xf = pw_xf(pt1); yf = pw_yf(pt1);
     }
-
-    // colour
+    // clip (morph.cpp:552-555)
+    if (x >= rc.width || y >= rc.height) {
+        if (x > rc.bx2 || x < rc.bx1 || y > rc.by2 || y < rc.by1) return;
+    }
+    // colour (morph.cpp:537-550)
     uint32_t c1 = rc1[(size_t) rf.y * A + a], c2 = rc2[(size_t) rf.y * A + a];
     double str = rf.w;
     if (rc.fading == K_COSINE) str = rf.str_cos;
     else if (rc.fading == K_PERLIN) str = ease_strength(rlag[(size_t) rf.y * A + a], rslope[(size_t) rf.y * A + a], rf.w, DevCos());
     uint32_t col = lerp_color(c1, c2, str);
 
-    // clip (morph.cpp:552-555)
-    if (x >= rc.width || y >= rc.height) {
-        if (x > rc.bx2 || x < rc.bx1 || y > rc.by2 || y < rc.by1) return;
-    }
-    // bilinear splats, integer numerators of weight/65025 (morph.cpp:558-588)
-    uint32_t w11 = (255u - xf) * (255u - yf), w21 = xf * (255u - yf), w12 = (255u - xf) * yf, w22 = xf * yf;
-    if (w11) splat_add<SINGLE>(ac, rc, x, y, c, col, w11);
-    if ((x < rc.bx2 || x + 1 < rc.width) && w21) splat_add<SINGLE>(ac, rc, x + 1, y, c, col, w21);
-    if ((y < rc.by2 || y + 1 < rc.height) && w12) splat_add<SINGLE>(ac, rc, x, y + 1, c, col, w12);
-    if (w22) {
-        if ((y < rc.by2 && x < rc.bx2) || (y + 1 < rc.height && x + 1 < rc.width)) splat_add<SINGLE>(ac, rc, x + 1, y + 1, c, col, w22);
+    uint32_t home = y * rc.cw + x;
+    uint32_t next = atomicExch(&head[home], (uint32_t) a);
+    rec[a] = make_uint4(next, col, xf | (yf << 8), 0u);
+}
+
+// ---------------------------------------------------------------------------------------- gather
+// Visit every contribution to pixel (px, py): f(atom, colour, n) with n the integer bilinear numerator.
+// Splat targets and their edge rules: morph.cpp:558-588.
+template <typename F>
+__device__ __forceinline__ void visit_contributions(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
+                                                    uint32_t px, uint32_t py, F f) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t dx = k & 1, dy = k >> 1;
+        if (px < dx || py < dy) continue;
+        uint32_t hx = px - dx, hy = py - dy;
+        bool ok;
+        if (k == 0) ok = true;
+        else if (k == 1) ok = (hx < rc.bx2 || hx + 1 < rc.width);
+        else if (k == 2) ok = (hy < rc.by2 || hy + 1 < rc.height);
+        else ok = (hy < rc.by2 && hx < rc.bx2) || (hy + 1 < rc.height && hx + 1 < rc.width);
+        if (!ok) continue;
+        uint32_t idx = head[hy * rc.cw + hx];
+        while (idx != NIL) {
+            uint4 r = rec[idx];
+            uint32_t xf = r.z & 255u, yf = (r.z >> 8) & 255u;
+            uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
+            if (n) f(idx, r.y, n);
+            idx = r.x;
+        }
     }
 }
 
-// exact round-half-up of num/den for non-negative integers
+// the reference's per-position normalisation, contributions already in atom order (morph.cpp:598-613)
+__device__ __forceinline__ uint32_t resolve_fp(const uint32_t *cc, const uint32_t *cn, int first, int last, uint32_t density) {
+    double r = 0.0, g = 0.0, b = 0.0, a = 0.0, weight_sum = 0.0;
+    for (int i = first; i < last; ++i) {
+        double w = (double) cn[i] / 65025.0;
+        uint32_t c = cc[i];
+        weight_sum += w;
+        r += (double) c_r(c) * w;
+        g += (double) c_g(c) * w;
+        b += (double) c_b(c) * w;
+        a += (double) c_a(c) * w;
+    }
+    double wd = density > 0 ? (double) (last - first) / (double) density : 0.0;
+    if (wd > 1.0) wd = 1.0;
+    r = round(r / weight_sum);
+    g = round(g / weight_sum);
+    b = round(b / weight_sum);
+    a = round(wd * (a / weight_sum));
+    return c_make(to_u8(r), to_u8(g), to_u8(b), to_u8(a));
+}
+
+// exact round-half-up of num/den for non-negative integers (fallback for pixels with > MAXK contributions)
 __device__ __forceinline__ uint32_t rdiv(unsigned long long num, unsigned long long den) {
     return (uint32_t) ((2ull * num + den) / (2ull * den));
 }
-
-__device__ __forceinline__ uint32_t resolve_px(unsigned long long R, unsigned long long G, unsigned long long B,
-                                               unsigned long long Av, unsigned long long NC, uint32_t density) {
-    unsigned long long N = NC & NC_MASK, cnt = NC >> NC_SHIFT;
+__device__ __forceinline__ uint32_t resolve_int(unsigned long long R, unsigned long long G, unsigned long long B, unsigned long long Av,
+                                                unsigned long long N, unsigned long long cnt, uint32_t density) {
     uint32_t r = rdiv(R, N), g = rdiv(G, N), b = rdiv(B, N), a;
     if (density == 0) a = 0;
     else if (cnt >= density) a = rdiv(Av, N);
@@ -179,27 +198,139 @@ __device__ __forceinline__ uint32_t resolve_px(unsigned long long R, unsigned lo
     return c_make(r, g, b, a);
 }
 
-// resolve every entry to its blob pixel (morph.cpp:591-623); zero the accumulators for the next frame
-__global__ void __launch_bounds__(256)
-k_resolve(Acc ac, uint32_t density, uint32_t *__restrict__ px0, uint8_t *__restrict__ layer0, uint32_t *__restrict__ pxo,
-          uint8_t *__restrict__ layero, size_t total) {
-    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    unsigned long long *base;
-    size_t stride;
-    uint32_t *px;
-    uint8_t *layer;
-    if (i < ac.canvas) { base = ac.acc + i; stride = ac.canvas; px = px0 + i; layer = layer0 + i; }
-    else {
-        size_t s = i - ac.canvas;
-        if (ac.ovf_key[s] == 0ull) return;
-        base = ac.ovf_acc + s; stride = ac.ovf_cap; px = pxo + s; layer = layero + s;
+// final colour of an entry: feather alpha (morph.cpp:658-669) and show_blobs substitution (1320-1340)
+__device__ __forceinline__ uint32_t entry_color(uint32_t px, uint32_t layer, uint32_t c, const RConst &rc, uint32_t y_frame,
+                                               const uint32_t *blob_avg, const uint32_t *blob_distinct) {
+    if (rc.feather > 0 && layer < 254u) {
+        double a = round((double) c_a(px) * ((double) (layer + 1u) / (double) (rc.feather + 1u)));
+        px = (px & 0x00ffffffu) | (to_u8(a) << 24);
     }
-    unsigned long long NC = base[4 * stride];
-    if (NC == 0ull) { *layer = 254; return; }   // 254 = no entry
-    *px = resolve_px(base[0], base[stride], base[2 * stride], base[3 * stride], NC, density);
-    *layer = 255;                               // 255 = entry present, not peeled
-    base[0] = 0; base[stride] = 0; base[2 * stride] = 0; base[3 * stride] = 0; base[4 * stride] = 0;
+    if (rc.show_blobs == SHOW_DISTINCT) return blob_distinct[c];
+    if (rc.show_blobs == SHOW_AVERAGE) return blob_avg[(size_t) y_frame * rc.nchains + c];
+    return px;
+}
+
+// cross-blob "over" accumulation in arrival order (morph.cpp:1342-1380)
+struct Over {
+    double r = 0, g = 0, b = 0, a = 0;
+    bool first = true;
+    __device__ __forceinline__ void add(uint32_t col) {
+        if (c_a(col) == 0) return;
+        double sr = c_r(col) / 255.0, sg = c_g(col) / 255.0, sb = c_b(col) / 255.0, sa = c_a(col) / 255.0;
+        if (first) { r = sr; g = sg; b = sb; a = sa; first = false; }
+        else {
+            r = sa * sr + (1.0 - sa) * r;
+            g = sa * sg + (1.0 - sa) * g;
+            b = sa * sb + (1.0 - sa) * b;
+            a = a + (1.0 - a) * sa;
+        }
+    }
+    __device__ __forceinline__ uint32_t finish(uint32_t bgc, bool keep_background) {
+        if (first) return bgc;
+        if (keep_background) {                      // morph.cpp:1388-1399
+            double bgr = c_r(bgc) / 255.0, bgg = c_g(bgc) / 255.0, bgb = c_b(bgc) / 255.0, bga = c_a(bgc) / 255.0;
+            r = a * r + (1.0 - a) * bgr;
+            g = a * g + (1.0 - a) * bgg;
+            b = a * b + (1.0 - a) * bgb;
+            a = bga + (1.0 - bga) * a;
+        }
+        return create_color_d(r, g, b, a);
+    }
+};
+
+// Emits the resolved blob pixels of one position in ascending blob order: emit(chain, px)
+template <bool SINGLE, typename E>
+__device__ __forceinline__ void resolve_position(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
+                                                 const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc,
+                                                 uint32_t px, uint32_t py, E emit) {
+    unsigned long long key[MAXK];
+    uint32_t cc[MAXK], cn[MAXK];
+    int count = 0;
+    visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+        if (count < MAXK) {
+            unsigned long long k = a;
+            if (!SINGLE) k |= (unsigned long long) (uint32_t) boc[chain_of[a]] << 32;
+            // insertion sort by (blob order, atom)
+            int i = count;
+            while (i > 0 && key[i - 1] > k) { key[i] = key[i - 1]; cc[i] = cc[i - 1]; cn[i] = cn[i - 1]; --i; }
+            key[i] = k; cc[i] = col; cn[i] = n;
+        }
+        ++count;
+    });
+    if (count == 0) return;
+    if (count <= MAXK) {
+        int first = 0;
+        while (first < count) {
+            int last = first + 1;
+            if (!SINGLE) while (last < count && (key[last] >> 32) == (key[first] >> 32)) ++last;
+            else last = count;
+            uint32_t chain = SINGLE ? 0u : chain_of[(uint32_t) key[first]];
+            emit(chain, resolve_fp(cc, cn, first, last, rc.density));
+            first = last;
+        }
+        return;
+    }
+    // heavy position: exact integer sums, one chain at a time in ascending blob order
+    long long prev = -1;
+    for (;;) {
+        long long best = LLONG_MAX;
+        uint32_t bchain = 0;
+        if (SINGLE) { if (prev < 0) best = 0; }
+        else visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t, uint32_t) {
+            uint32_t c = chain_of[a];
+            long long k = boc[c];
+            if (k > prev && k < best) { best = k; bchain = c; }
+        });
+        if (best == LLONG_MAX) break;
+        unsigned long long R = 0, G = 0, B = 0, Av = 0, N = 0, cnt = 0;
+        visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+            if (!SINGLE && chain_of[a] != bchain) return;
+            R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
+        });
+        emit(bchain, resolve_int(R, G, B, Av, N, cnt, rc.density));
+        prev = best;
+    }
+}
+
+// fused gather + composite (feather == 0): one thread per OUTPUT pixel
+template <bool SINGLE>
+__global__ void __launch_bounds__(256)
+k_gather_composite(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, RConst rc, uint32_t y_frame,
+                   const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+                   const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+                   const uint32_t *__restrict__ bg, uint32_t *__restrict__ out) {
+    uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= rc.width || py >= rc.height) return;
+    size_t i = (size_t) py * rc.width + px;
+    uint32_t bgc = rc.keep_background ? bg[i] : 0u;
+    const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
+    Over ov;
+    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t chain, uint32_t pxl) {
+        ov.add(entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct));
+    });
+    out[i] = ov.finish(bgc, rc.keep_background != 0);
+}
+
+// gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel
+template <bool SINGLE>
+__global__ void __launch_bounds__(256)
+k_gather_entries(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, RConst rc, uint32_t y_frame,
+                 const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain, Acc ac,
+                 uint32_t *__restrict__ px0, uint8_t *__restrict__ layer0, uint32_t *__restrict__ pxo, uint8_t *__restrict__ layero) {
+    uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= rc.cw || py >= rc.ch) return;
+    uint32_t ci = py * rc.cw + px;
+    const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
+    int emitted = 0;
+    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t chain, uint32_t pxl) {
+        if (emitted == 0) { ac.owner[ci] = (int32_t) chain; px0[ci] = pxl; layer0[ci] = 255; }
+        else {
+            uint32_t s = ovf_slot(ac, rc.ovf_mask, ci, chain, true);
+            if (s != 0xffffffffu) { pxo[s] = pxl; layero[s] = 255; ac.hasovf[ci] = 1; }
+        }
+        ++emitted;
+    });
+    if (emitted == 0) { ac.owner[ci] = -1; layer0[ci] = 254; }
 }
 
 // layer value of entry (pixel ci, chain c): 254 none, 255 unpeeled, else peel iteration
@@ -247,18 +378,6 @@ k_feather_pass(Acc ac, RConst rc, uint8_t *layer0, uint8_t *layero, uint32_t l, 
     if (border) *mine = (uint8_t) l;
 }
 
-// final colour of an entry: feather alpha (morph.cpp:658-669) and show_blobs substitution (1320-1340)
-__device__ __forceinline__ uint32_t entry_color(uint32_t px, uint32_t layer, uint32_t c, const RConst &rc, uint32_t y_frame,
-                                               const uint32_t *blob_avg, const uint32_t *blob_distinct) {
-    if (rc.feather > 0 && layer < 254u) {
-        double a = round((double) c_a(px) * ((double) (layer + 1u) / (double) (rc.feather + 1u)));
-        px = (px & 0x00ffffffu) | (to_u8(a) << 24);
-    }
-    if (rc.show_blobs == SHOW_DISTINCT) return blob_distinct[c];
-    if (rc.show_blobs == SHOW_AVERAGE) return blob_avg[(size_t) y_frame * rc.nchains + c];
-    return px;
-}
-
 template <bool SINGLE>
 __global__ void __launch_bounds__(256)
 k_composite(Acc ac, RConst rc, uint32_t y_frame, const uint32_t *__restrict__ px0, const uint8_t *__restrict__ layer0,
@@ -270,21 +389,8 @@ k_composite(Acc ac, RConst rc, uint32_t y_frame, const uint32_t *__restrict__ px
     uint32_t x = (uint32_t) (i % rc.width), y = (uint32_t) (i / rc.width);
     uint32_t ci = y * rc.cw + x;
     uint32_t bgc = rc.keep_background ? bg[i] : 0u;
-    uint32_t result = bgc;
-    double r = 0, g = 0, b = 0, a = 0;
-    bool first = true;
-
-    auto over = [&](uint32_t col) {
-        if (c_a(col) == 0) return;                 // morph.cpp:1342
-        double sr = c_r(col) / 255.0, sg = c_g(col) / 255.0, sb = c_b(col) / 255.0, sa = c_a(col) / 255.0;
-        if (first) { r = sr; g = sg; b = sb; a = sa; first = false; }
-        else {
-            r = sa * sr + (1.0 - sa) * r;
-            g = sa * sg + (1.0 - sa) * g;
-            b = sa * sb + (1.0 - sa) * b;
-            a = a + (1.0 - a) * sa;
-        }
-    };
+    Over ov;
+    auto over = [&](uint32_t col) { ov.add(col); };
 
     if (SINGLE) {
         uint32_t l = layer0[ci];
@@ -323,17 +429,7 @@ k_composite(Acc ac, RConst rc, uint32_t y_frame, const uint32_t *__restrict__ px
             }
         }
     }
-    if (!first) {
-        if (rc.keep_background) {                   // morph.cpp:1388-1399
-            double bgr = c_r(bgc) / 255.0, bgg = c_g(bgc) / 255.0, bgb = c_b(bgc) / 255.0, bga = c_a(bgc) / 255.0;
-            r = a * r + (1.0 - a) * bgr;
-            g = a * g + (1.0 - a) * bgg;
-            b = a * b + (1.0 - a) * bgb;
-            a = bga + (1.0 - bga) * a;
-        }
-        result = create_color_d(r, g, b, a);
-    }
-    out[i] = result;
+    out[i] = ov.finish(bgc, rc.keep_background != 0);
 }
 
 // clear ownership after a frame
@@ -403,10 +499,10 @@ void engine_render_free(Engine *E) {
     E->rc1 = E->rc2 = nullptr; E->rlag = E->rslope = nullptr;
     dev_free(E->d_blob_of_chain); dev_free(E->d_blob_avg); dev_free(E->d_blob_distinct);
     E->d_blob_of_chain = nullptr; E->d_blob_avg = nullptr; E->d_blob_distinct = nullptr;
-    dev_free(E->acc_owner); dev_free(E->acc); dev_free(E->acc_hasovf); dev_free(E->ovf_key); dev_free(E->ovf_acc);
-    dev_free(E->d_ovf_used); dev_free(E->blob_px);
-    E->acc_owner = nullptr; E->acc = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr; E->ovf_acc = nullptr;
-    E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
+    dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
+    dev_free(E->d_ovf_used); dev_free(E->blob_px); dev_free(E->ab_head); dev_free(E->ab_rec);
+    E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
+    E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0; E->ab_head = nullptr; E->ab_rec = nullptr;
     E->render_ready = false;
 }
 
@@ -458,20 +554,10 @@ int engine_render_prepare(Engine *E) {
     int rcode = ensure_perlin(E);
     if (rcode != AMX_OK) return rcode;
     size_t cv = E->canvas();
-    if (!E->acc) {
-        E->ovf_cap = 1u << 16;
-        if (E->nchains > 1) while (E->ovf_cap < cv && E->ovf_cap < (1u << 26)) E->ovf_cap <<= 1;
-        if (!dev_alloc(E, (void **) &E->acc_owner, cv * 4, "owner") || !dev_alloc(E, (void **) &E->acc, 5 * cv * 8, "acc") ||
-            !dev_alloc(E, (void **) &E->acc_hasovf, cv, "hasovf") || !dev_alloc(E, (void **) &E->ovf_key, (size_t) E->ovf_cap * 8, "ovf_key") ||
-            !dev_alloc(E, (void **) &E->ovf_acc, 5 * (size_t) E->ovf_cap * 8, "ovf_acc") || !dev_alloc(E, (void **) &E->d_ovf_used, 4, "ovf_used") ||
-            !dev_alloc(E, (void **) &E->blob_px, (cv + E->ovf_cap) * 5, "blob_px"))
+    if (!E->ab_head) {
+        // A-buffer: list heads per canvas position + one 16-byte record per atom
+        if (!dev_alloc(E, (void **) &E->ab_head, cv * 4, "abuf heads") || !dev_alloc(E, (void **) &E->ab_rec, E->A * 16, "abuf records"))
             return AMX_ERR_NOMEM;
-        cudaMemsetAsync(E->acc_owner, 0xff, cv * 4, E->stream);
-        cudaMemsetAsync(E->acc, 0, 5 * cv * 8, E->stream);
-        cudaMemsetAsync(E->acc_hasovf, 0, cv, E->stream);
-        cudaMemsetAsync(E->ovf_key, 0, (size_t) E->ovf_cap * 8, E->stream);
-        cudaMemsetAsync(E->ovf_acc, 0, 5 * (size_t) E->ovf_cap * 8, E->stream);
-        cudaMemsetAsync(E->d_ovf_used, 0, 4, E->stream);
     }
     // blob order / colours per (frame, chain)
     size_t m = (size_t) E->h * E->nchains;
@@ -549,9 +635,26 @@ static RFrame make_rframe(Engine *E, double time, uint32_t f, double tl) {
     return rf;
 }
 
+// entry storage for the feather / per-blob paths, allocated on first use
+static int ensure_entries(Engine *E) {
+    if (E->acc_owner) return AMX_OK;
+    size_t cv = E->canvas();
+    E->ovf_cap = 1u << 12;
+    if (E->nchains > 1) while (E->ovf_cap < cv && E->ovf_cap < (1u << 26)) E->ovf_cap <<= 1;
+    if (!dev_alloc(E, (void **) &E->acc_owner, cv * 4, "owner") || !dev_alloc(E, (void **) &E->acc_hasovf, cv, "hasovf") ||
+        !dev_alloc(E, (void **) &E->ovf_key, (size_t) E->ovf_cap * 8, "ovf_key") || !dev_alloc(E, (void **) &E->d_ovf_used, 4, "ovf_used") ||
+        !dev_alloc(E, (void **) &E->blob_px, (cv + E->ovf_cap) * 5, "blob_px"))
+        return AMX_ERR_NOMEM;
+    cudaMemsetAsync(E->acc_owner, 0xff, cv * 4, E->stream);
+    cudaMemsetAsync(E->acc_hasovf, 0, cv, E->stream);
+    cudaMemsetAsync(E->ovf_key, 0, (size_t) E->ovf_cap * 8, E->stream);
+    cudaMemsetAsync(E->d_ovf_used, 0, 4, E->stream);
+    return AMX_OK;
+}
+
 static Acc make_acc(Engine *E) {
     Acc ac;
-    ac.owner = E->acc_owner; ac.acc = E->acc; ac.hasovf = E->acc_hasovf; ac.ovf_key = E->ovf_key; ac.ovf_acc = E->ovf_acc;
+    ac.owner = E->acc_owner; ac.hasovf = E->acc_hasovf; ac.ovf_key = E->ovf_key;
     ac.ovf_used = E->d_ovf_used; ac.canvas = E->canvas(); ac.ovf_cap = E->ovf_cap;
     return ac;
 }
@@ -571,17 +674,27 @@ static void launch_background(Engine *E, const RConst &rc, const RFrame &rf, uin
     E->launches++;
 }
 
-// splat + resolve + feather of one frame; leaves entries (px/layer) valid and ownership set
+static dim3 grid2d(uint32_t w, uint32_t h) { return dim3(div_up(w, 32), div_up(h, 8)); }
+
+// scatter one frame into the A-buffer
+static void launch_scatter(Engine *E, const RConst &rc, const RFrame &rf) {
+    cudaMemsetAsync(E->ab_head, 0xff, E->canvas() * 4, E->stream);
+    k_scatter<<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, E->rc1, E->rc2, E->rlag, E->rslope, E->chain_of, rc, rf, E->ab_head, E->ab_rec);
+    E->launches++;
+}
+
+// scatter + gather into entries + feather of one frame; leaves entries (px/layer) valid and ownership set
 static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, const Acc &ac) {
     size_t cv = E->canvas();
     uint32_t *px0 = E->blob_px, *pxo = E->blob_px + cv;
     uint8_t *layer0 = (uint8_t *) (E->blob_px + cv + E->ovf_cap), *layero = layer0 + cv;
     bool single = E->nchains == 1;
-    if (single) k_splat<true><<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, E->rc1, E->rc2, E->rlag, E->rslope, E->chain_of, rc, rf, ac);
-    else        k_splat<false><<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, E->rc1, E->rc2, E->rlag, E->rslope, E->chain_of, rc, rf, ac);
+    launch_scatter(E, rc, rf);
+    const int32_t *boc = E->d_blob_of_chain;
+    if (single) k_gather_entries<true><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
+    else        k_gather_entries<false><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
+    E->launches++;
     size_t total = single ? cv : cv + E->ovf_cap;
-    k_resolve<<<div_up(total, 256), 256, 0, E->stream>>>(ac, rc.density, px0, layer0, pxo, layero, total);
-    E->launches += 2;
     for (uint32_t l = 0; l < rc.feather; ++l) {
         if (single) k_feather_pass<true><<<div_up(total, 256), 256, 0, E->stream>>>(ac, rc, layer0, layero, l, total);
         else        k_feather_pass<false><<<div_up(total, 256), 256, 0, E->stream>>>(ac, rc, layer0, layero, l, total);
@@ -592,9 +705,8 @@ static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, 
 static void launch_frame_cleanup(Engine *E) {
     if (E->nchains == 1) return;
     size_t cv = E->canvas();
-    k_clear_owner<<<div_up(cv, 256), 256, 0, E->stream>>>(E->acc_owner, E->acc_hasovf, cv);
+    cudaMemsetAsync(E->acc_hasovf, 0, cv, E->stream);
     cudaMemsetAsync(E->ovf_key, 0, (size_t) E->ovf_cap * 8, E->stream);
-    E->launches++;
 }
 
 int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int out_is_device) {
@@ -614,6 +726,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     }
     uint32_t *d_bg = nullptr;
     if (E->p.keep_background && !dev_alloc(E, (void **) &d_bg, np * 4, "bg")) return AMX_ERR_NOMEM;
+    if (have_chains && E->p.feather > 0) { int rcode = ensure_entries(E); if (rcode != AMX_OK) { dev_free(d_bg); return rcode; } }
     RConst rc = make_rconst(E);
     Acc ac = make_acc(E);
     size_t cv = E->canvas();
@@ -630,10 +743,18 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             else cudaMemsetAsync(dst, 0, np * 4, E->stream);
             continue;
         }
+        bool single = E->nchains == 1;
+        if (rc.feather == 0) {
+            launch_scatter(E, rc, rf);
+            if (single) k_gather_composite<true><<<grid2d(rc.width, rc.height), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
+            else        k_gather_composite<false><<<grid2d(rc.width, rc.height), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
+            E->launches++;
+            continue;
+        }
         launch_frame_entries(E, rc, rf, ac);
         uint32_t *px0 = E->blob_px, *pxo = E->blob_px + cv;
         uint8_t *layer0 = (uint8_t *) (E->blob_px + cv + E->ovf_cap), *layero = layer0 + cv;
-        if (E->nchains == 1)
+        if (single)
             k_composite<true><<<div_up(np, 256), 256, 0, E->stream>>>(ac, rc, rf.y, px0, layer0, pxo, layero, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
         else
             k_composite<false><<<div_up(np, 256), 256, 0, E->stream>>>(ac, rc, rf.y, px0, layer0, pxo, layero, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
@@ -649,7 +770,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     }
     if (E->check("render")) rcode = AMX_ERR_CUDA;
     dev_free(d_bg);
-    if (rcode == AMX_OK && E->nchains > 1 && !out_is_device) {
+    if (rcode == AMX_OK && E->nchains > 1 && !out_is_device && E->d_ovf_used) {
         uint32_t used = 0;
         cudaMemcpy(&used, E->d_ovf_used, 4, cudaMemcpyDeviceToHost);
         cudaMemsetAsync(E->d_ovf_used, 0, 4, E->stream);
@@ -703,6 +824,7 @@ int engine_render_blob(Engine *E, uint32_t blob, double t, uint64_t cap, uint16_
     if (it == E->chain_key.end()) return AMX_OK;        // reference returns nullptr
     uint32_t c = (uint32_t) (it - E->chain_key.begin());
     if (!E->render_ready) { int rcode = engine_render_prepare(E); if (rcode != AMX_OK) return rcode; }
+    { int rcode = ensure_entries(E); if (rcode != AMX_OK) return rcode; }
     RConst rc = make_rconst(E);
     Acc ac = make_acc(E);
     RFrame rf = make_rframe(E, time, f, tl);

@@ -103,6 +103,7 @@ def lib():
     sig("amref_fluid_get_particles", None, vp, u64, vp)
     sig("amref_fluid_step", None, vp, u64, f64, f64)
     sig("amref_fluid_get_nodes", None, vp, vp)
+    sig("amref_morph_fluid_sanitize", None, vp)
     sig("amref_morph_fluid_count", u64, vp)
     sig("amref_morph_fluid_get", None, vp, u64, vp)
     sig("amref_morph_fluid_dims", None, vp, vp)
@@ -330,6 +331,9 @@ class RefMorph:
     def time_render(self, t):
         out = np.zeros((self.height, self.width), dtype=np.uint32)
         return self.L.amref_time_render(self.h, float(t), _p(out)), out
+
+    def fluid_sanitize(self):
+        self.L.amref_morph_fluid_sanitize(self.h)
 
     def fluid_particles(self):
         n = self.L.amref_morph_fluid_count(self.h)

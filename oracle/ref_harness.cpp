@@ -397,7 +397,20 @@ unsigned amref_hardware_concurrency() { return std::thread::hardware_concurrency
 // 0 x 1 y 2 u 3 v 4 gravity_x 5 gravity_y 6 freedom_r 7 active 8 mature 9 R 10 G 11 B 12 A 13 r 14 g 15 b 16 a
 // 17 strength 18 source_owner 19 frame_key 20 source_pos 21 destination_pos 22 cx 23 cy
 enum { FP_STRIDE = 24 };
-void *amref_fluid_create(unsigned gx, unsigned gy, unsigned n) { return new FluidModel(gx, gy, n); }
+// Node::Node() leaves r,g,b,a,weight uninitialised (fluidmodel.cpp:58-69) and Node::clear() only runs for
+// nodes already on the active list, so a node's FIRST activation reads whatever new[] returned.  Fresh
+// large allocations are zero pages, small ones are recycled heap: give every node the cleared state the
+// algorithm assumes, so single-step comparisons are deterministic.
+static void sanitize_nodes(FluidModel *fm) {
+    for (unsigned i = 0; i < fm->gsizeX; ++i)
+        for (unsigned j = 0; j < fm->gsizeY; ++j) if (!fm->grid[i][j].active) fm->grid[i][j].clear();
+}
+void *amref_fluid_create(unsigned gx, unsigned gy, unsigned n) {
+    FluidModel *fm = new FluidModel(gx, gy, n);
+    sanitize_nodes(fm);
+    return fm;
+}
+void amref_morph_fluid_sanitize(void *h) { am::morph &m = R(h)->m; if (m.fluid) sanitize_nodes(m.fluid); }
 void amref_fluid_destroy(void *f) { delete reinterpret_cast<FluidModel *>(f); }
 static void put_particles(FluidModel *f, uint64_t n, const double *rec) {
     Particle *ps = f->getParticles();

@@ -81,7 +81,7 @@ def test_chain_build_matches_reference_without_duplicates(reflib):
     images[1] = np.roll(images[0], 3, axis=1)       # same pixel count in both frames
     m = build_ref(reflib, images, seed=1)
     ref = m.chains()
-    e = eng.Engine(0, seed=1)
+    e = eng.Engine(0, seed=1, threads=0, cycle_length=0)
     e.load_images(images)
     e.step(8)
     assert e.state() == eng.STATE_ATOM_MORPHING
@@ -96,7 +96,7 @@ def test_chain_build_with_duplicates_and_volatile(reflib):
     images[2][...] = 0                                # empty key frame -> volatile blob
     m = build_ref(reflib, images, seed=1, density=2)
     ref = m.chains()[0]
-    e = eng.Engine(0, seed=1, density=2)
+    e = eng.Engine(0, seed=1, density=2, threads=0, cycle_length=0)
     e.load_images(images)
     e.step(8)
     got = e.chains()[0]
