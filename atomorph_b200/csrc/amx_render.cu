@@ -292,6 +292,54 @@ __device__ __forceinline__ void resolve_position(const uint32_t *__restrict__ he
     }
 }
 
+// exact round(num/den) (half up) for num < 2^40, den < 2^31, quotient <= 255: float estimate + integer fix-up.
+// *tie is set when num/den is an exact .5 tie (the only place where the reference's double sums can differ).
+__device__ __forceinline__ uint32_t rdiv_small(unsigned long long num, unsigned long long den, bool *tie) {
+    unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
+    uint32_t q = (uint32_t) __fmul_rz(__ull2float_rz(n2), __frcp_rz(__ull2float_ru(d2)));   // every step rounds down: never above the true quotient
+    unsigned long long rem = n2 - (unsigned long long) q * d2;
+    while (rem >= d2) { rem -= d2; ++q; }
+    *tie |= (rem == 0ull);
+    return q;
+}
+
+// FAST PATH of the fused gather: one chain at the position and no exact tie -> integer sums, no sort, no
+// per-contribution double math.  Returns false when the generic ordered replay is needed.
+template <bool SINGLE>
+__device__ __forceinline__ bool resolve_fast(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
+                                             const uint32_t *__restrict__ chain_of, uint32_t px, uint32_t py, uint32_t *chain_out,
+                                             uint32_t *px_out, bool *empty) {
+    unsigned long long R = 0, G = 0, B = 0, Av = 0;
+    uint32_t N = 0, cnt = 0, chain = 0xffffffffu;
+    bool mixed = false;
+    visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+        if (!SINGLE) {
+            uint32_t c = chain_of[a];
+            if (chain == 0xffffffffu) chain = c;
+            else if (c != chain) mixed = true;
+        }
+        R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
+    });
+    *empty = (cnt == 0);
+    if (cnt == 0) return true;
+    if (mixed || cnt > 30000u) return false;       // N = sum(n) must stay below 2^31
+    bool tie = false;
+    uint32_t r = rdiv_small(R, N, &tie), g = rdiv_small(G, N, &tie), b = rdiv_small(B, N, &tie), a;
+    if (rc.density == 0) a = 0;
+    else if (cnt >= rc.density) a = rdiv_small(Av, N, &tie);
+    else {
+        unsigned long long num = Av * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
+        unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
+        unsigned long long q = n2 / d2;
+        tie |= (n2 - q * d2 == 0ull);
+        a = (uint32_t) q;
+    }
+    if (tie) return false;
+    *chain_out = SINGLE ? 0u : chain;
+    *px_out = c_make(r, g, b, a);
+    return true;
+}
+
 // fused gather + composite (feather == 0): one thread per OUTPUT pixel
 template <bool SINGLE>
 __global__ void __launch_bounds__(256)
@@ -303,10 +351,22 @@ k_gather_composite(const uint32_t *__restrict__ head, const uint4 *__restrict__ 
     if (px >= rc.width || py >= rc.height) return;
     size_t i = (size_t) py * rc.width + px;
     uint32_t bgc = rc.keep_background ? bg[i] : 0u;
+    uint32_t chain = 0, pxl = 0;
+    bool empty = false;
+    if (resolve_fast<SINGLE>(head, rec, rc, chain_of, px, py, &chain, &pxl, &empty)) {
+        if (empty) { out[i] = bgc; return; }
+        uint32_t col = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
+        if (!rc.keep_background) { out[i] = c_a(col) ? col : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
+        Over ov;
+        ov.add(col);
+        out[i] = ov.finish(bgc, true);
+        return;
+    }
+    // generic path: several blobs at the position, an exact tie, or a very long list
     const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
     Over ov;
-    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t chain, uint32_t pxl) {
-        ov.add(entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct));
+    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t ch, uint32_t p) {
+        ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
     });
     out[i] = ov.finish(bgc, rc.keep_background != 0);
 }

@@ -1,0 +1,118 @@
+"""The am::morph drop-in (include/atomorph/morph.h) driven like the reference's only in-tree caller
+(demo/main.cpp:215-298), through the flat C wrappers.  Compared stage by stage with the reference."""
+import numpy as np
+import pytest
+
+from atomorph_b200 import engine as eng
+from atomorph_b200 import scenes
+from atomorph_b200.morph import Morph
+from helpers import build_ref, diff_stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _drive(m, target, max_rounds=200):
+    """suspend(); synchronize(); iterate() until the state is reached -- the demo's loop with iterate."""
+    for _ in range(max_rounds):
+        m.suspend()
+        assert m.synchronize(), m.last_error()
+        if m.get_state() >= target:
+            return
+        if m.get_state() == eng.STATE_BLOB_MATCHING and m.get_blob_count() > 0:
+            m.next_state()
+            m.synchronize()
+        m.iterate(4)
+        m.wait()
+    raise AssertionError("state %d never reached" % target)
+
+
+def test_full_pipeline_through_facade(reflib):
+    images = scenes.ellipses(48, 2, seed=7)
+    m = Morph()
+    m.set_seed(1)
+    m.set_motion(eng.SPLINE)
+    m.set_fading(eng.COSINE)
+    m.set_threads(0)
+    m.set_cycle_length(0)
+    for k, im in enumerate(images):
+        m.add_image(k, im)
+    m.set_resolution(48, 48)
+    assert m.get_frame_count() == 2
+    assert m.get_pixel_count(0) == int((images[0][..., 3] != 0).sum())
+    _drive(m, eng.STATE_ATOM_MORPHING)
+    assert m.get_blob_count(0) == 1 and m.get_blob_count() == 2
+
+    ref = build_ref(reflib, images, seed=1, motion=eng.SPLINE, fading=eng.COSINE)
+    # ingest parity: stored/fetch round trip, averages
+    for pos in (20 * 65536 + 20, 24 * 65536 + 30, 0):
+        assert m.get_pixel(0, pos) == ref.L.amref_get_pixel(ref.h, 0, pos)
+    assert m.get_average_pixel(0) == ref.average_pixel(0)
+    rb = ref.blobs(0)[0]
+    b = m.get_blob(0, 0)
+    assert np.array_equal(b["surface"], rb["surface"])
+    assert np.allclose(b["stats"], rb["stats"], atol=1e-9, rtol=0)
+
+    # matching through iterate(): cost falls, and stays within 1% of the reference given the same budget
+    W = int((images[0][..., 3] != 0).sum())
+    m.set_cycle_length(W)
+    m.suspend(); m.synchronize()
+    e0 = m.get_energy()
+    m.iterate(1500)
+    m.wait()
+    m.suspend(); m.synchronize()
+    e1 = m.get_energy()
+    assert e1 < e0
+    ref.set(cycle_length=W)
+    ref.sync()
+    assert ref.true_cost() == e0           # identical initial table -> identical initial cost
+    ref.iterate(1500)
+    ref.sync()
+    assert e1 <= 1.01 * ref.true_cost()
+
+    # rendering through get_pixels(t): feed OUR table to the reference and compare bit for bit
+    from atomorph_b200.engine import Engine
+    ctx = m.device_context()
+    e = Engine.__new__(Engine)
+    e.L = m.L; e.h = ctx
+    chains = Engine.chains(e)
+    ref2 = reflib.RefMorph(seed=1, motion=eng.SPLINE, fading=eng.COSINE)
+    for k, im in enumerate(images):
+        ref2.add_image(k, im)
+    ref2.set_resolution(48, 48)
+    for k in range(2):
+        ref2.import_blobs(k, [m.get_blob(k, 0)])
+    for c in chains:
+        ref2.import_chain(c["key"], c["words"], c["max_surface"])
+    ref2.finish_import()
+    for f in range(8):
+        t = m.get_time(f, 8)
+        assert t == ref2.get_time(f, 8)
+        n, mx = diff_stats(ref2.render(t), m.get_pixels(t))
+        assert (n, mx) == (0, 0)
+    e.h = None
+
+
+def test_facade_setters_restart_and_errors(reflib):
+    images = scenes.ellipses(32, 2, seed=3)
+    m = Morph()
+    assert m.get_frame_key(0.3) == 2 ** 64 - 1          # SIZE_MAX without frames (morph.cpp:414)
+    assert m.get_pixel(0, 5) == 0                        # transparent pixel from the void
+    assert m.add_frame(0) and not m.add_frame(0)         # false if the frame exists (morph.cpp:288)
+    for k, im in enumerate(images):
+        m.add_image(k, im)
+    m.set_resolution(32, 32)
+    m.set_cycle_length(10)
+    _drive(m, eng.STATE_ATOM_MORPHING)
+    m.set_density(2)                                     # identifier change -> full restart at synchronize
+    m.suspend()
+    assert m.synchronize()
+    assert m.get_state() == eng.STATE_BLOB_DETECTION
+    _drive(m, eng.STATE_ATOM_MORPHING)
+    m.compute()
+    assert not m.synchronize()                           # busy -> false (morph.cpp:103)
+    m.suspend()
+    assert m.synchronize()
+    m.next_state()
+    m.synchronize()
+    m.iterate(1); m.wait(); m.suspend(); m.synchronize()
+    assert m.get_state() == eng.STATE_DONE
