@@ -62,19 +62,27 @@ def test_full_pipeline_through_facade(reflib):
     m.suspend(); m.synchronize()
     e1 = m.get_energy()
     assert e1 < e0
-    ref.set(cycle_length=W)
-    ref.sync()
-    assert ref.true_cost() == e0           # identical initial table -> identical initial cost
-    ref.iterate(1500)
-    ref.sync()
-    assert e1 <= 1.01 * ref.true_cost()
+    # The duplicate atoms of the smaller frame are RNG-placed (a different RNG on each side), which moves the
+    # OPTIMUM itself by several percent at this tiny size, so the yardstick here is the exact optimal assignment
+    # of our own table (scipy LSA); "within 1% of the reference on the same table" is tests/test_swap_gpu.py.
+    from atomorph_b200.engine import Engine
+    from scipy.optimize import linear_sum_assignment
+    e = Engine.__new__(Engine)
+    e.L = m.L; e.h = m.device_context()
+    chains = Engine.chains(e)
+    t = chains[0]["words"]
+
+    def xy256(c):
+        return (256 * (c & 0xffff).astype(np.int64) + ((c >> 32) & 255).astype(np.int64),
+                256 * ((c >> 16) & 0xffff).astype(np.int64) + ((c >> 40) & 255).astype(np.int64))
+    x0, y0 = xy256(t[0]); x1, y1 = xy256(t[1])
+    cost = (x0[:, None] - x1[None, :]) ** 2 + (y0[:, None] - y1[None, :]) ** 2
+    ri, ci = linear_sum_assignment(cost)
+    c_opt = 2.0 * cost[ri, ci].sum()
+    assert e1 <= 1.01 * c_opt, (e1, c_opt)
+    assert e1 == 2.0 * ((x0 - x1) ** 2 + (y0 - y1) ** 2).sum()      # get_energy() is the true cost of the table
 
     # rendering through get_pixels(t): feed OUR table to the reference and compare bit for bit
-    from atomorph_b200.engine import Engine
-    ctx = m.device_context()
-    e = Engine.__new__(Engine)
-    e.L = m.L; e.h = ctx
-    chains = Engine.chains(e)
     ref2 = reflib.RefMorph(seed=1, motion=eng.SPLINE, fading=eng.COSINE)
     for k, im in enumerate(images):
         ref2.add_image(k, im)
