@@ -60,6 +60,7 @@ def lib():
     sig("amref_energy", f64, vp)
     sig("amref_best_blob_energy", f64, vp)
     sig("amref_worker_values", None, vp, vp)
+    sig("amref_e1_state", u64, vp)
     sig("amref_run_until", C.c_uint, vp, C.c_uint, u64, u64)
     sig("amref_true_cost", f64, vp)
     sig("amref_frame_count", u64, vp)
@@ -196,6 +197,9 @@ class RefMorph:
         self.L.amref_worker_values(self.h, _p(out))
         return dict(zip(("blob_map_e", "best_e", "best_blob_map_e", "bbox_d", "blob_map_w", "blob_map_h", "counter",
                          "w_rgba", "w_size", "w_xy"), out))
+
+    def e1_state(self):
+        return int(self.L.amref_e1_state(self.h))
 
     def best_blob_energy(self):
         return self.L.amref_best_blob_energy(self.h)

@@ -30,6 +30,8 @@
 #include <future>
 #include <limits>
 #include <iostream>
+#include <sstream>
+#include <string>
 
 #define private public
 #include "atomorph.h"
@@ -125,6 +127,15 @@ void amref_worker_values(void *h, double *out10) {
     out10[0] = w.blob_map_e; out10[1] = w.best_e; out10[2] = w.best_blob_map_e; out10[3] = w.bbox_d;
     out10[4] = (double) w.blob_map_w; out10[5] = (double) w.blob_map_h; out10[6] = (double) w.counter;
     out10[7] = w.blob_rgba_weight; out10[8] = w.blob_size_weight; out10[9] = w.blob_xy_weight;
+}
+
+// state of the worker's std::default_random_engine (minstd_rand0: one integer), for exact replays
+uint64_t amref_e1_state(void *h) {
+    // x_{n+1} = 16807 x_n mod (2^31-1): read the next output of a COPY and step it back (no iostreams: this
+    // library carries a static libstdc++ whose stream locale is not initialised inside a dlopen'ed object)
+    std::default_random_engine probe = R(h)->m.worker.e1;
+    const uint64_t mod = 2147483647ull, inv = 1407677000ull;     // 16807 * inv = 1 (mod 2^31-1)
+    return ((uint64_t) probe() * inv) % mod;
 }
 
 // Drive the pre-stages deterministically until the state reaches `target`.
