@@ -107,6 +107,57 @@ k_swap_multi(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
     warp_add_stats(stats, prop, acc, gain);
 }
 
+// ---- multi-GPU atom-range sharding (h = 2: a single free column) ----------------------
+// An EPOCH fixes `sel_mask` (log2 N index bits): rank r owns the atoms whose selected bits equal r and only
+// draws pairing masks with zeros on those bits, so every pair stays inside the rank's slice.  Between epochs
+// the owned slices are exchanged with one all-gather of the column (pack -> NCCL -> unpack).
+__device__ __forceinline__ uint64_t deposit_bits(uint64_t u, uint64_t free_mask) {     // software pdep
+    uint64_t out = 0;
+    while (free_mask) {
+        uint64_t bit = free_mask & (~free_mask + 1);
+        if (u & 1ull) out |= bit;
+        u >>= 1;
+        free_mask &= free_mask - 1;
+    }
+    return out;
+}
+
+// thread t enumerates the owned pairs: free-bit index with a zero inserted at the (free) position of m's top bit
+__global__ void __launch_bounds__(256)
+k_swap_sharded(pword *__restrict__ col, const pword *__restrict__ prev, const pword *__restrict__ next, int h2, uint64_t off, uint64_t w,
+               uint64_t m, unsigned top_free_pos, uint64_t free_mask, uint64_t sel_val, uint64_t npairs, unsigned long long *__restrict__ stats) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned prop = 0, acc = 0;
+    unsigned long long gain = 0;
+    if (t < npairs) {
+        uint64_t l = deposit_bits(insert_zero_bit(t, top_free_pos), free_mask) | sel_val;
+        uint64_t r = l ^ m;
+        if (l < w && r < w) {
+            prop = 1;
+            acc = propose(col, prev, next, h2 != 0, off + l, off + r, &gain) ? 1u : 0u;
+        }
+    }
+    warp_add_stats(stats, prop, acc, gain);
+}
+
+// owned atoms of a column <-> contiguous buffer (slot u of rank r = atom deposit(u, free_mask) | r's bits)
+__global__ void __launch_bounds__(256)
+k_pack_owned(const pword *__restrict__ col, uint64_t off, uint64_t w, uint64_t free_mask, uint64_t sel_val, uint64_t n, pword *__restrict__ out) {
+    uint64_t u = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    uint64_t l = deposit_bits(u, free_mask) | sel_val;
+    out[u] = l < w ? col[off + l] : 0ull;
+}
+__global__ void __launch_bounds__(256)
+k_unpack_owned(pword *__restrict__ col, uint64_t off, uint64_t w, uint64_t free_mask, uint64_t sel_mask, uint64_t n, uint32_t nranks,
+               const pword *__restrict__ in) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * nranks) return;
+    uint64_t r = i / n, u = i % n;
+    uint64_t l = deposit_bits(u, free_mask) | deposit_bits(r, sel_mask);
+    if (l < w) col[off + l] = in[i];
+}
+
 // cost partial sums: sum_j d(p[x][j], p[x][j+1 mod h]) over atoms of chains with width > 1 (thread.cpp:1109-1125)
 __global__ void __launch_bounds__(256)
 k_cost(const pword *__restrict__ table, const uint32_t *__restrict__ chain_of, const uint64_t *__restrict__ chain_off, uint64_t A,
@@ -164,6 +215,42 @@ int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds
     return E->check("swap rounds") ? AMX_ERR_CUDA : AMX_OK;
 }
 
+static bool shard_geometry(Engine *E, uint32_t chain, uint64_t sel_mask, unsigned *k, uint64_t *free_mask) {
+    uint64_t w = E->chain_off[chain + 1] - E->chain_off[chain];
+    if (w < 2) return false;
+    *k = 0;
+    while ((1ull << *k) < w) ++*k;
+    uint64_t all = (1ull << *k) - 1ull;
+    if (sel_mask & ~all) return false;
+    *free_mask = all & ~sel_mask;
+    return *free_mask != 0;
+}
+
+int engine_swap_rounds_sharded(Engine *E, uint32_t chain, int32_t column, uint64_t rounds, uint64_t sel_mask, uint64_t sel_val) {
+    if (E->nchains == 0 || E->h < 2 || chain >= E->nchains || column >= (int32_t) E->h) return AMX_ERR_ARG;
+    unsigned k; uint64_t free_mask;
+    if (!shard_geometry(E, chain, sel_mask, &k, &free_mask) || (sel_val & ~sel_mask)) return AMX_ERR_ARG;
+    unsigned nfree = __builtin_popcountll(free_mask);
+    uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    bool h2 = E->h == 2;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        uint64_t round = E->rng_round++;
+        uint32_t y = column >= 0 ? (uint32_t) column : (uint32_t) (rng64(E->p.seed, 0xc01u, round) % E->h);
+        uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
+        // mask: uniform over the non-zero values of the free bits
+        uint64_t mfree = 1ull + rng64(E->p.seed ^ sel_val, 0x5157u + chain, round) % ((1ull << nfree) - 1ull);
+        unsigned top_free_pos = 63 - __builtin_clzll(mfree);
+        uint64_t m = 0, fm = free_mask, bits = mfree;
+        while (fm) { uint64_t bit = fm & (~fm + 1); if (bits & 1ull) m |= bit; bits >>= 1; fm &= fm - 1; }
+        uint64_t npairs = 1ull << (nfree - 1);
+        k_swap_sharded<<<div_up(npairs, 256), 256, 0, E->stream>>>(E->table + (size_t) y * E->A, E->table + (size_t) yp * E->A, E->table + (size_t) yn * E->A,
+                                                                  h2, off, w, m, top_free_pos, free_mask, sel_val, npairs, (unsigned long long *) E->d_swapstats);
+        E->launches++;
+    }
+    E->render_ready = false;
+    return E->check("sharded swap rounds") ? AMX_ERR_CUDA : AMX_OK;
+}
+
 int engine_cost(Engine *E, double *cost) {
     *cost = 0.0;
     if (E->nchains == 0 || E->A == 0) return AMX_OK;
@@ -209,6 +296,38 @@ int amx_swap_stats(amx_ctx *ctx, uint64_t stats3[3]) {
         return AMX_ERR_CUDA;
     for (int i = 0; i < 3; ++i) stats3[i] = E->swapstats[i];
     return AMX_OK;
+}
+
+int amx_swap_rounds_sharded(amx_ctx *ctx, uint32_t chain, int32_t column, uint64_t rounds, uint64_t sel_mask, uint64_t sel_val) {
+    if (!ctx) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    return engine_swap_rounds_sharded(&ctx->e, chain, column, rounds, sel_mask, sel_val);
+}
+
+int amx_pack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint64_t sel_val, void *d_out, uint64_t *count) {
+    if (!ctx || !d_out || chain >= ctx->e.nchains || column >= ctx->e.h) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    unsigned k; uint64_t free_mask;
+    if (!shard_geometry(E, chain, sel_mask, &k, &free_mask)) return AMX_ERR_ARG;
+    uint64_t n = 1ull << __builtin_popcountll(free_mask), off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    k_pack_owned<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, w, free_mask, sel_val, n, (pword *) d_out);
+    E->launches++;
+    if (count) *count = n;
+    return E->check("pack owned") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+int amx_unpack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint32_t nranks, const void *d_in) {
+    if (!ctx || !d_in || chain >= ctx->e.nchains || column >= ctx->e.h) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    unsigned k; uint64_t free_mask;
+    if (!shard_geometry(E, chain, sel_mask, &k, &free_mask) || nranks != (1u << __builtin_popcountll(sel_mask))) return AMX_ERR_ARG;
+    uint64_t n = 1ull << __builtin_popcountll(free_mask), off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    k_unpack_owned<<<div_up(n * nranks, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, w, free_mask, sel_mask, n, nranks, (const pword *) d_in);
+    E->launches++;
+    E->render_ready = false;
+    return E->check("unpack owned") ? AMX_ERR_CUDA : AMX_OK;
 }
 
 int amx_cost(amx_ctx *ctx, double *cost) {

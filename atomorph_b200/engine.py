@@ -241,6 +241,17 @@ class Engine:
         self._ck(self.L.amx_swap_rounds(self.h, chain, column, int(rounds), _p(st) if want_stats else None), "swap_rounds")
         return st
 
+    def swap_rounds_sharded(self, rounds, sel_mask, sel_val, chain=0, column=-1):
+        self._ck(self.L.amx_swap_rounds_sharded(self.h, chain, column, int(rounds), int(sel_mask), int(sel_val)), "swap_rounds_sharded")
+
+    def pack_owned(self, column, sel_mask, sel_val, d_out_ptr, chain=0):
+        n = C.c_uint64(0)
+        self._ck(self.L.amx_pack_owned(self.h, chain, column, int(sel_mask), int(sel_val), C.c_void_p(d_out_ptr), C.byref(n)), "pack_owned")
+        return int(n.value)
+
+    def unpack_owned(self, column, sel_mask, nranks, d_in_ptr, chain=0):
+        self._ck(self.L.amx_unpack_owned(self.h, chain, column, int(sel_mask), int(nranks), C.c_void_p(d_in_ptr)), "unpack_owned")
+
     def swap_stats(self):
         st = np.zeros(3, dtype=np.uint64)
         self._ck(self.L.amx_swap_stats(self.h, _p(st)), "swap_stats")

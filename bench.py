@@ -228,6 +228,7 @@ def run_b200(args):
     P = size * size
     e.swap_rounds(256, want_stats=False)          # leave the trivial initial table behind
     e.render_prepare()
+    e.sync()
 
     # weak scaling: rank r renders frames [r*F, (r+1)*F) of an (F*world)-frame morph
     total_frames = F * world
@@ -243,8 +244,15 @@ def run_b200(args):
     def render_step():
         e.render_into(times, out.data_ptr(), True)
 
+    from atomorph_b200 import dist as amd
+    if world > 1:
+        amd.broadcast_table(e, rank, world, dev)                 # every rank renders / refines the same table
+        e.render_prepare()
+    matcher = amd.ShardedMatcher(e, rank, world, device=dev, seed=1)
+
     def swap_step():
-        e.swap_rounds(SWAP_ROUNDS, want_stats=False)
+        # weak scaling: every rank proposes SWAP_ROUNDS * W/2 pairs per step on its atom slice, then ONE all-gather
+        matcher.run_epoch(SWAP_ROUNDS * world, column=1)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -316,7 +324,7 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2 synthetic %dx%d RGBA, 2 key frames, %d atoms, spline+cosine, %d frames per GPU" % (size, size, A, F),
                    "l2": "256 MB buffer written between timed steps", "step": "render %d frames; swap: %d rounds" % (F, SWAP_ROUNDS),
-                   "parallelism": "frame-range x%d" % world},
+                   "parallelism": "frames: frame-range x%d; swap: atom-range x%d + 1 all-gather/step" % (world, world)},
         "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None,
                      "peak_kind": peak_kind, "kernel": "k_splat+k_resolve+k_composite (per frame)",
                      "bytes_per_unit": render_bytes, "unit_name": "frame"},

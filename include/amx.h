@@ -110,6 +110,13 @@ int  amx_table_device_ptr(amx_ctx *ctx, uint32_t column, void **d_ptr, uint64_t 
  * column < 0) of chain `chain` (or all chains when chain < 0).  stats3 += proposals, accepted, gain. */
 int  amx_swap_rounds(amx_ctx *ctx, int32_t chain, int32_t column, uint64_t rounds, uint64_t stats3[3]);
 int  amx_swap_stats(amx_ctx *ctx, uint64_t stats3[3]);           /* cumulative since init / import  */
+/* Multi-GPU atom-range sharding of one column: only atoms whose index bits under
+ * `sel_mask` equal `sel_val` are paired, with pairing masks that are zero on those bits.  amx_pack_owned copies
+ * the owned atoms of a column into a contiguous device buffer (count = 2^(free bits)), amx_unpack_owned scatters
+ * the all-gathered buffers of `nranks` = 2^popcount(sel_mask) ranks (rank-major) back into the column. */
+int  amx_swap_rounds_sharded(amx_ctx *ctx, uint32_t chain, int32_t column, uint64_t rounds, uint64_t sel_mask, uint64_t sel_val);
+int  amx_pack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint64_t sel_val, void *d_out, uint64_t *count);
+int  amx_unpack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint32_t nranks, const void *d_in);
 int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_energy(chain*), thread.cpp:1109-1125, summed over chains */
 
 /* ---- K6 renderer (row a-R): morph::get_pixels / draw_atoms, morph.cpp:452-678, 1302-1421 ------- */

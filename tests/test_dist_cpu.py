@@ -1,0 +1,105 @@
+"""Host-side logic of the multi-GPU partitioning (atomorph_b200/dist.py) on CPU: index arithmetic, and a
+world_size-2 gloo run of the atom-range sharded epoch (numpy stand-in for the device rounds)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from atomorph_b200 import dist as amd
+
+
+def test_frame_ranges_cover_exactly():
+    for total in (1, 7, 64, 512):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                a, b = amd.frame_range(total, r, world)
+                seen += list(range(a, b))
+            assert seen == list(range(total))
+    t = np.concatenate([amd.frame_times(64, r, 4) for r in range(4)])
+    assert np.array_equal(t, np.arange(64) / 64.0)
+
+
+def test_owned_columns_partition_each_parity():
+    for h in (4, 5, 8):
+        for world in (1, 2, 4):
+            for parity in (0, 1):
+                cols = sorted(sum((amd.owned_columns(h, parity, r, world) for r in range(world)), []))
+                assert all(c % 2 == parity for c in cols)
+                # no two columns refined together are cyclic neighbours
+                for a in cols:
+                    for b in cols:
+                        assert a == b or (abs(a - b) % h not in (1, h - 1))
+
+
+@pytest.mark.parametrize("width", [1 << 10, 1000, 37])
+def test_owned_atoms_partition_the_chain(width):
+    for world in (2, 4, 8):
+        if world >= width:
+            continue
+        for epoch in range(5):
+            mask = amd.select_mask(width, world, epoch, seed=3)
+            assert bin(mask).count("1") == world.bit_length() - 1
+            allidx = np.concatenate([amd.owned_atoms(width, mask, r)[0] for r in range(world)])
+            k = int(width - 1).bit_length()
+            assert np.array_equal(np.sort(allidx), np.arange(1 << k, dtype=np.uint64))
+            for r in range(world):
+                idx, val = amd.owned_atoms(width, mask, r)
+                assert np.all((idx & np.uint64(mask)) == np.uint64(val))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, width, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    column = rng.integers(0, 2 ** 48, width, dtype=np.uint64)       # identical on both ranks
+    other = rng.integers(0, 2 ** 20, width, dtype=np.uint64)
+    original = column.copy()
+    for epoch in range(3):
+        mask = amd.select_mask(width, world, epoch, seed=9)
+        idx, val = amd.owned_atoms(width, mask, rank)
+        ok = idx < width
+        # stand-in for the device rounds: sort the owned slots by a key (any permutation inside the slice)
+        own = idx[ok].astype(np.int64)
+        vals = column[own]
+        order = np.argsort(other[own] ^ np.uint64(epoch), kind="stable")
+        column[own] = vals[order]
+        send = np.zeros(len(idx), dtype=np.int64)
+        send[ok] = column[own].astype(np.int64)
+        recv = [torch.zeros(len(idx), dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(recv, torch.from_numpy(send))
+        column = amd.scatter_gathered(column, [r.numpy().astype(np.uint64) for r in recv], width, mask, world)
+    q.put((rank, column, original))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("width", [256, 200])
+def test_sharded_epoch_world2_gloo(width):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, width, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        rank, col, orig = q.get(timeout=120)
+        res[rank] = (col, orig)
+    for p in procs:
+        p.join(timeout=60)
+    assert np.array_equal(res[0][0], res[1][0]), "ranks disagree after the all-gather"
+    assert np.array_equal(np.sort(res[0][0]), np.sort(res[0][1])), "a key point was lost or duplicated"
+    assert not np.array_equal(res[0][0], res[0][1])

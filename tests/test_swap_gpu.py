@@ -73,3 +73,44 @@ def test_multi_chain_sweep(reflib):
     assert c1 <= c0
     for b, a in zip(befores, e.chains()):
         assert _rows_are_permutation(b, a["words"])
+
+
+def test_sharded_rounds_and_pack_unpack(reflib):
+    """Atom-range sharding on ONE GPU: the slices of 2 (and 4) virtual ranks are refined one after the other on the
+    same table (what the ranks do concurrently on their own copies), then packed, concatenated like an
+    all-gather and unpacked into a second engine."""
+    import torch
+    from atomorph_b200 import dist as amd
+    images = scenes.ellipses(40, 2, seed=50)
+    m = build_ref(reflib, images, seed=1)
+    e = engine_from_ref(m, images, seed=1)
+    e2 = engine_from_ref(m, images, seed=1)
+    before = e.chains()[0]["words"].copy()
+    W = before.shape[1]
+    c0 = e.cost()
+    for world in (2, 4):
+        for epoch in range(6):
+            mask = amd.select_mask(W, world, epoch, seed=1)
+            sends = []
+            for r in range(world):
+                idx, val = amd.owned_atoms(W, mask, r)
+                st0 = e.swap_stats()
+                e.swap_rounds_sharded(50, mask, val, chain=0, column=1)
+                assert int(e.swap_stats()[0] - st0[0]) > 0
+                buf = torch.empty(len(idx), dtype=torch.int64, device="cuda")
+                torch.cuda.synchronize()
+                n = e.pack_owned(1, mask, val, buf.data_ptr())
+                e.sync()
+                assert n == len(idx)
+                col = e.chains()[0]["words"][1]
+                ok = idx < W
+                assert np.array_equal(buf.cpu().numpy().astype(np.uint64)[ok], col[idx[ok].astype(np.int64)])
+                sends.append(buf)
+            gathered = torch.cat(sends)
+            torch.cuda.synchronize()
+            e2.unpack_owned(1, mask, world, gathered.data_ptr())
+            e2.sync()
+            assert np.array_equal(e2.chains()[0]["words"][1], e.chains()[0]["words"][1])
+    after = e.chains()[0]["words"]
+    assert _rows_are_permutation(before, after)
+    assert e.cost() < c0
