@@ -19,21 +19,33 @@
  * Algorithmic bytes per proposal: 32 B (h = 2) or 48 B (h >= 3) read,
  * +16 B written per accepted swap.
  */
+#include <algorithm>
 #include "amx_engine.h"
 
 namespace amx {
 
 struct SwapStats { unsigned long long proposals, accepted, gain; };
 
+// proposals / accepted / gain: warp shuffle, then shared memory, then ONE set of atomics per block
+// (same-address atomics serialise in L2 at about one per clock: per-warp atomics used to dominate a round)
 __device__ __forceinline__ void warp_add_stats(unsigned long long *stats, unsigned prop, unsigned acc, unsigned long long gain) {
+    __shared__ unsigned s_prop[8], s_acc[8];
+    __shared__ unsigned long long s_gain[8];
     for (int o = 16; o > 0; o >>= 1) {
         prop += __shfl_down_sync(0xffffffffu, prop, o);
         acc += __shfl_down_sync(0xffffffffu, acc, o);
         gain += __shfl_down_sync(0xffffffffu, gain, o);
     }
-    if ((threadIdx.x & 31) == 0 && prop) {
-        atomicAdd(stats + 0, (unsigned long long) prop);
-        if (acc) { atomicAdd(stats + 1, (unsigned long long) acc); atomicAdd(stats + 2, gain); }
+    unsigned warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_prop[warp] = prop; s_acc[warp] = acc; s_gain[warp] = gain; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned nw = (blockDim.x + 31) >> 5;
+        unsigned p = 0, a = 0;
+        unsigned long long g = 0;
+        for (unsigned i = 0; i < nw; ++i) { p += s_prop[i]; a += s_acc[i]; g += s_gain[i]; }
+        if (p) atomicAdd(stats + 0, (unsigned long long) p);
+        if (a) { atomicAdd(stats + 1, (unsigned long long) a); atomicAdd(stats + 2, g); }
     }
 }
 
@@ -69,15 +81,15 @@ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t t, unsigned b) {
 __global__ void __launch_bounds__(256)
 k_swap_single(pword *__restrict__ col, const pword *__restrict__ prev, const pword *__restrict__ next, int h2, uint64_t off,
               uint64_t w, uint64_t m, unsigned topbit, uint64_t npairs, unsigned long long *__restrict__ stats) {
-    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     unsigned prop = 0, acc = 0;
     unsigned long long gain = 0;
-    if (t < npairs) {
+    for (uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; t < npairs; t += (uint64_t) gridDim.x * blockDim.x) {
         uint64_t l = insert_zero_bit(t, topbit);
         uint64_t r = l ^ m;
         if (r < w) {
-            prop = 1;
-            acc = propose(col, prev, next, h2 != 0, off + l, off + r, &gain) ? 1u : 0u;
+            unsigned long long g1 = 0;
+            prop += 1;
+            if (propose(col, prev, next, h2 != 0, off + l, off + r, &g1)) { acc += 1; gain += g1; }
         }
     }
     warp_add_stats(stats, prop, acc, gain);
@@ -204,7 +216,8 @@ int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds
             uint64_t m = 1ull + rng64(E->p.seed, 0x5157u + c, round) % ((1ull << k) - 1ull);
             unsigned topbit = 63 - __builtin_clzll(m);
             uint64_t npairs = 1ull << (k - 1);
-            k_swap_single<<<div_up(npairs, 256), 256, 0, E->stream>>>(col, prev, next, h2, off, w, m, topbit, npairs, (unsigned long long *) E->d_swapstats);
+            unsigned nb = (unsigned) std::min<uint64_t>(div_up(npairs, 256), 148 * 8);     // persistent: 8 CTAs of 256 threads per SM
+            k_swap_single<<<nb, 256, 0, E->stream>>>(col, prev, next, h2, off, w, m, topbit, npairs, (unsigned long long *) E->d_swapstats);
         } else {
             k_swap_multi<<<div_up(E->A, 256), 256, 0, E->stream>>>(col, prev, next, h2, E->chain_of, E->d_chain_off, E->A, E->p.seed, round,
                                                                  (unsigned long long *) E->d_swapstats);
