@@ -115,14 +115,24 @@ struct Engine {
 
     // render
     bool      render_ready = false;
+    // render inputs per interval, atoms sorted by the tile of their mid-interval position (amx_render.cu: RIn)
     uint32_t *rc1 = nullptr, *rc2 = nullptr;
     double   *rlag = nullptr, *rslope = nullptr;
+    pword    *rpts = nullptr;              // [h][rnpt][A]
+    uint32_t *ratom = nullptr, *rchain = nullptr;
+    uint32_t  rnpt = 0;
+    std::vector<uint32_t> r_live;          // live (drawn) atoms per interval
     int32_t  *d_blob_of_chain = nullptr;   // [h][nchains] blob vector index of chain c in frame y
     uint32_t *d_blob_avg = nullptr;        // [h][nchains] blob2pixel colour (AVERAGE) per frame/chain
     uint32_t *d_blob_distinct = nullptr;   // [nchains]   DISTINCT colour per chain (host mt19937(group))
-    // A-buffer of one frame: list head per canvas position, one record per atom {next, colour, fract}
-    uint32_t *ab_head = nullptr;
-    uint4    *ab_rec = nullptr;
+    // per-pixel A-buffer of one render batch (amx_render.cu): counters, direct record slots, overflow lists
+    uint32_t *ab_cnt = nullptr;
+    uint4    *ab_slots = nullptr;
+    uint32_t *ab_ovf_head = nullptr;
+    uint4    *ab_ovf_rec = nullptr;
+    uint32_t  render_batch = 4;            // frames per scatter/gather launch pair
+    uint32_t *d_bg = nullptr;              // background images of one batch (keep_background)
+    size_t    d_bg_cap = 0;
     // per-(pixel, blob) entries for the feather / per-blob paths (canvas sized + overflow hash)
     int32_t  *acc_owner = nullptr;
     uint8_t  *acc_hasovf = nullptr;

@@ -8,17 +8,22 @@
  *
  *   prepare  (once per table refresh)  per atom & interval: end colours with the one-sided
  *            alpha rule resolved, Perlin lag/slope  -> coalesced SoA, 24 B/atom/interval
- *   scatter  per atom: trajectory (linear / Catmull-Rom in double, reference operation order),
- *            colour fade; the atom is linked into the list of its HOME pixel (top-left splat
- *            target) with ONE 32-bit atomicExch; its 16-byte record {next, colour, fract} is
- *            written at index = atom (coalesced, no allocator)
- *   gather   per pixel: walk the lists of the 4 homes that can reach the pixel, keep the
- *            contributions (atom, colour, integer bilinear numerator n <= 65025), sort them by
- *            blob order and atom index and replay the reference's double sums in ITS order
- *            (morph.cpp:598-613): bit-exact, including the exact .5 ties where an order-free
- *            integer sum would differ by 1 LSB.  Without feather the same thread composites the
- *            blobs "over" each other and blends the background (morph.cpp:1357-1401) and
- *            writes the RGBA pixel: no accumulator ever touches HBM.
+ *   scatter  per atom, for every frame of a BATCH (the key points and end colours are loaded
+ *            once per batch): trajectory (linear / Catmull-Rom in double, reference operation
+ *            order), colour fade; ONE 32-bit atomicAdd on the counter of the atom's HOME pixel
+ *            (top-left splat target) hands out a slot, and the 16-byte record {colour, fract |
+ *            chain, atom} goes straight into that slot of the per-pixel A-buffer (K_SLOTS
+ *            direct slots per pixel, SoA; the rare pixel with more atoms chains the rest
+ *            through an overflow list whose length is known from the counter, so nothing but
+ *            the counters is ever cleared)
+ *   gather   per pixel: read counter + slots of the 4 homes that can reach the pixel (no
+ *            pointer chasing), exact integer sums sum(c*n)/sum(n) with exact rational rounding
+ *            -- provably the reference's double result unless the quotient is an exact .5 tie;
+ *            ties and pixels shared by several blobs sort their contributions by (blob order,
+ *            atom) and replay the reference's double sums in ITS order (morph.cpp:598-613):
+ *            bit-exact.  Without feather the same thread composites the blobs "over" each other
+ *            and blends the background (morph.cpp:1357-1401) and writes the RGBA pixel: no
+ *            accumulator ever touches HBM.
  *   feather  (only when feather > 0) per-(pixel, blob) entries, 4-neighbour erosion layers
  *            (morph.cpp:625-674), then a composite kernel.
  *
@@ -34,12 +39,14 @@
 #include <random>
 #include <numeric>
 #include <algorithm>
+#include <cub/cub.cuh>
 #include "amx_engine.h"
 
 namespace amx {
 
 #define MAXK 32
-#define NIL 0xffffffffu
+#define K_SLOTS 3          // direct A-buffer slots per pixel
+#define RBATCH 4           // frames per launch
 
 struct RConst {
     uint32_t width, height, cw, ch;
@@ -49,6 +56,7 @@ struct RConst {
     uint64_t A;
     uint32_t ovf_mask;     // ovf_cap - 1
     uint32_t feather;
+    uint32_t debug;
 };
 
 struct RFrame {
@@ -57,7 +65,27 @@ struct RFrame {
     double   b1, b2, b3, b4;      // Catmull-Rom basis at the local time
     double   w;                   // c1 / pt1 weight = 1 - local t
     double   str_cos;             // eased weight for COSINE fading (host libm)
-    int32_t  chain_only;          // >= 0: only this chain (per-blob fetch)
+    uint32_t dst;                 // index of the output image this frame is written to
+};
+
+// several frames per launch: the key points and end colours of an atom are loaded once per batch
+struct RBatch {
+    RFrame  f[RBATCH];
+    int32_t chain_only;           // >= 0: only this chain (per-blob fetch)
+};
+
+// Per-pixel A-buffer of one batch slot.  cnt[home] counts the atoms whose top-left splat target is `home`;
+// the first K_SLOTS of them sit in s[k][home], the others hang off ovf_head[home] as a list through
+// ovf_rec[atom].z.  Only cnt is cleared per batch: a list is walked for exactly cnt - K_SLOTS nodes.
+// Record: x = colour, y = x_fract | y_fract << 8 | (chain & 0xffff) << 16, z = atom (direct) / next (overflow).
+struct ABuf {
+    uint32_t *cnt;
+    uint4    *slots;              // [K_SLOTS][RBATCH][canvas]: slot k of batch slot b at slots + k*kstride + b*canvas
+    uint32_t *ovf_head;
+    uint4    *ovf_rec;
+    size_t    canvas;             // stride between batch slots (cnt, slots, ovf_head)
+    size_t    kstride;            // stride between direct slots = RBATCH * canvas
+    size_t    A;                  // stride between batch slots (ovf_rec)
 };
 
 // per-(pixel, blob) entries, used by the feather / per-blob paths
@@ -92,74 +120,220 @@ __device__ __forceinline__ uint32_t ovf_slot(const Acc &ac, uint32_t mask, uint3
 
 struct DevCos { __device__ double operator()(double x) const { return cos(x); } };
 
-// ---------------------------------------------------------------------------------------- scatter
-__global__ void __launch_bounds__(256)
-k_scatter(const pword *__restrict__ table, const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2,
-          const double *__restrict__ rlag, const double *__restrict__ rslope, const uint32_t *__restrict__ chain_of,
-          RConst rc, RFrame rf, uint32_t *__restrict__ head, uint4 *__restrict__ rec) {
-    size_t a = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= rc.A) return;
-    if (rf.chain_only >= 0 && chain_of[a] != (uint32_t) rf.chain_only) return;
-    size_t A = rc.A;
-    pword pt1 = table[(size_t) rf.y * A + a];
-    pword pt2 = table[(size_t) rf.yn * A + a];
-    bool has1 = pw_flags(pt1) & F_HAS_PIXEL, has2 = pw_flags(pt2) & F_HAS_PIXEL;
-    if (!has1 && !has2) return;
+// ---------------------------------------------------------------------------------------- exact conversions
+// int <-> double conversions issue on the quarter-rate XU pipe and were the busiest pipe of the scatter;
+// these do the same EXACT conversions with one add on the FP64 pipe.
+// u32 -> double: 2^52 + v holds v in the low mantissa bits
+__device__ __forceinline__ double u2d(uint32_t v) { return __hiloint2double(0x43300000, (int) v) - 4503599627370496.0; }
+// floor of a double in [0, 2^31): the round-down add of 2^52 leaves floor(v) in the low word
+__device__ __forceinline__ uint32_t d2u_floor(double v) { return (uint32_t) __double2loint(__dadd_rd(v, 4503599627370496.0)); }
+// round() (half away from zero) of a double in [0, 2^31): floor(v + 0.5), the add rounded down so that it never reaches
+// the next integer from below
+__device__ __forceinline__ uint32_t d2u_round(double v) { return d2u_floor(__dadd_rd(v, 0.5)); }
 
+// lerp_color (amx_math.h) on pre-converted channels
+struct ColD { double r, g, b, a; };
+__device__ __forceinline__ ColD col_d(uint32_t c) { ColD d; d.r = u2d(c_r(c)); d.g = u2d(c_g(c)); d.b = u2d(c_b(c)); d.a = u2d(c_a(c)); return d; }
+__device__ __forceinline__ uint32_t lerp_color_d(const ColD &c1, const ColD &c2, double w) {
+    double iw = 1.0 - w;
+    return c_make(d2u_round(w * c1.r + iw * c2.r), d2u_round(w * c1.g + iw * c2.g),
+                  d2u_round(w * c1.b + iw * c2.b), d2u_round(w * c1.a + iw * c2.a));
+}
+// split_spline_coord (amx_math.h); negative samples (spline overshoot, undefined in the reference) keep the generic code
+__device__ __forceinline__ void split_spline_fast(double v, uint32_t *i, uint32_t *f) {
+    if (v >= 0.0 && v < 2147483648.0) {
+        uint32_t ip = d2u_floor(v);
+        *i = ip & 0xffffu;
+        *f = d2u_round((v - u2d(ip)) * 255.0) & 255u;
+    } else split_spline_coord(v, i, f);
+}
+
+// ---------------------------------------------------------------------------------------- scatter
+// Render inputs of one interval y (written by k_prepare): the atoms that have a pixel on either side of the
+// interval, SORTED by the 8x4-pixel tile of their mid-interval position, so that the 32 atoms of a warp land on
+// neighbouring pixels (their counter atomics and record stores share sectors).
+struct RIn {
+    const pword    *pts;          // [h][npt][A]: key points of columns y, yn (and the outer spline controls p0, p3 when npt == 4)
+    const uint32_t *c1, *c2;      // [h][A] resolved end colours
+    const uint32_t *atom;         // [h][A] original atom index (the reference's summation order)
+    const uint32_t *chain;        // [h][A] chain of the atom, nullptr for a single chain
+    const double   *lag, *slope;  // [h][A] Perlin lag / slope, nullptr unless fading == PERLIN
+    const pword    *table;        // the unsorted table [h][A] (only for a control column that is none of the stored ones)
+    uint32_t        npt;
+};
+
+// per-interval inputs of one atom, converted once per batch
+struct AtomIn {
+    pword  pt1, pt2;
+    double x1, y1, x2, y2;        // end points in 1/256 px units (exact integers)
+    ColD   c1, c2;
+    uint32_t rc1, rc2;
+    double lag, slope;
+};
+
+// position + colour of one atom in one frame; false when the atom is clipped away
+__device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, const RFrame &rf, const AtomIn &in, size_t i, uint32_t atom,
+                                            uint32_t *home, uint32_t *col, uint32_t *fract) {
+    const size_t A = rc.A;
+    const double inv256 = 0.00390625;
     // trajectory (morph.cpp:523-531)
     uint32_t x, y, xf, yf;
     if (rc.motion == K_LINEAR) {
-        lerp_point(pt1, pt2, rf.w, &x, &y, &xf, &yf);
+        // lerp_point (amx_math.h / morph.cpp:1501-1515) on the pre-converted coordinates
+        double iw = 1.0 - rf.w;
+        double xx = rf.w * in.x1 + iw * in.x2, yy = rf.w * in.y1 + iw * in.y2;
+        if (xx >= 0.0 && yy >= 0.0) {
+            uint32_t ix = d2u_floor(xx * inv256) & 0xffffu, iy = d2u_floor(yy * inv256) & 0xffffu;
+            x = ix; y = iy;
+            xf = d2u_floor(xx - u2d(ix * 256u)) & 255u;
+            yf = d2u_floor(yy - u2d(iy * 256u)) & 255u;
+        } else lerp_point(in.pt1, in.pt2, rf.w, &x, &y, &xf, &yf);      // weight outside [0,1] (key frames not numbered 0..h-1)
     } else if (rc.motion == K_SPLINE) {
-        pword q0 = table[(size_t) rf.p0 * A + a], q1 = table[(size_t) rf.p1 * A + a];
-        pword q2 = table[(size_t) rf.p2 * A + a], q3 = table[(size_t) rf.p3 * A + a];
-        double vx = cr_eval(pw_xd(q0), pw_xd(q1), pw_xd(q2), pw_xd(q3), rf.b1, rf.b2, rf.b3, rf.b4);
-        double vy = cr_eval(pw_yd(q0), pw_yd(q1), pw_yd(q2), pw_yd(q3), rf.b1, rf.b2, rf.b3, rf.b4);
-        split_spline_coord(vx, &x, &xf);
-        split_spline_coord(vy, &y, &yf);
+        // the four control columns are y-1, y, y+1, y+2 (cyclic): the outer two coincide with yn / y when h = 2 and are
+        // stored next to them otherwise; a control coordinate x + x_fract/256 is exactly (256 x + x_fract) / 256
+        double qx[4], qy[4];
+        const int pk[4] = {rf.p0, rf.p1, rf.p2, rf.p3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((uint32_t) pk[k] == rf.y) { qx[k] = in.x1; qy[k] = in.y1; }
+            else if ((uint32_t) pk[k] == rf.yn) { qx[k] = in.x2; qy[k] = in.y2; }
+            else {
+                // npt == 4 here: slot 2 holds column y-1, slot 3 column y+2; anything else (the spline's interval index
+                // and the frame index disagree by rounding) comes from the unsorted table
+                pword q;
+                if ((uint32_t) pk[k] == (rf.y + rc.h - 1u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 2) * A + i];
+                else if ((uint32_t) pk[k] == (rf.y + 2u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 3) * A + i];
+                else q = ri.table[(size_t) pk[k] * A + atom];
+                qx[k] = u2d((uint32_t) pw_x256(q)); qy[k] = u2d((uint32_t) pw_y256(q));
+            }
+        }
+        double vx = cr_eval(qx[0] * inv256, qx[1] * inv256, qx[2] * inv256, qx[3] * inv256, rf.b1, rf.b2, rf.b3, rf.b4);
+        double vy = cr_eval(qy[0] * inv256, qy[1] * inv256, qy[2] * inv256, qy[3] * inv256, rf.b1, rf.b2, rf.b3, rf.b4);
+        split_spline_fast(vx, &x, &xf);
+        split_spline_fast(vy, &y, &yf);
     } else {
-        x = pw_x(pt1); y = pw_y(pt1); xf = pw_xf(pt1); yf = pw_yf(pt1);
+        x = pw_x(in.pt1); y = pw_y(in.pt1); xf = pw_xf(in.pt1); yf = pw_yf(in.pt1);
     }
     // clip (morph.cpp:552-555)
     if (x >= rc.width || y >= rc.height) {
-        if (x > rc.bx2 || x < rc.bx1 || y > rc.by2 || y < rc.by1) return;
+        if (x > rc.bx2 || x < rc.bx1 || y > rc.by2 || y < rc.by1) return false;
     }
     // colour (morph.cpp:537-550)
-    uint32_t c1 = rc1[(size_t) rf.y * A + a], c2 = rc2[(size_t) rf.y * A + a];
     double str = rf.w;
     if (rc.fading == K_COSINE) str = rf.str_cos;
-    else if (rc.fading == K_PERLIN) str = ease_strength(rlag[(size_t) rf.y * A + a], rslope[(size_t) rf.y * A + a], rf.w, DevCos());
-    uint32_t col = lerp_color(c1, c2, str);
+    else if (rc.fading == K_PERLIN) str = ease_strength(in.lag, in.slope, rf.w, DevCos());
+    if (str >= 0.0 && str <= 1.0) *col = lerp_color_d(in.c1, in.c2, str);
+    else *col = lerp_color(in.rc1, in.rc2, str);
+    *home = y * rc.cw + x;
+    *fract = xf | (yf << 8);
+    return true;
+}
 
-    uint32_t home = y * rc.cw + x;
-    uint32_t next = atomicExch(&head[home], (uint32_t) a);
-    rec[a] = make_uint4(next, col, xf | (yf << 8), 0u);
+struct LiveCount { uint32_t n[RBATCH]; };     // live (sorted) atoms of the interval of each frame of the batch
+
+// One thread per sorted atom index.  The samples of all frames of the batch are computed first, then all slot-claiming
+// atomics are issued back to back (their round trips overlap), then the records are stored.
+__global__ void __launch_bounds__(256)
+k_scatter(RIn ri, RConst rc, RBatch rb, LiveCount live, uint32_t nb, ABuf ab) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rc.A) return;
+    const size_t A = rc.A;
+
+    uint32_t cur_y = 0xffffffffu;
+    AtomIn in;
+    in.lag = in.slope = 0.0;
+    uint32_t atom = 0, meta_chain = 0;
+    bool use = false;
+    uint32_t home[RBATCH], col[RBATCH], meta[RBATCH], who[RBATCH];
+    bool ok[RBATCH];
+#pragma unroll
+    for (uint32_t s = 0; s < RBATCH; ++s) {
+        ok[s] = false;
+        if (s >= nb) continue;
+        const RFrame &rf = rb.f[s];
+        if (rf.y != cur_y) {                        // (re)load the interval: uniform across the grid
+            cur_y = rf.y;
+            use = i < live.n[s];
+            if (use && ri.chain) {
+                uint32_t chain = ri.chain[(size_t) rf.y * A + i];
+                meta_chain = (chain & 0xffffu) << 16;
+                if (rb.chain_only >= 0 && chain != (uint32_t) rb.chain_only) use = false;
+            }
+            if (use) {
+                const size_t o = (size_t) rf.y * A + i;
+                in.pt1 = ri.pts[((size_t) rf.y * ri.npt + 0) * A + i];
+                in.pt2 = ri.pts[((size_t) rf.y * ri.npt + 1) * A + i];
+                atom = ri.atom[o];
+                in.rc1 = ri.c1[o]; in.rc2 = ri.c2[o];
+                in.x1 = u2d((uint32_t) pw_x256(in.pt1)); in.y1 = u2d((uint32_t) pw_y256(in.pt1));
+                in.x2 = u2d((uint32_t) pw_x256(in.pt2)); in.y2 = u2d((uint32_t) pw_y256(in.pt2));
+                in.c1 = col_d(in.rc1);
+                in.c2 = col_d(in.rc2);
+                if (rc.fading == K_PERLIN) { in.lag = ri.lag[o]; in.slope = ri.slope[o]; }
+            }
+        }
+        if (!use) continue;
+        uint32_t fr;
+        ok[s] = atom_sample(ri, rc, rf, in, i, atom, &home[s], &col[s], &fr);
+        meta[s] = fr | meta_chain;
+        who[s] = atom;
+    }
+    // claim a slot in the A-buffer of every frame ...
+    uint32_t k[RBATCH];
+#pragma unroll
+    for (uint32_t s = 0; s < RBATCH; ++s)
+        if (ok[s]) { if (rc.debug & 1) k[s] = 0; else k[s] = atomicAdd(&ab.cnt[(size_t) s * ab.canvas + home[s]], 1u); }
+    // ... and store the records
+#pragma unroll
+    for (uint32_t s = 0; s < RBATCH; ++s) {
+        if (!ok[s] || (rc.debug & 2)) continue;
+        size_t hp = (size_t) s * ab.canvas + home[s];
+        if (k[s] < K_SLOTS) ab.slots[(size_t) k[s] * ab.kstride + hp] = make_uint4(col[s], meta[s], who[s], 0u);
+        else {
+            // overflow: list through ovf_rec, indexed by the ORIGINAL atom (unique per frame)
+            uint32_t next = atomicExch(&ab.ovf_head[hp], who[s]);
+            ab.ovf_rec[(size_t) s * ab.A + who[s]] = make_uint4(col[s], meta[s], next, 0u);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------- gather
-// Visit every contribution to pixel (px, py): f(atom, colour, n) with n the integer bilinear numerator.
-// Splat targets and their edge rules: morph.cpp:558-588.
+// Visit every contribution to pixel (px, py): f(atom, colour, n, chain16) with n the integer bilinear numerator.
+// Splat targets and their edge rules: morph.cpp:558-588.  `ab` is already offset to the batch slot.
 template <typename F>
-__device__ __forceinline__ void visit_contributions(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
-                                                    uint32_t px, uint32_t py, F f) {
+__device__ __forceinline__ void visit_contributions(const ABuf &ab, const RConst &rc, uint32_t px, uint32_t py, F f) {
+    // the four homes that can reach (px, py): counters and first slots are independent loads, issued together
+    uint32_t cn[4];
+    uint32_t hp[4];
+    uint4 first[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t dx = k & 1, dy = k >> 1;
-        if (px < dx || py < dy) continue;
+        bool ok = px >= dx && py >= dy;
         uint32_t hx = px - dx, hy = py - dy;
-        bool ok;
-        if (k == 0) ok = true;
-        else if (k == 1) ok = (hx < rc.bx2 || hx + 1 < rc.width);
-        else if (k == 2) ok = (hy < rc.by2 || hy + 1 < rc.height);
-        else ok = (hy < rc.by2 && hx < rc.bx2) || (hy + 1 < rc.height && hx + 1 < rc.width);
-        if (!ok) continue;
-        uint32_t idx = head[hy * rc.cw + hx];
-        while (idx != NIL) {
-            uint4 r = rec[idx];
-            uint32_t xf = r.z & 255u, yf = (r.z >> 8) & 255u;
+        if (k == 1) ok = ok && (hx < rc.bx2 || hx + 1 < rc.width);
+        else if (k == 2) ok = ok && (hy < rc.by2 || hy + 1 < rc.height);
+        else if (k == 3) ok = ok && ((hy < rc.by2 && hx < rc.bx2) || (hy + 1 < rc.height && hx + 1 < rc.width));
+        hp[k] = ok ? hy * rc.cw + hx : py * rc.cw + px;
+        cn[k] = ok ? ab.cnt[hp[k]] : 0u;
+        first[k] = ab.slots[hp[k]];                // unconditional: stale when the home is empty, never used then
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (cn[k] == 0) continue;
+        uint32_t dx = k & 1, dy = k >> 1;
+        auto emit = [&](uint32_t atom, const uint4 &r) {
+            uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
             uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
-            if (n) f(idx, r.y, n);
-            idx = r.x;
+            if (n) f(atom, r.x, n, r.y >> 16);
+        };
+        emit(first[k].z, first[k]);
+#pragma unroll
+        for (int j = 1; j < K_SLOTS; ++j)
+            if (cn[k] > (uint32_t) j) { uint4 r = ab.slots[(size_t) j * ab.kstride + hp[k]]; emit(r.z, r); }
+        if (cn[k] > K_SLOTS) {
+            uint32_t i = ab.ovf_head[hp[k]];
+            for (uint32_t j = K_SLOTS; j < cn[k]; ++j) { uint4 r = ab.ovf_rec[i]; emit(i, r); i = r.z; }
         }
     }
 }
@@ -240,13 +414,13 @@ struct Over {
 
 // Emits the resolved blob pixels of one position in ascending blob order: emit(chain, px)
 template <bool SINGLE, typename E>
-__device__ __forceinline__ void resolve_position(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
+__device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &rc,
                                                  const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc,
                                                  uint32_t px, uint32_t py, E emit) {
     unsigned long long key[MAXK];
     uint32_t cc[MAXK], cn[MAXK];
     int count = 0;
-    visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+    visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
         if (count < MAXK) {
             unsigned long long k = a;
             if (!SINGLE) k |= (unsigned long long) (uint32_t) boc[chain_of[a]] << 32;
@@ -276,14 +450,14 @@ __device__ __forceinline__ void resolve_position(const uint32_t *__restrict__ he
         long long best = LLONG_MAX;
         uint32_t bchain = 0;
         if (SINGLE) { if (prev < 0) best = 0; }
-        else visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t, uint32_t) {
+        else visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t, uint32_t, uint32_t) {
             uint32_t c = chain_of[a];
             long long k = boc[c];
             if (k > prev && k < best) { best = k; bchain = c; }
         });
         if (best == LLONG_MAX) break;
         unsigned long long R = 0, G = 0, B = 0, Av = 0, N = 0, cnt = 0;
-        visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+        visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
             if (!SINGLE && chain_of[a] != bchain) return;
             R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
         });
@@ -292,68 +466,81 @@ __device__ __forceinline__ void resolve_position(const uint32_t *__restrict__ he
     }
 }
 
-// exact round(num/den) (half up) for num < 2^40, den < 2^31, quotient <= 255: float estimate + integer fix-up.
+// exact round(num/den) (half up) for 2*num + den < 2^32, quotient <= 255: float estimate + integer fix-up.
 // *tie is set when num/den is an exact .5 tie (the only place where the reference's double sums can differ).
-__device__ __forceinline__ uint32_t rdiv_small(unsigned long long num, unsigned long long den, bool *tie) {
-    unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
-    uint32_t q = (uint32_t) __fmul_rz(__ull2float_rz(n2), __frcp_rz(__ull2float_ru(d2)));   // every step rounds down: never above the true quotient
-    unsigned long long rem = n2 - (unsigned long long) q * d2;
+__device__ __forceinline__ uint32_t rdiv_small(uint32_t num, uint32_t den, float rcp_d2, bool *tie) {
+    uint32_t n2 = 2u * num + den, d2 = 2u * den;
+    uint32_t q = (uint32_t) __fmul_rz(__uint2float_rz(n2), rcp_d2);   // every step rounds down: never above the true quotient
+    uint32_t rem = n2 - q * d2;
     while (rem >= d2) { rem -= d2; ++q; }
-    *tie |= (rem == 0ull);
+    *tie |= (rem == 0u);
     return q;
 }
 
-// FAST PATH of the fused gather: one chain at the position and no exact tie -> integer sums, no sort, no
-// per-contribution double math.  Returns false when the generic ordered replay is needed.
+// FAST PATH of the fused gather: one chain at the position, at most MAXK contributions and no exact tie ->
+// 32-bit integer sums, no sort, no per-contribution double math.  Returns false when the generic ordered replay is
+// needed.  (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits.)
 template <bool SINGLE>
-__device__ __forceinline__ bool resolve_fast(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, const RConst &rc,
-                                             const uint32_t *__restrict__ chain_of, uint32_t px, uint32_t py, uint32_t *chain_out,
+__device__ __forceinline__ bool resolve_fast(const ABuf &ab, const RConst &rc, uint32_t px, uint32_t py, uint32_t *chain_out,
                                              uint32_t *px_out, bool *empty) {
-    unsigned long long R = 0, G = 0, B = 0, Av = 0;
+    uint32_t R = 0, G = 0, B = 0, Av = 0;
     uint32_t N = 0, cnt = 0, chain = 0xffffffffu;
     bool mixed = false;
-    visit_contributions(head, rec, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n) {
+    visit_contributions(ab, rc, px, py, [&](uint32_t, uint32_t col, uint32_t n, uint32_t c16) {
         if (!SINGLE) {
-            uint32_t c = chain_of[a];
-            if (chain == 0xffffffffu) chain = c;
-            else if (c != chain) mixed = true;
+            if (chain == 0xffffffffu) chain = c16;
+            else if (c16 != chain) mixed = true;
         }
-        R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
+        if (cnt < MAXK) { R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; }
+        ++cnt;
     });
     *empty = (cnt == 0);
     if (cnt == 0) return true;
-    if (mixed || cnt > 30000u) return false;       // N = sum(n) must stay below 2^31
+    if (mixed || cnt > MAXK) return false;
+    if (!SINGLE && rc.nchains > 65536u) return false;              // 16-bit chain tags are ambiguous: let the generic path look
     bool tie = false;
-    uint32_t r = rdiv_small(R, N, &tie), g = rdiv_small(G, N, &tie), b = rdiv_small(B, N, &tie), a;
+    float rcp_d2 = __frcp_rz(__uint2float_ru(2u * N));
+    uint32_t r = rdiv_small(R, N, rcp_d2, &tie), g = rdiv_small(G, N, rcp_d2, &tie), b = rdiv_small(B, N, rcp_d2, &tie), a;
     if (rc.density == 0) a = 0;
-    else if (cnt >= rc.density) a = rdiv_small(Av, N, &tie);
+    else if (cnt >= rc.density) a = rdiv_small(Av, N, rcp_d2, &tie);
     else {
-        unsigned long long num = Av * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
+        unsigned long long num = (unsigned long long) Av * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
         unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
         unsigned long long q = n2 / d2;
         tie |= (n2 - q * d2 == 0ull);
         a = (uint32_t) q;
     }
     if (tie) return false;
-    *chain_out = SINGLE ? 0u : chain;
+    *chain_out = SINGLE ? 0u : chain;   // the 16-bit tag is the chain itself here (nchains <= 65536)
     *px_out = c_make(r, g, b, a);
     return true;
 }
 
-// fused gather + composite (feather == 0): one thread per OUTPUT pixel
+// the A-buffer of batch slot `slot`
+__device__ __forceinline__ ABuf ab_at(ABuf ab, uint32_t slot) {
+    size_t o = (size_t) slot * ab.canvas;
+    ab.cnt += o; ab.slots += o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
+    return ab;
+}
+
+// fused gather + composite (feather == 0): one thread per OUTPUT pixel, blockIdx.z = batch slot
 template <bool SINGLE>
 __global__ void __launch_bounds__(256)
-k_gather_composite(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, RConst rc, uint32_t y_frame,
+k_gather_composite(ABuf abuf, RConst rc, RBatch rb,
                    const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
                    const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
                    const uint32_t *__restrict__ bg, uint32_t *__restrict__ out) {
     uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= rc.width || py >= rc.height) return;
+    const uint32_t slot = blockIdx.z, y_frame = rb.f[slot].y;
+    const ABuf ab = ab_at(abuf, slot);
+    const size_t np = (size_t) rc.width * rc.height;
+    out += (size_t) rb.f[slot].dst * np;
     size_t i = (size_t) py * rc.width + px;
-    uint32_t bgc = rc.keep_background ? bg[i] : 0u;
+    uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
     uint32_t chain = 0, pxl = 0;
     bool empty = false;
-    if (resolve_fast<SINGLE>(head, rec, rc, chain_of, px, py, &chain, &pxl, &empty)) {
+    if (resolve_fast<SINGLE>(ab, rc, px, py, &chain, &pxl, &empty)) {
         if (empty) { out[i] = bgc; return; }
         uint32_t col = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
         if (!rc.keep_background) { out[i] = c_a(col) ? col : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
@@ -365,16 +552,16 @@ k_gather_composite(const uint32_t *__restrict__ head, const uint4 *__restrict__ 
     // generic path: several blobs at the position, an exact tie, or a very long list
     const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
     Over ov;
-    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t ch, uint32_t p) {
+    resolve_position<SINGLE>(ab, rc, chain_of, boc, px, py, [&](uint32_t ch, uint32_t p) {
         ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
     });
     out[i] = ov.finish(bgc, rc.keep_background != 0);
 }
 
-// gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel
+// gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
 template <bool SINGLE>
 __global__ void __launch_bounds__(256)
-k_gather_entries(const uint32_t *__restrict__ head, const uint4 *__restrict__ rec, RConst rc, uint32_t y_frame,
+k_gather_entries(ABuf ab, RConst rc, uint32_t y_frame,
                  const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain, Acc ac,
                  uint32_t *__restrict__ px0, uint8_t *__restrict__ layer0, uint32_t *__restrict__ pxo, uint8_t *__restrict__ layero) {
     uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
@@ -382,7 +569,7 @@ k_gather_entries(const uint32_t *__restrict__ head, const uint4 *__restrict__ re
     uint32_t ci = py * rc.cw + px;
     const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
     int emitted = 0;
-    resolve_position<SINGLE>(head, rec, rc, chain_of, boc, px, py, [&](uint32_t chain, uint32_t pxl) {
+    resolve_position<SINGLE>(ab, rc, chain_of, boc, px, py, [&](uint32_t chain, uint32_t pxl) {
         if (emitted == 0) { ac.owner[ci] = (int32_t) chain; px0[ci] = pxl; layer0[ci] = 255; }
         else {
             uint32_t s = ovf_slot(ac, rc.ovf_mask, ci, chain, true);
@@ -522,14 +709,38 @@ k_background(const uint32_t *__restrict__ f1, const uint32_t *__restrict__ f2, R
     out[i] = lerp_color(c1, c2, str);
 }
 
-// prepare: per atom & interval end colours + Perlin lag/slope (morph.cpp:495-548)
+// sort key of an atom for interval (y, yn): the 8x4-pixel tile of its mid-interval position, row-major inside the
+// tile (8 pixels = one 32-byte sector of counters, two sectors of records).  Atoms without a pixel on either side are
+// never drawn (morph.cpp:503-518 leaves them out): key 0xffffffff sorts them behind the live ones.
 __global__ void __launch_bounds__(256)
-k_prepare(const pword *__restrict__ table, const uint32_t *__restrict__ fetch_y, const uint32_t *__restrict__ fetch_yn,
-          uint32_t y, uint32_t yn, RConst rc, const int32_t *__restrict__ perlin, uint32_t *__restrict__ rc1,
-          uint32_t *__restrict__ rc2, double *__restrict__ rlag, double *__restrict__ rslope) {
+k_sortkey(const pword *__restrict__ table, uint32_t y, uint32_t yn, size_t A, uint32_t *__restrict__ key, uint32_t *__restrict__ val,
+          uint32_t *__restrict__ live) {
     size_t a = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= rc.A) return;
-    pword pt1 = table[(size_t) y * rc.A + a], pt2 = table[(size_t) yn * rc.A + a];
+    bool is_live = false;
+    if (a < A) {
+        pword pt1 = table[(size_t) y * A + a], pt2 = table[(size_t) yn * A + a];
+        is_live = ((pw_flags(pt1) | pw_flags(pt2)) & F_HAS_PIXEL) != 0;
+        uint32_t mx = (pw_x(pt1) + pw_x(pt2)) >> 1, my = (pw_y(pt1) + pw_y(pt2)) >> 1;
+        key[a] = is_live ? ((my >> 2) << 18) | ((mx >> 3) << 5) | ((my & 3u) << 3) | (mx & 7u) : 0xffffffffu;
+        val[a] = (uint32_t) a;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, is_live);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(live, (uint32_t) __popc(m));
+}
+
+// prepare: per SORTED atom & interval: key points, end colours with the one-sided alpha rule, Perlin lag/slope
+// (morph.cpp:495-548)
+__global__ void __launch_bounds__(256)
+k_prepare(const pword *__restrict__ table, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ chain_of,
+          const uint32_t *__restrict__ fetch_y, const uint32_t *__restrict__ fetch_yn,
+          uint32_t y, uint32_t yn, uint32_t npt, RConst rc, const int32_t *__restrict__ perlin,
+          pword *__restrict__ rpts, uint32_t *__restrict__ ratom, uint32_t *__restrict__ rchain, uint32_t *__restrict__ rc1,
+          uint32_t *__restrict__ rc2, double *__restrict__ rlag, double *__restrict__ rslope) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rc.A) return;
+    const size_t A = rc.A;
+    const uint32_t a = perm[i];
+    pword pt1 = table[(size_t) y * A + a], pt2 = table[(size_t) yn * A + a];
     bool has1 = pw_flags(pt1) & F_HAS_PIXEL, has2 = pw_flags(pt2) & F_HAS_PIXEL;
     uint32_t c1 = 0, c2 = 0;
     auto fetch = [&](const uint32_t *img, pword p) -> uint32_t {
@@ -539,16 +750,26 @@ k_prepare(const pword *__restrict__ table, const uint32_t *__restrict__ fetch_y,
     if (has1 && !has2) { c1 = fetch(fetch_y, pt1); c2 = c1 & 0x00ffffffu; }
     else if (has2 && !has1) { c2 = fetch(fetch_yn, pt2); c1 = c2 & 0x00ffffffu; }
     else if (has1 && has2) { c1 = fetch(fetch_y, pt1); c2 = fetch(fetch_yn, pt2); }
-    rc1[(size_t) y * rc.A + a] = c1;
-    rc2[(size_t) y * rc.A + a] = c2;
+    const size_t o = (size_t) y * A + i;
+    rpts[((size_t) y * npt + 0) * A + i] = pt1;
+    rpts[((size_t) y * npt + 1) * A + i] = pt2;
+    if (npt == 4) {
+        uint32_t h = rc.h;
+        rpts[((size_t) y * npt + 2) * A + i] = table[(size_t) ((y + h - 1) % h) * A + a];     // spline control p0 = y - 1
+        rpts[((size_t) y * npt + 3) * A + i] = table[(size_t) ((y + 2) % h) * A + a];         // spline control p3 = y + 2
+    }
+    ratom[o] = a;
+    if (rchain) rchain[o] = chain_of[a];
+    rc1[o] = c1;
+    rc2[o] = c2;
     if (rlag) {
         double f = 8.0;
         double bbox_w = (double) ((int) rc.bx2 - (int) rc.bx1) + 1.0;
         double bbox_h = (double) ((int) rc.by2 - (int) rc.by1) + 1.0;
         double px = ((double) (((int) pw_x(pt1) - (int) rc.bx1) * 256 + (int) pw_xf(pt1)) / (bbox_w * 256.0)) * f;
         double py = ((double) (((int) pw_y(pt1) - (int) rc.by1) * 256 + (int) pw_yf(pt1)) / (bbox_h * 256.0)) * f;
-        rlag[(size_t) y * rc.A + a] = pn_octave2(perlin, px, py, 8) * 0.5 + 0.5;
-        rslope[(size_t) y * rc.A + a] = pn_octave2(perlin + 512, px, py, 8) * 0.5 + 0.5;
+        rlag[o] = pn_octave2(perlin, px, py, 8) * 0.5 + 0.5;
+        rslope[o] = pn_octave2(perlin + 512, px, py, 8) * 0.5 + 0.5;
     }
 }
 
@@ -557,12 +778,16 @@ k_prepare(const pword *__restrict__ table, const uint32_t *__restrict__ fetch_y,
 void engine_render_free(Engine *E) {
     dev_free(E->rc1); dev_free(E->rc2); dev_free(E->rlag); dev_free(E->rslope);
     E->rc1 = E->rc2 = nullptr; E->rlag = E->rslope = nullptr;
+    dev_free(E->rpts); dev_free(E->ratom); dev_free(E->rchain);
+    E->rpts = nullptr; E->ratom = E->rchain = nullptr; E->rnpt = 0; E->r_live.clear();
     dev_free(E->d_blob_of_chain); dev_free(E->d_blob_avg); dev_free(E->d_blob_distinct);
     E->d_blob_of_chain = nullptr; E->d_blob_avg = nullptr; E->d_blob_distinct = nullptr;
     dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
-    dev_free(E->d_ovf_used); dev_free(E->blob_px); dev_free(E->ab_head); dev_free(E->ab_rec);
+    dev_free(E->d_ovf_used); dev_free(E->blob_px);
+    dev_free(E->ab_cnt); dev_free(E->ab_slots); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
-    E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0; E->ab_head = nullptr; E->ab_rec = nullptr;
+    E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
+    E->ab_cnt = nullptr; E->ab_slots = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
 
@@ -584,6 +809,7 @@ static RConst make_rconst(Engine *E) {
     rc.nchains = E->nchains; rc.h = E->h; rc.A = E->A;
     rc.ovf_mask = E->ovf_cap ? E->ovf_cap - 1 : 0;
     rc.feather = (uint32_t) std::min<uint64_t>(E->p.feather, 253);
+    rc.debug = getenv("AMX_DEBUG") ? atoi(getenv("AMX_DEBUG")) : 0;
     return rc;
 }
 
@@ -605,8 +831,13 @@ int engine_render_prepare(Engine *E) {
     if (E->frames.size() != E->h) { E->err = "chain height != frame count"; return AMX_ERR_STATE; }
     size_t n = (size_t) E->h * E->A;
     bool perlin = E->p.fading == K_PERLIN;
+    const uint32_t npt = E->h >= 3 ? 4u : 2u;
     if (!E->rc1) {
-        if (!dev_alloc(E, (void **) &E->rc1, n * 4, "rc1") || !dev_alloc(E, (void **) &E->rc2, n * 4, "rc2")) return AMX_ERR_NOMEM;
+        if (!dev_alloc(E, (void **) &E->rc1, n * 4, "rc1") || !dev_alloc(E, (void **) &E->rc2, n * 4, "rc2") ||
+            !dev_alloc(E, (void **) &E->rpts, n * npt * 8, "sorted key points") || !dev_alloc(E, (void **) &E->ratom, n * 4, "sorted atoms"))
+            return AMX_ERR_NOMEM;
+        if (E->nchains > 1 && !dev_alloc(E, (void **) &E->rchain, n * 4, "sorted chains")) return AMX_ERR_NOMEM;
+        E->rnpt = npt;
     }
     if (perlin && !E->rlag) {
         if (!dev_alloc(E, (void **) &E->rlag, n * 8, "rlag") || !dev_alloc(E, (void **) &E->rslope, n * 8, "rslope")) return AMX_ERR_NOMEM;
@@ -614,9 +845,12 @@ int engine_render_prepare(Engine *E) {
     int rcode = ensure_perlin(E);
     if (rcode != AMX_OK) return rcode;
     size_t cv = E->canvas();
-    if (!E->ab_head) {
-        // A-buffer: list heads per canvas position + one 16-byte record per atom
-        if (!dev_alloc(E, (void **) &E->ab_head, cv * 4, "abuf heads") || !dev_alloc(E, (void **) &E->ab_rec, E->A * 16, "abuf records"))
+    if (!E->ab_cnt) {
+        // A-buffer for RBATCH frames: counters + K_SLOTS direct records per canvas position, overflow list per atom
+        if (!dev_alloc(E, (void **) &E->ab_cnt, RBATCH * cv * 4, "abuf counters") ||
+            !dev_alloc(E, (void **) &E->ab_slots, (size_t) K_SLOTS * RBATCH * cv * 16, "abuf slots") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_head, RBATCH * cv * 4, "abuf overflow heads") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_rec, RBATCH * E->A * 16, "abuf overflow records"))
             return AMX_ERR_NOMEM;
     }
     // blob order / colours per (frame, chain)
@@ -656,13 +890,31 @@ int engine_render_prepare(Engine *E) {
     cudaMemcpyAsync(E->d_blob_distinct, distinct.data(), (size_t) E->nchains * 4, cudaMemcpyHostToDevice, E->stream);
 
     RConst rc = make_rconst(E);
-    for (uint32_t y = 0; y < E->h; ++y) {
-        uint32_t yn = (y + 1) % E->h;
-        k_prepare<<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, E->frames[y].fetch, E->frames[yn].fetch, y, yn, rc, E->d_perlin,
-                                                           E->rc1, E->rc2, perlin ? E->rlag : nullptr, perlin ? E->rslope : nullptr);
-        E->launches++;
+    // sort scratch: keys / atom indices in and out, the live counters and cub's workspace
+    uint32_t *d_key = nullptr, *d_key2 = nullptr, *d_val = nullptr, *d_perm = nullptr, *d_live = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_val, d_perm, (int) E->A, 0, 32, E->stream);
+    bool okay = dev_alloc(E, (void **) &d_key, E->A * 4, "sort keys") && dev_alloc(E, (void **) &d_key2, E->A * 4, "sort keys") &&
+                dev_alloc(E, (void **) &d_val, E->A * 4, "sort values") && dev_alloc(E, (void **) &d_perm, E->A * 4, "sort values") &&
+                dev_alloc(E, (void **) &d_live, (size_t) E->h * 4, "live counters") && dev_alloc(E, &d_tmp, tmp_bytes, "sort workspace");
+    if (okay) {
+        cudaMemsetAsync(d_live, 0, (size_t) E->h * 4, E->stream);
+        for (uint32_t y = 0; y < E->h; ++y) {
+            uint32_t yn = (y + 1) % E->h;
+            k_sortkey<<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, y, yn, E->A, d_key, d_val, d_live + y);
+            cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_val, d_perm, (int) E->A, 0, 32, E->stream);
+            k_prepare<<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, d_perm, E->chain_of, E->frames[y].fetch, E->frames[yn].fetch, y, yn, npt, rc,
+                                                               E->d_perlin, E->rpts, E->ratom, E->rchain, E->rc1, E->rc2,
+                                                               perlin ? E->rlag : nullptr, perlin ? E->rslope : nullptr);
+            E->launches += 2;
+        }
+        E->r_live.assign(E->h, 0);
+        cudaMemcpyAsync(E->r_live.data(), d_live, (size_t) E->h * 4, cudaMemcpyDeviceToHost, E->stream);
     }
-    if (E->fail(cudaStreamSynchronize(E->stream), "render prepare") || E->check("render prepare")) return AMX_ERR_CUDA;
+    bool bad = !okay || E->fail(cudaStreamSynchronize(E->stream), "render prepare") || E->check("render prepare");
+    dev_free(d_key); dev_free(d_key2); dev_free(d_val); dev_free(d_perm); dev_free(d_live); dev_free(d_tmp);
+    if (bad) return okay ? AMX_ERR_CUDA : AMX_ERR_NOMEM;
     E->render_ready = true;
     return AMX_OK;
 }
@@ -691,7 +943,7 @@ static RFrame make_rframe(Engine *E, double time, uint32_t f, double tl) {
     cr_basis(lt, &rf.b1, &rf.b2, &rf.b3, &rf.b4);
     rf.w = 1.0 - tl;
     rf.str_cos = ease_strength(0.5, 0.5, rf.w, LibmCos());
-    rf.chain_only = -1;
+    rf.dst = 0;
     return rf;
 }
 
@@ -736,23 +988,44 @@ static void launch_background(Engine *E, const RConst &rc, const RFrame &rf, uin
 
 static dim3 grid2d(uint32_t w, uint32_t h) { return dim3(div_up(w, 32), div_up(h, 8)); }
 
-// scatter one frame into the A-buffer
-static void launch_scatter(Engine *E, const RConst &rc, const RFrame &rf) {
-    cudaMemsetAsync(E->ab_head, 0xff, E->canvas() * 4, E->stream);
-    k_scatter<<<div_up(E->A, 256), 256, 0, E->stream>>>(E->table, E->rc1, E->rc2, E->rlag, E->rslope, E->chain_of, rc, rf, E->ab_head, E->ab_rec);
+static ABuf make_abuf(Engine *E) {
+    ABuf ab;
+    size_t cv = E->canvas();
+    ab.cnt = E->ab_cnt; ab.slots = E->ab_slots; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
+    ab.canvas = cv; ab.kstride = (size_t) RBATCH * cv; ab.A = E->A;
+    return ab;
+}
+
+// scatter `nb` frames (<= RBATCH) into the slots of the A-buffer
+static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb) {
+    cudaMemsetAsync(E->ab_cnt, 0, (size_t) nb * E->canvas() * 4, E->stream);
+    RIn ri;
+    ri.pts = E->rpts; ri.c1 = E->rc1; ri.c2 = E->rc2; ri.atom = E->ratom; ri.chain = E->rchain;
+    ri.lag = E->rlag; ri.slope = E->rslope; ri.npt = E->rnpt; ri.table = E->table;
+    LiveCount live;
+    uint32_t most = 0;
+    for (uint32_t s = 0; s < RBATCH; ++s) {
+        live.n[s] = s < nb ? E->r_live[rb.f[s].y] : 0u;
+        most = std::max(most, live.n[s]);
+    }
+    if (most == 0) return;
+    k_scatter<<<div_up(most, 256), 256, 0, E->stream>>>(ri, rc, rb, live, nb, make_abuf(E));
     E->launches++;
 }
 
 // scatter + gather into entries + feather of one frame; leaves entries (px/layer) valid and ownership set
-static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, const Acc &ac) {
+static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, int32_t chain_only, const Acc &ac) {
     size_t cv = E->canvas();
     uint32_t *px0 = E->blob_px, *pxo = E->blob_px + cv;
     uint8_t *layer0 = (uint8_t *) (E->blob_px + cv + E->ovf_cap), *layero = layer0 + cv;
     bool single = E->nchains == 1;
-    launch_scatter(E, rc, rf);
+    RBatch one;
+    one.f[0] = rf; one.chain_only = chain_only;
+    launch_scatter(E, rc, one, 1);
     const int32_t *boc = E->d_blob_of_chain;
-    if (single) k_gather_entries<true><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
-    else        k_gather_entries<false><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
+    ABuf ab = make_abuf(E);
+    if (single) k_gather_entries<true><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(ab, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
+    else        k_gather_entries<false><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(ab, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
     E->launches++;
     size_t total = single ? cv : cv + E->ovf_cap;
     for (uint32_t l = 0; l < rc.feather; ++l) {
@@ -784,12 +1057,32 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         if (rcode != AMX_OK) return rcode;
         d_dst = E->d_out;
     }
-    uint32_t *d_bg = nullptr;
-    if (E->p.keep_background && !dev_alloc(E, (void **) &d_bg, np * 4, "bg")) return AMX_ERR_NOMEM;
-    if (have_chains && E->p.feather > 0) { int rcode = ensure_entries(E); if (rcode != AMX_OK) { dev_free(d_bg); return rcode; } }
+    const uint32_t NB = std::max(1u, std::min<uint32_t>(E->render_batch, RBATCH));
+    if (E->p.keep_background && E->d_bg_cap < (size_t) NB * np) {
+        dev_free(E->d_bg); E->d_bg = nullptr; E->d_bg_cap = 0;
+        if (!dev_alloc(E, (void **) &E->d_bg, (size_t) NB * np * 4, "bg")) return AMX_ERR_NOMEM;
+        E->d_bg_cap = (size_t) NB * np;
+    }
+    uint32_t *d_bg = E->p.keep_background ? E->d_bg : nullptr;
+    if (have_chains && E->p.feather > 0) { int rcode = ensure_entries(E); if (rcode != AMX_OK) return rcode; }
     RConst rc = make_rconst(E);
     Acc ac = make_acc(E);
     size_t cv = E->canvas();
+    const bool single = E->nchains == 1;
+    RBatch rb;
+    rb.chain_only = -1;
+    uint32_t nb = 0;
+    auto flush_batch = [&]() {
+        // feather == 0: nb frames share one scatter and one fused gather/composite launch
+        if (nb == 0) return;
+        launch_scatter(E, rc, rb, nb);
+        dim3 grid(div_up(rc.width, 32), div_up(rc.height, 8), nb);
+        if (rc.debug & 4) { nb = 0; return; }
+        if (single) k_gather_composite<true><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst);
+        else        k_gather_composite<false><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst);
+        E->launches++;
+        nb = 0;
+    };
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t *dst = d_dst + (size_t) i * np;
         double time, tl; uint32_t f;
@@ -797,21 +1090,20 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         RFrame rf;
         if (have_chains) rf = make_rframe(E, time, f, tl);
         else { rf.y = f; rf.yn = (f + 1) % (uint32_t) E->frames.size(); rf.w = 1.0 - tl; rf.str_cos = ease_strength(0.5, 0.5, rf.w, LibmCos()); }
-        if (E->p.keep_background) launch_background(E, rc, rf, d_bg);
+        rf.dst = i;
         if (!have_chains) {
-            if (E->p.keep_background) cudaMemcpyAsync(dst, d_bg, np * 4, cudaMemcpyDeviceToDevice, E->stream);
+            if (E->p.keep_background) launch_background(E, rc, rf, dst);
             else cudaMemsetAsync(dst, 0, np * 4, E->stream);
             continue;
         }
-        bool single = E->nchains == 1;
         if (rc.feather == 0) {
-            launch_scatter(E, rc, rf);
-            if (single) k_gather_composite<true><<<grid2d(rc.width, rc.height), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
-            else        k_gather_composite<false><<<grid2d(rc.width, rc.height), dim3(32, 8), 0, E->stream>>>(E->ab_head, E->ab_rec, rc, rf.y, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, dst);
-            E->launches++;
+            if (E->p.keep_background) launch_background(E, rc, rf, d_bg + (size_t) nb * np);
+            rb.f[nb++] = rf;
+            if (nb == NB) flush_batch();
             continue;
         }
-        launch_frame_entries(E, rc, rf, ac);
+        if (E->p.keep_background) launch_background(E, rc, rf, d_bg);
+        launch_frame_entries(E, rc, rf, -1, ac);
         uint32_t *px0 = E->blob_px, *pxo = E->blob_px + cv;
         uint8_t *layer0 = (uint8_t *) (E->blob_px + cv + E->ovf_cap), *layero = layer0 + cv;
         if (single)
@@ -821,15 +1113,15 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         E->launches++;
         launch_frame_cleanup(E);
     }
+    flush_batch();
     int rcode = AMX_OK;
     if (!out_is_device) {
         if (E->fail(cudaMemcpyAsync(out, d_dst, np * n * 4, cudaMemcpyDeviceToHost, E->stream), "render D2H")) rcode = AMX_ERR_CUDA;
     }
-    if (!out_is_device || d_bg) {
+    if (!out_is_device) {
         if (E->fail(cudaStreamSynchronize(E->stream), "render")) rcode = AMX_ERR_CUDA;
     }
     if (E->check("render")) rcode = AMX_ERR_CUDA;
-    dev_free(d_bg);
     if (rcode == AMX_OK && E->nchains > 1 && !out_is_device && E->d_ovf_used) {
         uint32_t used = 0;
         cudaMemcpy(&used, E->d_ovf_used, 4, cudaMemcpyDeviceToHost);
@@ -888,8 +1180,7 @@ int engine_render_blob(Engine *E, uint32_t blob, double t, uint64_t cap, uint16_
     RConst rc = make_rconst(E);
     Acc ac = make_acc(E);
     RFrame rf = make_rframe(E, time, f, tl);
-    rf.chain_only = (int32_t) c;
-    launch_frame_entries(E, rc, rf, ac);
+    launch_frame_entries(E, rc, rf, (int32_t) c, ac);
     size_t cv = E->canvas();
     std::vector<uint32_t> px(cv);
     std::vector<uint8_t> layer(cv);
