@@ -83,6 +83,8 @@ int amx_create(amx_ctx **out, int device) {
     amx_ctx *c = new (std::nothrow) amx_ctx();
     if (!c) return AMX_ERR_NOMEM;
     c->e.device = device;
+    cudaDeviceGetAttribute(&c->e.sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (c->e.sm_count < 1) c->e.sm_count = 148;
     if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AMX_ERR_CUDA; }
     c->e.own_stream = true;
     if (const char *nb = getenv("AMX_RENDER_BATCH")) c->e.render_batch = (uint32_t) std::max(1, atoi(nb));   // tuning knob (frames per launch pair)

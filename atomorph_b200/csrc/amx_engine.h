@@ -74,6 +74,7 @@ struct Fluid;   // amx_fluid.cu
 
 struct Engine {
     int          device = 0;
+    int          sm_count = 148;
     cudaStream_t stream = nullptr;
     bool         own_stream = false;
     std::string  err;
@@ -126,11 +127,15 @@ struct Engine {
     uint32_t *d_blob_avg = nullptr;        // [h][nchains] blob2pixel colour (AVERAGE) per frame/chain
     uint32_t *d_blob_distinct = nullptr;   // [nchains]   DISTINCT colour per chain (host mt19937(group))
     // per-pixel A-buffer of one render batch (amx_render.cu): counters, direct record slots, overflow lists
-    uint32_t *ab_cnt = nullptr;
-    uint4    *ab_slots = nullptr;
+    uint32_t *ab_cnt = nullptr;            // two buffers (ping-pong), each [RBATCH][canvas]
+    uint32_t  ab_parity = 0, ab_dirty[2] = {0, 0};
+    void     *d_render_stats = nullptr;
+    uint4    *ab_pair = nullptr, *ab_third = nullptr;
+    uint32_t *ab_cnt_base = nullptr;       // allocations behind ab_cnt / ab_pair (guard in front)
+    uint4    *ab_pair_base = nullptr;
     uint32_t *ab_ovf_head = nullptr;
     uint4    *ab_ovf_rec = nullptr;
-    uint32_t  render_batch = 4;            // frames per scatter/gather launch pair
+    uint32_t  render_batch = 2;            // frames per scatter/gather launch pair
     uint32_t *d_bg = nullptr;              // background images of one batch (keep_background)
     size_t    d_bg_cap = 0;
     // per-(pixel, blob) entries for the feather / per-blob paths (canvas sized + overflow hash)

@@ -35,6 +35,8 @@
  * (spline, h >= 4) read + P*4 B written.
  */
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <numeric>
@@ -46,7 +48,7 @@ namespace amx {
 
 #define MAXK 32
 #define K_SLOTS 3          // direct A-buffer slots per pixel
-#define RBATCH 4           // frames per launch
+#define RBATCH 2           // frames per launch (all of one key-frame interval)
 
 struct RConst {
     uint32_t width, height, cw, ch;
@@ -56,7 +58,6 @@ struct RConst {
     uint64_t A;
     uint32_t ovf_mask;     // ovf_cap - 1
     uint32_t feather;
-    uint32_t debug;
 };
 
 struct RFrame {
@@ -65,7 +66,9 @@ struct RFrame {
     double   b1, b2, b3, b4;      // Catmull-Rom basis at the local time
     double   w;                   // c1 / pt1 weight = 1 - local t
     double   str_cos;             // eased weight for COSINE fading (host libm)
+    double   str;                 // colour weight of every atom unless fading == PERLIN: w (LINEAR / NONE) or str_cos (COSINE)
     uint32_t dst;                 // index of the output image this frame is written to
+    uint32_t h2_swapped;          // h == 2 only: the spline's interval index is yn, not y (its controls are pt1 pt2 pt1 pt2)
 };
 
 // several frames per launch: the key points and end colours of an atom are loaded once per batch
@@ -74,17 +77,18 @@ struct RBatch {
     int32_t chain_only;           // >= 0: only this chain (per-blob fetch)
 };
 
-// Per-pixel A-buffer of one batch slot.  cnt[home] counts the atoms whose top-left splat target is `home`;
-// the first K_SLOTS of them sit in s[k][home], the others hang off ovf_head[home] as a list through
-// ovf_rec[atom].z.  Only cnt is cleared per batch: a list is walked for exactly cnt - K_SLOTS nodes.
+// Per-pixel A-buffer of one batch slot.  cnt[home] counts the atoms whose top-left splat target is `home`; the first
+// two of them sit side by side in pair[home] (one 32-byte sector per pixel), the third in third[home], the others
+// hang off ovf_head[home] as a list through ovf_rec[atom].z.  Only cnt is ever cleared: a list is walked for exactly
+// cnt - K_SLOTS nodes.
 // Record: x = colour, y = x_fract | y_fract << 8 | (chain & 0xffff) << 16, z = atom (direct) / next (overflow).
 struct ABuf {
     uint32_t *cnt;
-    uint4    *slots;              // [K_SLOTS][RBATCH][canvas]: slot k of batch slot b at slots + k*kstride + b*canvas
+    uint4    *pair;               // [RBATCH][canvas][2]
+    uint4    *third;              // [RBATCH][canvas]
     uint32_t *ovf_head;
     uint4    *ovf_rec;
-    size_t    canvas;             // stride between batch slots (cnt, slots, ovf_head)
-    size_t    kstride;            // stride between direct slots = RBATCH * canvas
+    size_t    canvas;             // stride between batch slots (cnt, pair/2, third, ovf_head)
     size_t    A;                  // stride between batch slots (ovf_rec)
 };
 
@@ -165,50 +169,66 @@ struct RIn {
 // per-interval inputs of one atom, converted once per batch
 struct AtomIn {
     pword  pt1, pt2;
-    double x1, y1, x2, y2;        // end points in 1/256 px units (exact integers)
+    double x1, y1, x2, y2;        // end points in pixels: (256 x + x_fract) / 256, exact
     ColD   c1, c2;
     uint32_t rc1, rc2;
     double lag, slope;
 };
 
+enum : int { M_NONE = 0, M_LINEAR = 1, M_SPLINE = 2 };
+
 // position + colour of one atom in one frame; false when the atom is clipped away
+template <int MOTION, bool PERLIN, bool H2>
 __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, const RFrame &rf, const AtomIn &in, size_t i, uint32_t atom,
                                             uint32_t *home, uint32_t *col, uint32_t *fract) {
     const size_t A = rc.A;
     const double inv256 = 0.00390625;
     // trajectory (morph.cpp:523-531)
     uint32_t x, y, xf, yf;
-    if (rc.motion == K_LINEAR) {
-        // lerp_point (amx_math.h / morph.cpp:1501-1515) on the pre-converted coordinates
+    if (MOTION == M_LINEAR) {
+        // lerp_point (amx_math.h / morph.cpp:1501-1515).  The reference interpolates in 1/256 px units and splits with
+        // /256; scaling by a power of two commutes with every rounding, so the same is done here in pixel units.
         double iw = 1.0 - rf.w;
         double xx = rf.w * in.x1 + iw * in.x2, yy = rf.w * in.y1 + iw * in.y2;
         if (xx >= 0.0 && yy >= 0.0) {
-            uint32_t ix = d2u_floor(xx * inv256) & 0xffffu, iy = d2u_floor(yy * inv256) & 0xffffu;
-            x = ix; y = iy;
-            xf = d2u_floor(xx - u2d(ix * 256u)) & 255u;
-            yf = d2u_floor(yy - u2d(iy * 256u)) & 255u;
+            uint32_t ix = d2u_floor(xx), iy = d2u_floor(yy);
+            xf = d2u_floor((xx - u2d(ix)) * 256.0) & 255u;
+            yf = d2u_floor((yy - u2d(iy)) * 256.0) & 255u;
+            x = ix & 0xffffu; y = iy & 0xffffu;
         } else lerp_point(in.pt1, in.pt2, rf.w, &x, &y, &xf, &yf);      // weight outside [0,1] (key frames not numbered 0..h-1)
-    } else if (rc.motion == K_SPLINE) {
-        // the four control columns are y-1, y, y+1, y+2 (cyclic): the outer two coincide with yn / y when h = 2 and are
-        // stored next to them otherwise; a control coordinate x + x_fract/256 is exactly (256 x + x_fract) / 256
-        double qx[4], qy[4];
-        const int pk[4] = {rf.p0, rf.p1, rf.p2, rf.p3};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if ((uint32_t) pk[k] == rf.y) { qx[k] = in.x1; qy[k] = in.y1; }
-            else if ((uint32_t) pk[k] == rf.yn) { qx[k] = in.x2; qy[k] = in.y2; }
-            else {
-                // npt == 4 here: slot 2 holds column y-1, slot 3 column y+2; anything else (the spline's interval index
-                // and the frame index disagree by rounding) comes from the unsorted table
-                pword q;
-                if ((uint32_t) pk[k] == (rf.y + rc.h - 1u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 2) * A + i];
-                else if ((uint32_t) pk[k] == (rf.y + 2u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 3) * A + i];
-                else q = ri.table[(size_t) pk[k] * A + atom];
-                qx[k] = u2d((uint32_t) pw_x256(q)); qy[k] = u2d((uint32_t) pw_y256(q));
+    } else if (MOTION == M_SPLINE) {
+        // the four control columns are p-1, p, p+1, p+2 (cyclic) of the spline's interval p: a control coordinate
+        // x + x_fract/256 is exactly (256 x + x_fract) / 256
+        double vx, vy;
+        if (H2) {
+            // two key frames: the controls alternate between the two end points
+            if (!rf.h2_swapped) {
+                vx = cr_eval(in.x2, in.x1, in.x2, in.x1, rf.b1, rf.b2, rf.b3, rf.b4);
+                vy = cr_eval(in.y2, in.y1, in.y2, in.y1, rf.b1, rf.b2, rf.b3, rf.b4);
+            } else {
+                vx = cr_eval(in.x1, in.x2, in.x1, in.x2, rf.b1, rf.b2, rf.b3, rf.b4);
+                vy = cr_eval(in.y1, in.y2, in.y1, in.y2, rf.b1, rf.b2, rf.b3, rf.b4);
             }
+        } else {
+            double qx[4], qy[4];
+            const int pk[4] = {rf.p0, rf.p1, rf.p2, rf.p3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((uint32_t) pk[k] == rf.y) { qx[k] = in.x1; qy[k] = in.y1; }
+                else if ((uint32_t) pk[k] == rf.yn) { qx[k] = in.x2; qy[k] = in.y2; }
+                else {
+                    // npt == 4 here: slot 2 holds column y-1, slot 3 column y+2; anything else (the spline's interval
+                    // index and the frame index disagree by rounding) comes from the unsorted table
+                    pword q;
+                    if ((uint32_t) pk[k] == (rf.y + rc.h - 1u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 2) * A + i];
+                    else if ((uint32_t) pk[k] == (rf.y + 2u) % rc.h) q = ri.pts[((size_t) rf.y * ri.npt + 3) * A + i];
+                    else q = ri.table[(size_t) pk[k] * A + atom];
+                    qx[k] = u2d((uint32_t) pw_x256(q)) * inv256; qy[k] = u2d((uint32_t) pw_y256(q)) * inv256;
+                }
+            }
+            vx = cr_eval(qx[0], qx[1], qx[2], qx[3], rf.b1, rf.b2, rf.b3, rf.b4);
+            vy = cr_eval(qy[0], qy[1], qy[2], qy[3], rf.b1, rf.b2, rf.b3, rf.b4);
         }
-        double vx = cr_eval(qx[0] * inv256, qx[1] * inv256, qx[2] * inv256, qx[3] * inv256, rf.b1, rf.b2, rf.b3, rf.b4);
-        double vy = cr_eval(qy[0] * inv256, qy[1] * inv256, qy[2] * inv256, qy[3] * inv256, rf.b1, rf.b2, rf.b3, rf.b4);
         split_spline_fast(vx, &x, &xf);
         split_spline_fast(vy, &y, &yf);
     } else {
@@ -219,9 +239,8 @@ __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, con
         if (x > rc.bx2 || x < rc.bx1 || y > rc.by2 || y < rc.by1) return false;
     }
     // colour (morph.cpp:537-550)
-    double str = rf.w;
-    if (rc.fading == K_COSINE) str = rf.str_cos;
-    else if (rc.fading == K_PERLIN) str = ease_strength(in.lag, in.slope, rf.w, DevCos());
+    double str = rf.str;
+    if (PERLIN) str = ease_strength(in.lag, in.slope, rf.w, DevCos());
     if (str >= 0.0 && str <= 1.0) *col = lerp_color_d(in.c1, in.c2, str);
     else *col = lerp_color(in.rc1, in.rc2, str);
     *home = y * rc.cw + x;
@@ -229,111 +248,128 @@ __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, con
     return true;
 }
 
-struct LiveCount { uint32_t n[RBATCH]; };     // live (sorted) atoms of the interval of each frame of the batch
+// diagnostics (amx_render_stats): pixels resolved by the ordered double replay, of which exact ties; overflow-list records
+struct RenderStats { unsigned long long generic, ties, overflow; };
 
-// One thread per sorted atom index.  The samples of all frames of the batch are computed first, then all slot-claiming
-// atomics are issued back to back (their round trips overlap), then the records are stored.
-__global__ void __launch_bounds__(256)
-k_scatter(RIn ri, RConst rc, RBatch rb, LiveCount live, uint32_t nb, ABuf ab) {
-    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rc.A) return;
-    const size_t A = rc.A;
+// raw render inputs of one sorted atom
+struct RawIn { pword pt1, pt2; uint32_t atom, c1, c2, chain; double lag, slope; };
 
-    uint32_t cur_y = 0xffffffffu;
-    AtomIn in;
-    in.lag = in.slope = 0.0;
-    uint32_t atom = 0, meta_chain = 0;
-    bool use = false;
-    uint32_t home[RBATCH], col[RBATCH], meta[RBATCH], who[RBATCH];
-    bool ok[RBATCH];
+template <bool PERLIN>
+__device__ __forceinline__ RawIn load_raw(const RIn &ri, size_t A, uint32_t y, size_t i) {
+    RawIn r;
+    const size_t o = (size_t) y * A + i;
+    r.pt1 = ri.pts[((size_t) y * ri.npt + 0) * A + i];
+    r.pt2 = ri.pts[((size_t) y * ri.npt + 1) * A + i];
+    r.atom = ri.atom[o];
+    r.c1 = ri.c1[o]; r.c2 = ri.c2[o];
+    r.chain = ri.chain ? ri.chain[o] : 0u;
+    r.lag = r.slope = 0.0;
+    if (PERLIN) { r.lag = ri.lag[o]; r.slope = ri.slope[o]; }
+    return r;
+}
+
+// records of one atom whose slots have been claimed but not yet stored
+struct Pending { uint32_t home[RBATCH], col[RBATCH], meta[RBATCH], k[RBATCH], who, okmask; };
+
+__device__ __forceinline__ void store_pending(const Pending &p, const ABuf &ab, RenderStats *__restrict__ stats) {
 #pragma unroll
     for (uint32_t s = 0; s < RBATCH; ++s) {
-        ok[s] = false;
-        if (s >= nb) continue;
-        const RFrame &rf = rb.f[s];
-        if (rf.y != cur_y) {                        // (re)load the interval: uniform across the grid
-            cur_y = rf.y;
-            use = i < live.n[s];
-            if (use && ri.chain) {
-                uint32_t chain = ri.chain[(size_t) rf.y * A + i];
-                meta_chain = (chain & 0xffffu) << 16;
-                if (rb.chain_only >= 0 && chain != (uint32_t) rb.chain_only) use = false;
-            }
-            if (use) {
-                const size_t o = (size_t) rf.y * A + i;
-                in.pt1 = ri.pts[((size_t) rf.y * ri.npt + 0) * A + i];
-                in.pt2 = ri.pts[((size_t) rf.y * ri.npt + 1) * A + i];
-                atom = ri.atom[o];
-                in.rc1 = ri.c1[o]; in.rc2 = ri.c2[o];
-                in.x1 = u2d((uint32_t) pw_x256(in.pt1)); in.y1 = u2d((uint32_t) pw_y256(in.pt1));
-                in.x2 = u2d((uint32_t) pw_x256(in.pt2)); in.y2 = u2d((uint32_t) pw_y256(in.pt2));
-                in.c1 = col_d(in.rc1);
-                in.c2 = col_d(in.rc2);
-                if (rc.fading == K_PERLIN) { in.lag = ri.lag[o]; in.slope = ri.slope[o]; }
-            }
-        }
-        if (!use) continue;
-        uint32_t fr;
-        ok[s] = atom_sample(ri, rc, rf, in, i, atom, &home[s], &col[s], &fr);
-        meta[s] = fr | meta_chain;
-        who[s] = atom;
-    }
-    // claim a slot in the A-buffer of every frame ...
-    uint32_t k[RBATCH];
-#pragma unroll
-    for (uint32_t s = 0; s < RBATCH; ++s)
-        if (ok[s]) { if (rc.debug & 1) k[s] = 0; else k[s] = atomicAdd(&ab.cnt[(size_t) s * ab.canvas + home[s]], 1u); }
-    // ... and store the records
-#pragma unroll
-    for (uint32_t s = 0; s < RBATCH; ++s) {
-        if (!ok[s] || (rc.debug & 2)) continue;
-        size_t hp = (size_t) s * ab.canvas + home[s];
-        if (k[s] < K_SLOTS) ab.slots[(size_t) k[s] * ab.kstride + hp] = make_uint4(col[s], meta[s], who[s], 0u);
+        if (!(p.okmask & (1u << s))) continue;
+        const size_t hp = (size_t) s * ab.canvas + p.home[s];
+        const uint4 rec = make_uint4(p.col[s], p.meta[s], p.who, 0u);
+        if (p.k[s] < 2u) ab.pair[2 * hp + p.k[s]] = rec;
+        else if (p.k[s] == 2u) ab.third[hp] = rec;
         else {
             // overflow: list through ovf_rec, indexed by the ORIGINAL atom (unique per frame)
-            uint32_t next = atomicExch(&ab.ovf_head[hp], who[s]);
-            ab.ovf_rec[(size_t) s * ab.A + who[s]] = make_uint4(col[s], meta[s], next, 0u);
+            uint32_t next = atomicExch(&ab.ovf_head[hp], p.who);
+            ab.ovf_rec[(size_t) s * ab.A + p.who] = make_uint4(p.col[s], p.meta[s], next, 0u);
+            if (stats) atomicAdd(&stats->overflow, 1ull);
         }
     }
 }
 
+// Persistent, software-pipelined: a thread walks the sorted atoms i, i + stride, ...  In one iteration it (1) takes the
+// inputs prefetched during the previous iteration and prefetches the next ones, (2) computes the samples of all frames
+// of the batch, (3) stores the records of the PREVIOUS atom, whose slot-claiming atomics were issued one iteration ago
+// and have had a whole iteration of arithmetic to come back, (4) issues the atomics of the current atom.  Neither
+// the input loads nor the atomics' round trips stall the arithmetic.  All frames of a batch share one interval y.
+template <int MOTION, bool PERLIN, bool H2>
+__global__ void __launch_bounds__(256, 3)
+k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, RenderStats *__restrict__ stats) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_live) return;
+    const size_t A = rc.A;
+    const double inv256 = 0.00390625;
+    const uint32_t y = rb.f[0].y;
+
+    Pending pend;
+    pend.okmask = 0u;
+    RawIn next = load_raw<PERLIN>(ri, A, y, i);
+    for (; i < n_live; i += stride) {
+        const RawIn raw = next;
+        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
+
+        Pending cur;
+        cur.okmask = 0u;
+        cur.who = raw.atom;
+        bool use = ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
+        if (rb.chain_only >= 0 && raw.chain != (uint32_t) rb.chain_only) use = false;
+        if (use) {
+            AtomIn in;
+            in.pt1 = raw.pt1; in.pt2 = raw.pt2;
+            in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
+            in.x2 = u2d((uint32_t) pw_x256(raw.pt2)) * inv256; in.y2 = u2d((uint32_t) pw_y256(raw.pt2)) * inv256;
+            in.rc1 = raw.c1; in.rc2 = raw.c2;
+            in.c1 = col_d(raw.c1); in.c2 = col_d(raw.c2);
+            in.lag = raw.lag; in.slope = raw.slope;
+            const uint32_t meta_chain = (raw.chain & 0xffffu) << 16;
+#pragma unroll
+            for (uint32_t s = 0; s < RBATCH; ++s) {
+                if (s >= nb) continue;
+                uint32_t fr;
+                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &cur.home[s], &cur.col[s], &fr)) {
+                    cur.meta[s] = fr | meta_chain;
+                    cur.okmask |= 1u << s;
+                }
+            }
+        }
+        store_pending(pend, ab, stats);
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s)
+            if (cur.okmask & (1u << s)) cur.k[s] = atomicAdd(&ab.cnt[(size_t) s * ab.canvas + cur.home[s]], 1u);
+        pend = cur;
+    }
+    store_pending(pend, ab, stats);
+}
+
 // ---------------------------------------------------------------------------------------- gather
 // Visit every contribution to pixel (px, py): f(atom, colour, n, chain16) with n the integer bilinear numerator.
-// Splat targets and their edge rules: morph.cpp:558-588.  `ab` is already offset to the batch slot.
+// Splat targets and their edge rules: morph.cpp:558-588.  `ab` is already offset to the batch slot.  (Generic path.)
 template <typename F>
 __device__ __forceinline__ void visit_contributions(const ABuf &ab, const RConst &rc, uint32_t px, uint32_t py, F f) {
-    // the four homes that can reach (px, py): counters and first slots are independent loads, issued together
-    uint32_t cn[4];
-    uint32_t hp[4];
-    uint4 first[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        uint32_t dx = k & 1, dy = k >> 1;
+        const uint32_t dx = k & 1, dy = k >> 1;
         bool ok = px >= dx && py >= dy;
-        uint32_t hx = px - dx, hy = py - dy;
+        const uint32_t hx = px - dx, hy = py - dy;
         if (k == 1) ok = ok && (hx < rc.bx2 || hx + 1 < rc.width);
         else if (k == 2) ok = ok && (hy < rc.by2 || hy + 1 < rc.height);
         else if (k == 3) ok = ok && ((hy < rc.by2 && hx < rc.bx2) || (hy + 1 < rc.height && hx + 1 < rc.width));
-        hp[k] = ok ? hy * rc.cw + hx : py * rc.cw + px;
-        cn[k] = ok ? ab.cnt[hp[k]] : 0u;
-        first[k] = ab.slots[hp[k]];                // unconditional: stale when the home is empty, never used then
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (cn[k] == 0) continue;
-        uint32_t dx = k & 1, dy = k >> 1;
+        if (!ok) continue;
+        const size_t hp = (size_t) hy * rc.cw + hx;
+        const uint32_t cn = ab.cnt[hp];
         auto emit = [&](uint32_t atom, const uint4 &r) {
             uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
             uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
             if (n) f(atom, r.x, n, r.y >> 16);
         };
-        emit(first[k].z, first[k]);
-#pragma unroll
-        for (int j = 1; j < K_SLOTS; ++j)
-            if (cn[k] > (uint32_t) j) { uint4 r = ab.slots[(size_t) j * ab.kstride + hp[k]]; emit(r.z, r); }
-        if (cn[k] > K_SLOTS) {
-            uint32_t i = ab.ovf_head[hp[k]];
-            for (uint32_t j = K_SLOTS; j < cn[k]; ++j) { uint4 r = ab.ovf_rec[i]; emit(i, r); i = r.z; }
+        if (cn > 0) { uint4 r = ab.pair[2 * hp]; emit(r.z, r); }
+        if (cn > 1) { uint4 r = ab.pair[2 * hp + 1]; emit(r.z, r); }
+        if (cn > 2) { uint4 r = ab.third[hp]; emit(r.z, r); }
+        if (cn > K_SLOTS) {
+            uint32_t i = ab.ovf_head[hp];
+            for (uint32_t j = K_SLOTS; j < cn; ++j) { uint4 r = ab.ovf_rec[i]; emit(i, r); i = r.z; }
         }
     }
 }
@@ -477,85 +513,169 @@ __device__ __forceinline__ uint32_t rdiv_small(uint32_t num, uint32_t den, float
     return q;
 }
 
-// FAST PATH of the fused gather: one chain at the position, at most MAXK contributions and no exact tie ->
-// 32-bit integer sums, no sort, no per-contribution double math.  Returns false when the generic ordered replay is
-// needed.  (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits.)
-template <bool SINGLE>
-__device__ __forceinline__ bool resolve_fast(const ABuf &ab, const RConst &rc, uint32_t px, uint32_t py, uint32_t *chain_out,
-                                             uint32_t *px_out, bool *empty) {
-    uint32_t R = 0, G = 0, B = 0, Av = 0;
-    uint32_t N = 0, cnt = 0, chain = 0xffffffffu;
-    bool mixed = false;
-    visit_contributions(ab, rc, px, py, [&](uint32_t, uint32_t col, uint32_t n, uint32_t c16) {
-        if (!SINGLE) {
-            if (chain == 0xffffffffu) chain = c16;
-            else if (c16 != chain) mixed = true;
-        }
-        if (cnt < MAXK) { R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; }
-        ++cnt;
-    });
-    *empty = (cnt == 0);
-    if (cnt == 0) return true;
-    if (mixed || cnt > MAXK) return false;
-    if (!SINGLE && rc.nchains > 65536u) return false;              // 16-bit chain tags are ambiguous: let the generic path look
-    bool tie = false;
-    float rcp_d2 = __frcp_rz(__uint2float_ru(2u * N));
-    uint32_t r = rdiv_small(R, N, rcp_d2, &tie), g = rdiv_small(G, N, rcp_d2, &tie), b = rdiv_small(B, N, rcp_d2, &tie), a;
-    if (rc.density == 0) a = 0;
-    else if (cnt >= rc.density) a = rdiv_small(Av, N, rcp_d2, &tie);
-    else {
-        unsigned long long num = (unsigned long long) Av * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
-        unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
-        unsigned long long q = n2 / d2;
-        tie |= (n2 - q * d2 == 0ull);
-        a = (uint32_t) q;
-    }
-    if (tie) return false;
-    *chain_out = SINGLE ? 0u : chain;   // the 16-bit tag is the chain itself here (nchains <= 65536)
-    *px_out = c_make(r, g, b, a);
-    return true;
-}
-
 // the A-buffer of batch slot `slot`
 __device__ __forceinline__ ABuf ab_at(ABuf ab, uint32_t slot) {
     size_t o = (size_t) slot * ab.canvas;
-    ab.cnt += o; ab.slots += o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
+    ab.cnt += o; ab.pair += 2 * o; ab.third += o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
     return ab;
 }
 
-// fused gather + composite (feather == 0): one thread per OUTPUT pixel, blockIdx.z = batch slot
+// ---- fused gather + composite (feather == 0) --------------------------------------------------------------------
+// One thread per CANVAS position.  The four homes that can reach the pixel are read with twelve INDEPENDENT loads
+// (counter + the 32-byte record pair of each home): no pointer chasing, and the two records of a pair are folded in
+// branch-free (a record beyond the counter gets weight 0), so a warp does not diverge on the common cases.  Third
+// records and overflow lists are rare and handled behind a vote.  The pixel is then resolved from exact integer sums.
+//
+// Template flags: SINGLE = one chain (no chain tags); COUNTED = density > 1, the only case where the NUMBER of
+// contributions with a non-zero weight enters the result (alpha scale min(1, count/density), morph.cpp:606-611);
+// otherwise "non-empty" is sum(n) > 0 and the count is only bounded through the homes' counters.
+#define PART_NONE 0xffffffffu
+#define PART_GENERIC 0xfffffffeu
+struct Part { uint32_t R, G, B, A, N, cnt, chain; };
+
+__device__ __forceinline__ uint32_t merge_chain(uint32_t a, uint32_t b) {
+    if (a == PART_NONE) return b;
+    if (b == PART_NONE) return a;
+    return a == b ? a : PART_GENERIC;
+}
+
+// fold one record into the sums of a pixel; on == false disables it (record beyond the counter / splat not allowed).
+// Byte extraction is one PRMT each; 255 - fract is fract ^ 255.
+template <bool SINGLE, bool COUNTED, int DX, int DY>
+__device__ __forceinline__ void fold(Part &P, const uint4 &r, bool on) {
+    const uint32_t fr = r.y ^ ((DX ? 0u : 0x00ffu) | (DY ? 0u : 0xff00u));      // (DX ? xf : 255 - xf) | (DY ? yf : 255 - yf) << 8
+    const uint32_t wx = __byte_perm(fr, 0, 0x4440), wy = on ? __byte_perm(fr, 0, 0x4441) : 0u;
+    const uint32_t n = wx * wy;
+    P.R += __byte_perm(r.x, 0, 0x4440) * n; P.G += __byte_perm(r.x, 0, 0x4441) * n;
+    P.B += __byte_perm(r.x, 0, 0x4442) * n; P.A += __byte_perm(r.x, 0, 0x4443) * n; P.N += n;
+    if (COUNTED) P.cnt += (n != 0u);
+    if (!SINGLE) { if (n) P.chain = merge_chain(P.chain, r.y >> 16); }
+}
+
+// the ordered double replay of one pixel (ties, several blobs, very long lists): rare, kept out of line so that its
+// local arrays and registers do not burden the gather kernel
 template <bool SINGLE>
+__device__ __noinline__ uint32_t resolve_generic(const ABuf *abuf, uint32_t slot, const RConst *rcp, const uint32_t *__restrict__ chain_of,
+                                                 const int32_t *__restrict__ boc, const uint32_t *__restrict__ blob_avg,
+                                                 const uint32_t *__restrict__ blob_distinct, uint32_t y_frame, uint32_t ux, uint32_t uy, uint32_t bgc) {
+    // abuf / rcp point at the kernel's __grid_constant__ parameters: nothing is copied to the caller's stack
+    const ABuf ab = ab_at(*abuf, slot);
+    const RConst rc = *rcp;
+    Over ov;
+    resolve_position<SINGLE>(ab, rc, chain_of, boc, ux, uy, [&](uint32_t ch, uint32_t p) {
+        ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
+    });
+    return ov.finish(bgc, rc.keep_background != 0);
+}
+
+template <bool SINGLE, bool COUNTED>
 __global__ void __launch_bounds__(256)
-k_gather_composite(ABuf abuf, RConst rc, RBatch rb,
-                   const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
-                   const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-                   const uint32_t *__restrict__ bg, uint32_t *__restrict__ out) {
-    uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
-    if (px >= rc.width || py >= rc.height) return;
+k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_clean, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+               const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+               const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+               const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= rc.cw || py >= rc.ch) return;
     const uint32_t slot = blockIdx.z, y_frame = rb.f[slot].y;
     const ABuf ab = ab_at(abuf, slot);
+    const uint32_t ci = py * rc.cw + px;
+    // this position's counter in the OTHER counter buffer (dirty from the previous batch) is cleared for the next batch
+    cnt_clean[(size_t) slot * ab.canvas + ci] = 0u;
+    if (px >= rc.width || py >= rc.height) return;
+
+    // homes (px - dx, py - dy); edge rules of the splat targets: morph.cpp:558-588
+    const bool hasx = px >= 1u, hasy = py >= 1u;
+    const uint32_t hx = px - 1u, hy = py - 1u;
+    const bool ok1 = hasx && (hx < rc.bx2 || px < rc.width);
+    const bool ok2 = hasy && (hy < rc.by2 || py < rc.height);
+    const bool ok3 = hasx && hasy && ((hy < rc.by2 && hx < rc.bx2) || (py < rc.height && px < rc.width));
+    // twelve independent loads at fixed offsets from this position (the buffers have a guard of cw + 1 positions in
+    // front, so the neighbours of the first row / column are readable; they are ignored through ok1..ok3)
+    const uint32_t *cp = ab.cnt + ci;
+    const uint4 *pp = ab.pair + 2 * (size_t) ci;
+    const ptrdiff_t up = -(ptrdiff_t) rc.cw;
+    const uint32_t h0 = ci, h1 = ci - 1u, h2 = ci - rc.cw, h3 = ci - rc.cw - 1u;
+    const uint32_t c0 = cp[0], c1 = ok1 ? cp[-1] : 0u, c2 = ok2 ? cp[up] : 0u, c3 = ok3 ? cp[up - 1] : 0u;
+    const uint4 a0 = pp[0], b0 = pp[1];
+    const uint4 a1 = pp[-2], b1 = pp[-1];
+    const uint4 a2 = pp[2 * up], b2 = pp[2 * up + 1];
+    const uint4 a3 = pp[2 * up - 2], b3 = pp[2 * up - 1];
     const size_t np = (size_t) rc.width * rc.height;
+    const size_t i = (size_t) py * rc.width + px;
+    const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+
+    Part P;
+    P.R = P.G = P.B = P.A = P.N = P.cnt = 0; P.chain = PART_NONE;
+    fold<SINGLE, COUNTED, 0, 0>(P, a0, c0 > 0u); fold<SINGLE, COUNTED, 0, 0>(P, b0, c0 > 1u);
+    fold<SINGLE, COUNTED, 1, 0>(P, a1, c1 > 0u); fold<SINGLE, COUNTED, 1, 0>(P, b1, c1 > 1u);
+    fold<SINGLE, COUNTED, 0, 1>(P, a2, c2 > 0u); fold<SINGLE, COUNTED, 0, 1>(P, b2, c2 > 1u);
+    fold<SINGLE, COUNTED, 1, 1>(P, a3, c3 > 0u); fold<SINGLE, COUNTED, 1, 1>(P, b3, c3 > 1u);
+    const uint32_t csum = c0 + c1 + c2 + c3;                      // upper bound of the contributions
+    bool generic = csum > MAXK;
+    const uint32_t cmax = max(max(c0, c1), max(c2, c3));
+    if (cmax > 2u) {
+        // third records: loaded only by the lanes that have one, folded in by every lane with weight 0 / 1
+        uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
+        if (c0 > 2u) t0 = ab.third[h0];
+        if (c1 > 2u) t1 = ab.third[h1];
+        if (c2 > 2u) t2 = ab.third[h2];
+        if (c3 > 2u) t3 = ab.third[h3];
+        fold<SINGLE, COUNTED, 0, 0>(P, t0, c0 > 2u); fold<SINGLE, COUNTED, 1, 0>(P, t1, c1 > 2u);
+        fold<SINGLE, COUNTED, 0, 1>(P, t2, c2 > 2u); fold<SINGLE, COUNTED, 1, 1>(P, t3, c3 > 2u);
+        if (!generic && cmax > K_SLOTS) {
+            // overflow lists: rare
+            const uint32_t hh[4] = {h0, h1, h2, h3}, cc[4] = {c0, c1, c2, c3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (cc[k] <= K_SLOTS) continue;
+                uint32_t ovf_i = ab.ovf_head[hh[k]];
+                for (uint32_t j = K_SLOTS; j < cc[k]; ++j) {
+                    const uint4 r = ab.ovf_rec[ovf_i];
+                    ovf_i = r.z;
+                    if (k == 0) fold<SINGLE, COUNTED, 0, 0>(P, r, true);
+                    else if (k == 1) fold<SINGLE, COUNTED, 1, 0>(P, r, true);
+                    else if (k == 2) fold<SINGLE, COUNTED, 0, 1>(P, r, true);
+                    else fold<SINGLE, COUNTED, 1, 1>(P, r, true);
+                }
+            }
+        }
+    }
     out += (size_t) rb.f[slot].dst * np;
-    size_t i = (size_t) py * rc.width + px;
-    uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
-    uint32_t chain = 0, pxl = 0;
-    bool empty = false;
-    if (resolve_fast<SINGLE>(ab, rc, px, py, &chain, &pxl, &empty)) {
-        if (empty) { out[i] = bgc; return; }
-        uint32_t col = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
-        if (!rc.keep_background) { out[i] = c_a(col) ? col : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
+    if (!generic && P.N == 0) { out[i] = bgc; return; }           // no contribution with a non-zero weight
+    if (!COUNTED) P.cnt = csum;
+    if (!SINGLE) generic = generic || P.chain == PART_GENERIC || rc.nchains > 65536u;   // 16-bit chain tags are ambiguous beyond 65536 chains
+    uint32_t pxl = 0;
+    if (!generic) {
+        // integer sums with exact rational rounding: the reference's result unless a quotient is an exact .5 tie
+        // (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits)
+        bool tie = false;
+        const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * P.N));
+        uint32_t cr = rdiv_small(P.R, P.N, rcp_d2, &tie), cg = rdiv_small(P.G, P.N, rcp_d2, &tie), cb = rdiv_small(P.B, P.N, rcp_d2, &tie), ca;
+        if (!COUNTED) ca = rc.density == 0 ? 0u : rdiv_small(P.A, P.N, rcp_d2, &tie);       // density 1: min(1, count/1) = 1
+        else if (P.cnt >= rc.density) ca = rdiv_small(P.A, P.N, rcp_d2, &tie);
+        else {
+            unsigned long long num = (unsigned long long) P.A * P.cnt, den = (unsigned long long) P.N * rc.density;   // round(cnt*A / (density*N))
+            unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
+            unsigned long long q = n2 / d2;
+            tie |= (n2 - q * d2 == 0ull);
+            ca = (uint32_t) q;
+        }
+        pxl = c_make(cr, cg, cb, ca);
+        generic = tie;
+        if (tie && stats) atomicAdd(&stats->ties, 1ull);
+    }
+    if (!generic) {
+        const uint32_t chain = SINGLE ? 0u : P.chain;           // the 16-bit tag is the chain itself here (nchains <= 65536)
+        uint32_t colr = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
+        if (!rc.keep_background) { out[i] = c_a(colr) ? colr : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
         Over ov;
-        ov.add(col);
+        ov.add(colr);
         out[i] = ov.finish(bgc, true);
         return;
     }
     // generic path: several blobs at the position, an exact tie, or a very long list
-    const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
-    Over ov;
-    resolve_position<SINGLE>(ab, rc, chain_of, boc, px, py, [&](uint32_t ch, uint32_t p) {
-        ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
-    });
-    out[i] = ov.finish(bgc, rc.keep_background != 0);
+    if (stats) atomicAdd(&stats->generic, 1ull);
+    out[i] = resolve_generic<SINGLE>(&abuf, slot, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct, y_frame, px, py, bgc);
 }
 
 // gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
@@ -784,10 +904,10 @@ void engine_render_free(Engine *E) {
     E->d_blob_of_chain = nullptr; E->d_blob_avg = nullptr; E->d_blob_distinct = nullptr;
     dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
     dev_free(E->d_ovf_used); dev_free(E->blob_px);
-    dev_free(E->ab_cnt); dev_free(E->ab_slots); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
+    dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_third); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
-    E->ab_cnt = nullptr; E->ab_slots = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
+    E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_third = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
 
@@ -809,7 +929,6 @@ static RConst make_rconst(Engine *E) {
     rc.nchains = E->nchains; rc.h = E->h; rc.A = E->A;
     rc.ovf_mask = E->ovf_cap ? E->ovf_cap - 1 : 0;
     rc.feather = (uint32_t) std::min<uint64_t>(E->p.feather, 253);
-    rc.debug = getenv("AMX_DEBUG") ? atoi(getenv("AMX_DEBUG")) : 0;
     return rc;
 }
 
@@ -847,11 +966,21 @@ int engine_render_prepare(Engine *E) {
     size_t cv = E->canvas();
     if (!E->ab_cnt) {
         // A-buffer for RBATCH frames: counters + K_SLOTS direct records per canvas position, overflow list per atom
-        if (!dev_alloc(E, (void **) &E->ab_cnt, RBATCH * cv * 4, "abuf counters") ||
-            !dev_alloc(E, (void **) &E->ab_slots, (size_t) K_SLOTS * RBATCH * cv * 16, "abuf slots") ||
+        // (cnt and pair get a guard of cw + 1 positions in front: the gather reads its left / upper neighbours unconditionally)
+        const size_t guard = (size_t) E->cw + 1;
+        if (!dev_alloc(E, (void **) &E->ab_cnt_base, (2 * RBATCH * cv + guard) * 4, "abuf counters") ||
+            !dev_alloc(E, (void **) &E->d_render_stats, sizeof(RenderStats), "render stats") ||
+            !dev_alloc(E, (void **) &E->ab_pair_base, ((size_t) 2 * RBATCH * cv + 2 * guard) * 16, "abuf record pairs") ||
+            !dev_alloc(E, (void **) &E->ab_third, (size_t) RBATCH * cv * 16, "abuf third records") ||
             !dev_alloc(E, (void **) &E->ab_ovf_head, RBATCH * cv * 4, "abuf overflow heads") ||
             !dev_alloc(E, (void **) &E->ab_ovf_rec, RBATCH * E->A * 16, "abuf overflow records"))
             return AMX_ERR_NOMEM;
+        // two counter buffers: the gather of a batch clears the one the previous batch used, so no memset per batch
+        E->ab_cnt = E->ab_cnt_base + guard;
+        E->ab_pair = E->ab_pair_base + 2 * guard;
+        cudaMemsetAsync(E->ab_cnt_base, 0, (2 * RBATCH * cv + guard) * 4, E->stream);
+        cudaMemsetAsync(E->d_render_stats, 0, sizeof(RenderStats), E->stream);
+        E->ab_parity = 0; E->ab_dirty[0] = E->ab_dirty[1] = 0;
     }
     // blob order / colours per (frame, chain)
     size_t m = (size_t) E->h * E->nchains;
@@ -943,6 +1072,8 @@ static RFrame make_rframe(Engine *E, double time, uint32_t f, double tl) {
     cr_basis(lt, &rf.b1, &rf.b2, &rf.b3, &rf.b4);
     rf.w = 1.0 - tl;
     rf.str_cos = ease_strength(0.5, 0.5, rf.w, LibmCos());
+    rf.str = E->p.fading == K_COSINE ? rf.str_cos : rf.w;
+    rf.h2_swapped = (E->h == 2 && (uint32_t) rf.p1 != rf.y) ? 1u : 0u;
     rf.dst = 0;
     return rf;
 }
@@ -988,28 +1119,53 @@ static void launch_background(Engine *E, const RConst &rc, const RFrame &rf, uin
 
 static dim3 grid2d(uint32_t w, uint32_t h) { return dim3(div_up(w, 32), div_up(h, 8)); }
 
+// AMX_KTIME=1: per-kernel device times (cudaEvents, one sync per launch) accumulated and printed -- diagnostics only
+struct KTime {
+    bool on; cudaEvent_t a, b; double tot[4]; uint64_t n[4];
+    KTime() : on(getenv("AMX_KTIME") != nullptr), a(nullptr), b(nullptr) { for (int i = 0; i < 4; ++i) { tot[i] = 0; n[i] = 0; } }
+    void begin(cudaStream_t st) { if (!on) return; if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, st); }
+    void end(cudaStream_t st, int k, uint32_t frames) {
+        if (!on) return;
+        cudaEventRecord(b, st); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b); tot[k] += ms; n[k] += frames;
+    }
+    ~KTime() { if (on) for (int k = 0; k < 2; ++k) if (n[k]) fprintf(stderr, "[AMX_KTIME] %s: %.2f us/frame over %llu frames\n", k ? "gather" : "scatter", 1000.0 * tot[k] / n[k], (unsigned long long) n[k]); }
+};
+static KTime g_ktime;
+
 static ABuf make_abuf(Engine *E) {
     ABuf ab;
     size_t cv = E->canvas();
-    ab.cnt = E->ab_cnt; ab.slots = E->ab_slots; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
-    ab.canvas = cv; ab.kstride = (size_t) RBATCH * cv; ab.A = E->A;
+    ab.cnt = E->ab_cnt + (size_t) E->ab_parity * RBATCH * cv; ab.pair = E->ab_pair; ab.third = E->ab_third; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
+    ab.canvas = cv; ab.A = E->A;
     return ab;
 }
 
 // scatter `nb` frames (<= RBATCH) into the slots of the A-buffer
+// (into the counter buffer E->ab_parity, which is clean by invariant)
 static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb) {
-    cudaMemsetAsync(E->ab_cnt, 0, (size_t) nb * E->canvas() * 4, E->stream);
     RIn ri;
     ri.pts = E->rpts; ri.c1 = E->rc1; ri.c2 = E->rc2; ri.atom = E->ratom; ri.chain = E->rchain;
     ri.lag = E->rlag; ri.slope = E->rslope; ri.npt = E->rnpt; ri.table = E->table;
-    LiveCount live;
-    uint32_t most = 0;
-    for (uint32_t s = 0; s < RBATCH; ++s) {
-        live.n[s] = s < nb ? E->r_live[rb.f[s].y] : 0u;
-        most = std::max(most, live.n[s]);
-    }
-    if (most == 0) return;
-    k_scatter<<<div_up(most, 256), 256, 0, E->stream>>>(ri, rc, rb, live, nb, make_abuf(E));
+    const uint32_t n_live = E->r_live[rb.f[0].y];
+    if (n_live == 0) return;
+    RenderStats *st = (RenderStats *) E->d_render_stats;
+    const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
+    // persistent grid: as many blocks as stay resident (queried once per kernel instance)
+#define AMX_SCATTER(M, P, H) do { \
+        static int per_sm = 0; \
+        if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
+        const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
+        k_scatter<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, make_abuf(E), st); } while (0)
+#define AMX_SCATTER_M(M) do { if (perlin) { if (h2) AMX_SCATTER(M, true, true); else AMX_SCATTER(M, true, false); } \
+                              else        { if (h2) AMX_SCATTER(M, false, true); else AMX_SCATTER(M, false, false); } } while (0)
+    g_ktime.begin(E->stream);
+    if (rc.motion == K_LINEAR) AMX_SCATTER_M(M_LINEAR);
+    else if (rc.motion == K_SPLINE) AMX_SCATTER_M(M_SPLINE);
+    else AMX_SCATTER_M(M_NONE);
+#undef AMX_SCATTER_M
+#undef AMX_SCATTER
+    g_ktime.end(E->stream, 0, nb);
     E->launches++;
 }
 
@@ -1027,6 +1183,7 @@ static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, 
     if (single) k_gather_entries<true><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(ab, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
     else        k_gather_entries<false><<<grid2d(rc.cw, rc.ch), dim3(32, 8), 0, E->stream>>>(ab, rc, rf.y, E->chain_of, boc, ac, px0, layer0, pxo, layero);
     E->launches++;
+    cudaMemsetAsync(ab.cnt, 0, cv * 4, E->stream);          // this path keeps the counter buffer it used clean itself
     size_t total = single ? cv : cv + E->ovf_cap;
     for (uint32_t l = 0; l < rc.feather; ++l) {
         if (single) k_feather_pass<true><<<div_up(total, 256), 256, 0, E->stream>>>(ac, rc, layer0, layero, l, total);
@@ -1076,11 +1233,21 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         // feather == 0: nb frames share one scatter and one fused gather/composite launch
         if (nb == 0) return;
         launch_scatter(E, rc, rb, nb);
-        dim3 grid(div_up(rc.width, 32), div_up(rc.height, 8), nb);
-        if (rc.debug & 4) { nb = 0; return; }
-        if (single) k_gather_composite<true><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst);
-        else        k_gather_composite<false><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst);
+        const uint32_t p = E->ab_parity, q = p ^ 1u;
+        uint32_t *cnt_other = E->ab_cnt + (size_t) q * RBATCH * cv;
+        // the gather clears slots [0, nb) of the other counter buffer; a longer dirty tail (previous batch was larger) is memset
+        if (E->ab_dirty[q] > nb) cudaMemsetAsync(cnt_other + (size_t) nb * cv, 0, (size_t) (E->ab_dirty[q] - nb) * cv * 4, E->stream);
+        dim3 grid(div_up(rc.cw, 32), div_up(rc.ch, 8), nb);
+        RenderStats *st = (RenderStats *) E->d_render_stats;
+#define AMX_GATHER(S, C) k_gather_pixel<S, C><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), cnt_other, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st)
+        const bool counted = rc.density > 1;
+        g_ktime.begin(E->stream);
+        if (single) { if (counted) AMX_GATHER(true, true); else AMX_GATHER(true, false); }
+        else        { if (counted) AMX_GATHER(false, true); else AMX_GATHER(false, false); }
+#undef AMX_GATHER
+        g_ktime.end(E->stream, 1, nb);
         E->launches++;
+        E->ab_dirty[q] = 0; E->ab_dirty[p] = nb; E->ab_parity = q;
         nb = 0;
     };
     for (uint32_t i = 0; i < n; ++i) {
@@ -1097,6 +1264,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             continue;
         }
         if (rc.feather == 0) {
+            if (nb > 0 && rb.f[0].y != rf.y) flush_batch();           // a batch stays inside one key-frame interval
             if (E->p.keep_background) launch_background(E, rc, rf, d_bg + (size_t) nb * np);
             rb.f[nb++] = rf;
             if (nb == NB) flush_batch();
@@ -1229,6 +1397,18 @@ int amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_
     if (!ctx || !n) return AMX_ERR_ARG;
     cudaSetDevice(ctx->e.device);
     return engine_render_blob(&ctx->e, blob, t, cap, xy_out, rgba_out, n, group);
+}
+int amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]) {
+    if (!ctx || !stats3) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    stats3[0] = stats3[1] = stats3[2] = 0;
+    if (!E->d_render_stats) return AMX_OK;
+    unsigned long long h[3];
+    if (E->fail(cudaMemcpyAsync(h, E->d_render_stats, sizeof h, cudaMemcpyDeviceToHost, E->stream), "render stats") ||
+        E->fail(cudaStreamSynchronize(E->stream), "render stats")) return AMX_ERR_CUDA;
+    for (int i = 0; i < 3; ++i) stats3[i] = h[i];
+    return AMX_OK;
 }
 int amx_background(amx_ctx *ctx, double t, uint32_t *out, int out_is_device) {
     if (!ctx || !out) return AMX_ERR_ARG;

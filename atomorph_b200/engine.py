@@ -276,6 +276,11 @@ class Engine:
         times = np.ascontiguousarray(np.atleast_1d(times), dtype=np.float64)
         self._ck(self.L.amx_render(self.h, _p(times), len(times), C.c_void_p(out_ptr), 1 if is_device else 0), "render")
 
+    def render_stats(self):
+        st = np.zeros(3, dtype=np.uint64)
+        self._ck(self.L.amx_render_stats(self.h, _p(st)), "render_stats")
+        return dict(generic=int(st[0]), ties=int(st[1]), overflow=int(st[2]))
+
     def render_blob(self, b, t):
         cap = self.cw * self.ch + 16
         xy = np.zeros((cap, 2), dtype=np.uint16)

@@ -339,6 +339,7 @@ def run_b200(args):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "render_stats": e.render_stats(),
         "match": {"rounds": int(args.match_rounds), "proposals_per_atom": args.match_rounds / 2.0, "cost_initial": cost0, "cost_matched": cost1},
     }
 

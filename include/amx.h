@@ -125,6 +125,10 @@ int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_
 int  amx_render_prepare(amx_ctx *ctx);
 /* n frames at times t[i] -> out[i*width*height ...] packed RGBA.  out_is_device: out is a device pointer. */
 int  amx_render(amx_ctx *ctx, const double *times, uint32_t n, uint32_t *out, int out_is_device);
+/* renderer diagnostics, cumulative since the render buffers were (re)built: [0] pixels resolved by the ordered double
+ * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
+ * went to an overflow list */
+int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
 /* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
  * returns count via *n (pixels in reference emission order), -1 in *n when the blob index is out of range */
 int  amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_t *xy_out, uint32_t *rgba_out, int64_t *n, uint64_t *group);
