@@ -16,6 +16,16 @@
  * block).  Cost arithmetic is exact 64-bit integer (the reference sums u64 squares in double,
  * exact below 2^53).
  *
+ * Two kernels do this.  k_swap_single / k_swap_multi run ONE round per launch straight on the table in
+ * L2 / HBM (32-48 B of global loads per proposal).  k_swap_tiled is the fast path for a long chain: an
+ * EPOCH scatters the atoms of the chain into tiles of 2^TB atoms through a per-epoch random bijection of
+ * the atom index (so that any two atoms share a tile with the same probability), each CTA loads its tile
+ * ONCE into shared memory (key points unpacked to 24-bit fixed point), runs R rounds of disjoint
+ * XOR-pairings inside the tile from shared memory, and writes the column back.  Global traffic per
+ * proposal drops by R (16-24 B per atom per epoch instead of 32-48 B per proposal) and a proposal costs
+ * about 45 instructions, so the kernel is bound by the issue rate, not by memory.  Over epochs every pair
+ * of atoms is proposed with equal probability, like the reference's uniform draw.
+ *
  * Algorithmic bytes per proposal: 32 B (h = 2) or 48 B (h >= 3) read,
  * +16 B written per accepted swap.
  */
@@ -119,6 +129,129 @@ k_swap_multi(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
     warp_add_stats(stats, prop, acc, gain);
 }
 
+// ---- shared-memory tiled rounds -----------------------------------------------------------------------------
+#define TILE_BITS 11                       // 2048 atoms per tile: 32 KB (h = 2) / 48 KB (h >= 3) of shared memory
+#define TILE_ATOMS (1u << TILE_BITS)
+#define TILE_THREADS 256
+#define TILE_MAX_ROUNDS 64                 // rounds per epoch (one load / store of the tile)
+
+// Per-epoch bijection u -> atom on k-bit indices: two multiply / xorshift rounds (each step is invertible mod 2^k).
+// Tile t owns u in [t * TILE_ATOMS, (t + 1) * TILE_ATOMS): a pseudo-random subset of the chain.
+struct TileMap { uint32_t a1, a2, c, s1, s2, mask; };
+__host__ __device__ __forceinline__ uint32_t tile_atom(const TileMap &tm, uint32_t u) {
+    uint32_t v = (u * tm.a1) & tm.mask;
+    v ^= v >> tm.s1;
+    v = (v * tm.a2 + tm.c) & tm.mask;
+    v ^= v >> tm.s2;
+    return v;
+}
+static TileMap make_tilemap(uint64_t seed, uint64_t stream, uint64_t epoch, unsigned k) {
+    TileMap tm;
+    uint64_t r1 = rng64(seed, 0x7111u + stream, epoch), r2 = rng64(seed, 0x7222u + stream, epoch);
+    tm.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+    tm.a1 = ((uint32_t) r1 | 1u) & tm.mask;
+    tm.a2 = ((uint32_t) (r1 >> 32) | 1u) & tm.mask;
+    tm.c = (uint32_t) r2 & tm.mask;
+    tm.s1 = std::max(1u, k / 2);
+    tm.s2 = std::max(1u, (k + 1) / 2);
+    return tm;
+}
+
+// key point in shared memory: x in 1/256 px (24 bits) | flags << 24 in the low word, y in 1/256 px in the high word
+__device__ __forceinline__ uint2 kp_unpack(pword w) {
+    return make_uint2((uint32_t) pw_x256(w) | (pw_flags(w) << 24), (uint32_t) pw_y256(w));
+}
+__device__ __forceinline__ pword kp_pack(uint2 p) {
+    uint32_t x = p.x & 0xffffffu, f = p.x >> 24;
+    return pw_make(x >> 8, p.y >> 8, x & 255u, p.y & 255u, f);
+}
+__device__ __forceinline__ unsigned long long kp_dist(uint2 a, uint2 b) {
+    long long dx = (long long) (int) (a.x & 0xffffffu) - (long long) (int) (b.x & 0xffffffu);
+    long long dy = (long long) (int) a.y - (long long) (int) b.y;
+    return (unsigned long long) (dx * dx) + (unsigned long long) (dy * dy);
+}
+
+// One CTA = one tile.  `rounds` rounds of TILE_ATOMS / 2 disjoint proposals each, all inside shared memory.
+// Slots whose atom index falls behind the chain (w not a power of two) are marked invalid and never proposed.
+template <bool H2>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pword *__restrict__ next, uint64_t off, uint32_t w,
+             TileMap tm, uint32_t tile0, uint32_t rounds, uint64_t seed, uint64_t round_base, unsigned long long *__restrict__ stats) {
+    extern __shared__ uint2 sm[];
+    uint2 *s_col = sm, *s_next = sm + TILE_ATOMS, *s_prev = sm + 2 * TILE_ATOMS;     // s_prev only when !H2
+    const uint32_t tile = tile0 + blockIdx.x;
+    const uint32_t ubase = tile << TILE_BITS;
+    // load: atom index from the bijection (recomputed at write-back), invalid slots get flag byte 0xff
+    for (uint32_t j = threadIdx.x; j < TILE_ATOMS; j += TILE_THREADS) {
+        uint32_t a = tile_atom(tm, ubase + j);
+        if (a < w) {
+            s_col[j] = kp_unpack(col[off + a]);
+            s_next[j] = kp_unpack(next[off + a]);
+            if (!H2) s_prev[j] = kp_unpack(prev[off + a]);
+        } else {
+            s_col[j] = make_uint2(0xff000000u, 0u);
+        }
+    }
+    // pairing masks of the epoch's rounds inside this tile: uniform over the non-zero TILE_BITS-bit values
+    __shared__ uint32_t s_mask[TILE_MAX_ROUNDS];
+    for (uint32_t r = threadIdx.x; r < rounds; r += TILE_THREADS)
+        s_mask[r] = 1u + (uint32_t) (rng64(seed, 0x5157u + tile, round_base + r) % (TILE_ATOMS - 1u));
+    __syncthreads();
+    unsigned prop = 0, acc = 0;
+    unsigned long long gain = 0;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t m = s_mask[r];
+        const unsigned topbit = 31u - __clz(m);
+        const uint32_t lowmask = (1u << topbit) - 1u;
+#pragma unroll
+        for (uint32_t q = 0; q < TILE_ATOMS / 2 / TILE_THREADS; ++q) {
+            const uint32_t t = q * TILE_THREADS + threadIdx.x;
+            const uint32_t i = ((t & ~lowmask) << 1) | (t & lowmask);        // t with a zero inserted at m's top bit
+            const uint32_t j = i ^ m;
+            const uint2 a = s_col[i], b = s_col[j];
+            if ((a.x >> 24) == 0xffu || (b.x >> 24) == 0xffu) continue;       // padding slot
+            const uint2 an = s_next[i], bn = s_next[j];
+            unsigned long long c1, c2;
+            if (H2) {
+                c1 = kp_dist(a, an) + kp_dist(b, bn);
+                c2 = kp_dist(b, an) + kp_dist(a, bn);
+            } else {
+                const uint2 ap = s_prev[i], bp = s_prev[j];
+                c1 = kp_dist(ap, a) + kp_dist(a, an) + kp_dist(bp, b) + kp_dist(b, bn);
+                c2 = kp_dist(ap, b) + kp_dist(b, an) + kp_dist(bp, a) + kp_dist(a, bn);
+            }
+            ++prop;
+            if (c1 >= c2) {                // thread.cpp:1022 -- equal cost is accepted
+                s_col[i] = b; s_col[j] = a;
+                ++acc;
+                gain += H2 ? 2ull * (c1 - c2) : (c1 - c2);
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t j = threadIdx.x; j < TILE_ATOMS; j += TILE_THREADS) {
+        uint32_t a = tile_atom(tm, ubase + j);
+        if (a < w) col[off + a] = kp_pack(s_col[j]);
+    }
+    warp_add_stats(stats, prop, acc, gain);
+}
+
+// owned slots of an epoch <-> contiguous buffer (multi-GPU: rank r runs tiles [r * T / N, (r + 1) * T / N))
+__global__ void __launch_bounds__(256)
+k_pack_tiled(const pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t u0, uint32_t n, pword *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = tile_atom(tm, u0 + i);
+    out[i] = a < w ? col[off + a] : 0ull;
+}
+__global__ void __launch_bounds__(256)
+k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t n, const pword *__restrict__ in) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = tile_atom(tm, i);
+    if (a < w) col[off + a] = in[i];
+}
+
 // ---- multi-GPU atom-range sharding (h = 2: a single free column) ----------------------
 // An EPOCH fixes `sel_mask` (log2 N index bits): rank r owns the atoms whose selected bits equal r and only
 // draws pairing masks with zeros on those bits, so every pair stays inside the rank's slice.  Between epochs
@@ -197,10 +330,61 @@ k_cost(const pword *__restrict__ table, const uint32_t *__restrict__ chain_of, c
     }
 }
 
+static unsigned ceil_log2(uint64_t w) { unsigned k = 0; while ((1ull << k) < w) ++k; return k; }
+
+// true when the chain is long enough for the shared-memory tiled path
+static bool tiled_ok(Engine *E, uint32_t chain) {
+    uint64_t w = E->chain_off[chain + 1] - E->chain_off[chain];
+    return w >= 4ull * TILE_ATOMS && w <= 0x80000000ull;
+}
+
+// One EPOCH of the tiled path on column y of `chain`: `rounds` (<= TILE_MAX_ROUNDS) rounds inside every tile of the
+// rank's share [rank * T / nranks, (rank + 1) * T / nranks) of the T tiles.
+int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks) {
+    if (chain >= E->nchains || y >= E->h || rounds == 0 || rounds > TILE_MAX_ROUNDS || nranks == 0 || rank >= nranks || !tiled_ok(E, chain))
+        return AMX_ERR_ARG;
+    const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    const unsigned k = ceil_log2(w);
+    const uint32_t ntiles = 1u << (k - TILE_BITS);
+    const uint32_t t0 = (uint32_t) ((uint64_t) ntiles * rank / nranks), t1 = (uint32_t) ((uint64_t) ntiles * (rank + 1) / nranks);
+    if (t1 <= t0) return AMX_OK;
+    const TileMap tm = make_tilemap(E->p.seed, chain, epoch, k);
+    const uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
+    pword *col = E->table + (size_t) y * E->A;
+    const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
+    const bool h2 = E->h == 2;
+    const size_t smem = (size_t) (h2 ? 2 : 3) * TILE_ATOMS * sizeof(uint2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_swap_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_ATOMS * (int) sizeof(uint2));
+        cudaFuncSetAttribute(k_swap_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_ATOMS * (int) sizeof(uint2));
+        attr_set = true;
+    }
+    unsigned long long *st = (unsigned long long *) E->d_swapstats;
+    if (h2) k_swap_tiled<true><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, rounds, E->p.seed, epoch * TILE_MAX_ROUNDS, st);
+    else    k_swap_tiled<false><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, rounds, E->p.seed, epoch * TILE_MAX_ROUNDS, st);
+    E->launches++;
+    E->render_ready = false;
+    return E->check("tiled swap epoch") ? AMX_ERR_CUDA : AMX_OK;
+}
+
 int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds) {
     if (E->nchains == 0 || E->h < 2) return AMX_OK;
     if (chain >= (int32_t) E->nchains || column >= (int32_t) E->h) return AMX_ERR_ARG;
     bool h2 = E->h == 2;
+    if ((chain >= 0 || E->nchains == 1) && tiled_ok(E, chain >= 0 ? (uint32_t) chain : 0u) && !E->swap_global_only) {
+        // long single chain: epochs of up to TILE_MAX_ROUNDS rounds in shared memory (one column per epoch)
+        const uint32_t c = chain >= 0 ? (uint32_t) chain : 0u;
+        while (rounds > 0) {
+            const uint32_t r = (uint32_t) std::min<uint64_t>(rounds, TILE_MAX_ROUNDS);
+            const uint64_t epoch = E->rng_round++;
+            const uint32_t y = column >= 0 ? (uint32_t) column : (uint32_t) (rng64(E->p.seed, 0xc01u, epoch) % E->h);
+            int rcode = engine_swap_tiled_epoch(E, c, y, epoch, r, 0, 1);
+            if (rcode != AMX_OK) return rcode;
+            rounds -= r;
+        }
+        return AMX_OK;
+    }
     for (uint64_t r = 0; r < rounds; ++r) {
         uint64_t round = E->rng_round++;
         uint32_t y = column >= 0 ? (uint32_t) column : (uint32_t) (rng64(E->p.seed, 0xc01u, round) % E->h);
@@ -315,6 +499,43 @@ int amx_swap_rounds_sharded(amx_ctx *ctx, uint32_t chain, int32_t column, uint64
     if (!ctx) return AMX_ERR_ARG;
     cudaSetDevice(ctx->e.device);
     return engine_swap_rounds_sharded(&ctx->e, chain, column, rounds, sel_mask, sel_val);
+}
+
+int amx_swap_tiled_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks) {
+    if (!ctx) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    return engine_swap_tiled_epoch(&ctx->e, chain, column, epoch, rounds, rank, nranks);
+}
+
+// the slots u of the epoch's bijection that rank `rank` owns, as a contiguous buffer (count = its tiles * 2^TILE_BITS)
+int amx_pack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rank, uint32_t nranks, void *d_out, uint64_t *count) {
+    if (!ctx || !d_out || chain >= ctx->e.nchains || column >= ctx->e.h || nranks == 0 || rank >= nranks || !tiled_ok(&ctx->e, chain)) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    const unsigned k = ceil_log2(w);
+    const uint32_t ntiles = 1u << (k - TILE_BITS);
+    const uint32_t t0 = (uint32_t) ((uint64_t) ntiles * rank / nranks), t1 = (uint32_t) ((uint64_t) ntiles * (rank + 1) / nranks);
+    const uint32_t n = (t1 - t0) << TILE_BITS;
+    if (count) *count = n;
+    if (n == 0) return AMX_OK;
+    k_pack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), t0 << TILE_BITS, n, (pword *) d_out);
+    E->launches++;
+    return E->check("pack tiled") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+// scatter the all-gathered slots (all ranks, slot order) back into the column
+int amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, const void *d_in) {
+    if (!ctx || !d_in || chain >= ctx->e.nchains || column >= ctx->e.h || !tiled_ok(&ctx->e, chain)) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    const unsigned k = ceil_log2(w);
+    const uint32_t n = 1u << k;
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), n, (const pword *) d_in);
+    E->launches++;
+    E->render_ready = false;
+    return E->check("unpack tiled") ? AMX_ERR_CUDA : AMX_OK;
 }
 
 int amx_pack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint64_t sel_val, void *d_out, uint64_t *count) {

@@ -252,6 +252,17 @@ class Engine:
     def unpack_owned(self, column, sel_mask, nranks, d_in_ptr, chain=0):
         self._ck(self.L.amx_unpack_owned(self.h, chain, column, int(sel_mask), int(nranks), C.c_void_p(d_in_ptr)), "unpack_owned")
 
+    def swap_tiled_epoch(self, epoch, rounds, column, rank=0, nranks=1, chain=0):
+        self._ck(self.L.amx_swap_tiled_epoch(self.h, chain, column, int(epoch), int(rounds), int(rank), int(nranks)), "swap_tiled_epoch")
+
+    def pack_tiled(self, epoch, column, rank, nranks, d_out_ptr, chain=0):
+        n = C.c_uint64(0)
+        self._ck(self.L.amx_pack_tiled(self.h, chain, column, int(epoch), int(rank), int(nranks), C.c_void_p(d_out_ptr), C.byref(n)), "pack_tiled")
+        return int(n.value)
+
+    def unpack_tiled(self, epoch, column, d_in_ptr, chain=0):
+        self._ck(self.L.amx_unpack_tiled(self.h, chain, column, int(epoch), C.c_void_p(d_in_ptr)), "unpack_tiled")
+
     def swap_stats(self):
         st = np.zeros(3, dtype=np.uint64)
         self._ck(self.L.amx_swap_stats(self.h, _p(st)), "swap_stats")

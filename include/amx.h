@@ -117,6 +117,14 @@ int  amx_swap_stats(amx_ctx *ctx, uint64_t stats3[3]);           /* cumulative s
 int  amx_swap_rounds_sharded(amx_ctx *ctx, uint32_t chain, int32_t column, uint64_t rounds, uint64_t sel_mask, uint64_t sel_val);
 int  amx_pack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint64_t sel_val, void *d_out, uint64_t *count);
 int  amx_unpack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint32_t nranks, const void *d_in);
+/* Shared-memory tiled path (long single chains; amx_swap_rounds uses it by itself on one GPU).  An EPOCH spreads the
+ * atoms of `chain` over tiles of 2048 through a bijection derived from (seed, chain, epoch) and runs `rounds` (<= 64)
+ * rounds inside each tile.  Multi-GPU: rank r of n runs its contiguous share of the tiles; amx_pack_tiled copies the
+ * slots the rank owns into a contiguous device buffer, the ranks all-gather those buffers (equal sizes when n divides
+ * the tile count) and amx_unpack_tiled scatters the gathered slots (rank-major = slot order) back into the column. */
+int  amx_swap_tiled_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks);
+int  amx_pack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rank, uint32_t nranks, void *d_out, uint64_t *count);
+int  amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, const void *d_in);
 int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_energy(chain*), thread.cpp:1109-1125, summed over chains */
 
 /* ---- K6 renderer (row a-R): morph::get_pixels / draw_atoms, morph.cpp:452-678, 1302-1421 ------- */

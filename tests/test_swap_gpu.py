@@ -114,3 +114,70 @@ def test_sharded_rounds_and_pack_unpack(reflib):
     after = e.chains()[0]["words"]
     assert _rows_are_permutation(before, after)
     assert e.cost() < c0
+
+
+def _big_engine(size=128, seed=1, **kw):
+    """square -> disc at `size`^2 through the whole device pipeline (size^2 atoms, one chain, h = 2)."""
+    e = eng.Engine(0, seed=seed, motion=eng.LINEAR, fading=eng.LINEAR, threads=0, cycle_length=1000, **kw)
+    e.load_images(scenes.square_to_disc(size))
+    e.step(8)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    return e
+
+
+def test_tiled_path_is_exact_and_converges_like_global_rounds(monkeypatch):
+    """The shared-memory tiled epochs (chains >= 8192 atoms) against the one-round-per-launch kernel on the same table and
+    the same number of proposals: rows stay permutations, the gain bookkeeping is exact, the cost curve is the same."""
+    e = _big_engine(128)
+    start = e.chains()
+    before = start[0]["words"].copy()
+    W = before.shape[1]
+    assert W == 128 * 128
+    c0 = e.cost()
+    st0 = e.swap_stats()
+    e.swap_rounds(2048, column=1)            # tiled: 32 epochs x 64 rounds
+    st = e.swap_stats()
+    c_tiled = e.cost()
+    after = e.chains()[0]["words"]
+    assert _rows_are_permutation(before, after), "a tiled epoch lost or duplicated a key point"
+    assert np.array_equal(before[0], after[0]), "column 0 must not move"
+    assert int(st[0] - st0[0]) == 2048 * W // 2
+    assert c0 - c_tiled == float(int(st[2] - st0[2]))
+    monkeypatch.setenv("AMX_SWAP_GLOBAL", "1")
+    g = _big_engine(128)
+    g.import_chains([dict(key=start[0]["key"], words=before, max_surface=start[0]["max_surface"])])
+    assert g.cost() == c0
+    g.swap_rounds(2048, column=1)
+    c_global = g.cost()
+    assert c_tiled <= 1.02 * c_global, (c_tiled, c_global)
+    assert c_global <= 1.02 * c_tiled, (c_tiled, c_global)
+
+
+def test_tiled_epochs_shard_across_ranks():
+    """Two virtual ranks on one GPU: each runs its half of the tiles of an epoch on its own copy of the table, the owned
+    slots are packed, concatenated like an all-gather and unpacked: both copies end up identical and improved."""
+    import torch
+    ea, eb = _big_engine(128), _big_engine(128)
+    start = ea.chains()
+    eb.import_chains([dict(key=start[0]["key"], words=start[0]["words"], max_surface=start[0]["max_surface"])])
+    c0 = ea.cost()
+    assert eb.cost() == c0
+    W = start[0]["width"]
+    for epoch in range(8):
+        bufs = []
+        for r, e in enumerate((ea, eb)):
+            e.swap_tiled_epoch(epoch, 32, 1, rank=r, nranks=2)
+            buf = torch.empty(W // 2, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            assert e.pack_tiled(epoch, 1, r, 2, buf.data_ptr()) == W // 2
+            e.sync()
+            bufs.append(buf)
+        gathered = torch.cat(bufs)
+        torch.cuda.synchronize()
+        for e in (ea, eb):
+            e.unpack_tiled(epoch, 1, gathered.data_ptr())
+            e.sync()
+        wa, wb = ea.chains()[0]["words"], eb.chains()[0]["words"]
+        assert np.array_equal(wa, wb)
+    assert np.array_equal(np.sort(wa[1]), np.sort(start[0]["words"][1]))
+    assert ea.cost() < 0.5 * c0
