@@ -338,10 +338,10 @@ static bool tiled_ok(Engine *E, uint32_t chain) {
     return w >= 4ull * TILE_ATOMS && w <= 0x80000000ull;
 }
 
-// One EPOCH of the tiled path on column y of `chain`: `rounds` (<= TILE_MAX_ROUNDS) rounds inside every tile of the
+// One EPOCH of the tiled path on column y of `chain`: `rounds` rounds (TILE_MAX_ROUNDS per launch) inside every tile of the
 // rank's share [rank * T / nranks, (rank + 1) * T / nranks) of the T tiles.
 int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks) {
-    if (chain >= E->nchains || y >= E->h || rounds == 0 || rounds > TILE_MAX_ROUNDS || nranks == 0 || rank >= nranks || !tiled_ok(E, chain))
+    if (chain >= E->nchains || y >= E->h || rounds == 0 || nranks == 0 || rank >= nranks || !tiled_ok(E, chain))
         return AMX_ERR_ARG;
     const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
     const unsigned k = ceil_log2(w);
@@ -361,9 +361,14 @@ int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
         attr_set = true;
     }
     unsigned long long *st = (unsigned long long *) E->d_swapstats;
-    if (h2) k_swap_tiled<true><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, rounds, E->p.seed, epoch * TILE_MAX_ROUNDS, st);
-    else    k_swap_tiled<false><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, rounds, E->p.seed, epoch * TILE_MAX_ROUNDS, st);
-    E->launches++;
+    // more than TILE_MAX_ROUNDS rounds: further launches on the SAME tiles (same bijection) with fresh pairing masks
+    for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
+        const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
+        const uint64_t round_base = (epoch << 20) + done;
+        if (h2) k_swap_tiled<true><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, r, E->p.seed, round_base, st);
+        else    k_swap_tiled<false><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, r, E->p.seed, round_base, st);
+        E->launches++;
+    }
     E->render_ready = false;
     return E->check("tiled swap epoch") ? AMX_ERR_CUDA : AMX_OK;
 }

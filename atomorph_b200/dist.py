@@ -95,6 +95,44 @@ def scatter_gathered(column, gathered, width, sel_mask, world):
     return column
 
 
+# ------------------------------------------------------------------ tile-range ownership (long chains, amx_swap.cu k_swap_tiled)
+TILE_BITS = 11
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    z = (z + 0x9e3779b97f4a7c15) & _M64
+    z = ((z ^ (z >> 30)) * 0xbf58476d1ce4e5b9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94d049bb133111eb) & _M64
+    return z ^ (z >> 31)
+
+
+def _rng64(seed, stream, counter):
+    return _mix64(_mix64((seed ^ ((stream * 0xd1342543de82ef95) & _M64)) & _M64) ^ ((counter * 0x2545f4914f6cdd1d) & _M64))
+
+
+def tile_slots(width, seed, chain, epoch):
+    """numpy mirror of the epoch's bijection (amx_swap.cu: make_tilemap / tile_atom): atom index of every slot u in
+    [0, 2^k).  Slots whose atom is >= width are padding.  Rank r of n owns slots [r * 2^k / n, (r + 1) * 2^k / n)."""
+    k = max(1, int(width - 1).bit_length())
+    mask = (1 << k) - 1 if k < 32 else 0xffffffff
+    r1, r2 = _rng64(seed, 0x7111 + chain, epoch), _rng64(seed, 0x7222 + chain, epoch)
+    a1 = ((r1 & 0xffffffff) | 1) & mask
+    a2 = (((r1 >> 32) & 0xffffffff) | 1) & mask
+    c = (r2 & 0xffffffff) & mask
+    s1, s2 = max(1, k // 2), max(1, (k + 1) // 2)
+    u = np.arange(1 << k, dtype=np.uint64)
+    v = (u * np.uint64(a1)) & np.uint64(mask)
+    v ^= v >> np.uint64(s1)
+    v = (v * np.uint64(a2) + np.uint64(c)) & np.uint64(mask)
+    v ^= v >> np.uint64(s2)
+    return v
+
+
+def tiled_supported(width):
+    return width >= 4 * (1 << TILE_BITS)
+
+
 # ------------------------------------------------------------------ device orchestration
 class ShardedMatcher:
     """Atom-range sharded pair-swap rounds for a single-chain, h = 2 morph (BASELINE config 2)."""
@@ -111,12 +149,24 @@ class ShardedMatcher:
         self.device = device
         self.send = torch.empty(self.slots, dtype=torch.int64, device=device)
         self.recv = torch.empty(self.slots * world, dtype=torch.int64, device=device)
+        ntiles = (1 << k) >> TILE_BITS
+        self.tiled = tiled_supported(self.width) and ntiles % world == 0
 
     def run_epoch(self, rounds, column=1):
         """`rounds` sharded rounds on `column`, then one all-gather of that column."""
         import torch.distributed as dist
         if self.world == 1:
             self.e.swap_rounds(rounds, chain=0, column=column, want_stats=False)
+            return
+        if self.tiled:
+            # long chain: every rank refines its share of the epoch's shared-memory tiles, then the owned slots travel
+            ep = self.epoch
+            self.epoch += 1
+            self.e.swap_tiled_epoch(ep, rounds, column, rank=self.rank, nranks=self.world)
+            n = self.e.pack_tiled(ep, column, self.rank, self.world, self.send.data_ptr())
+            assert n == self.slots
+            dist.all_gather_into_tensor(self.recv, self.send)      # NCCL over NVLink: W*8 B per epoch
+            self.e.unpack_tiled(ep, column, self.recv.data_ptr())
             return
         mask = select_mask(self.width, self.world, self.epoch, self.seed)
         self.epoch += 1

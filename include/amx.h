@@ -118,8 +118,8 @@ int  amx_swap_rounds_sharded(amx_ctx *ctx, uint32_t chain, int32_t column, uint6
 int  amx_pack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint64_t sel_val, void *d_out, uint64_t *count);
 int  amx_unpack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t sel_mask, uint32_t nranks, const void *d_in);
 /* Shared-memory tiled path (long single chains; amx_swap_rounds uses it by itself on one GPU).  An EPOCH spreads the
- * atoms of `chain` over tiles of 2048 through a bijection derived from (seed, chain, epoch) and runs `rounds` (<= 64)
- * rounds inside each tile.  Multi-GPU: rank r of n runs its contiguous share of the tiles; amx_pack_tiled copies the
+ * atoms of `chain` over tiles of 2048 through a bijection derived from (seed, chain, epoch) and runs `rounds` rounds
+ * inside each tile (64 per launch).  Multi-GPU: rank r of n runs its contiguous share of the tiles; amx_pack_tiled copies the
  * slots the rank owns into a contiguous device buffer, the ranks all-gather those buffers (equal sizes when n divides
  * the tile count) and amx_unpack_tiled scatters the gathered slots (rank-major = slot order) back into the column. */
 int  amx_swap_tiled_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks);

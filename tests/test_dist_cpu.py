@@ -49,6 +49,18 @@ def test_owned_atoms_partition_the_chain(width):
                 assert np.all((idx & np.uint64(mask)) == np.uint64(val))
 
 
+@pytest.mark.parametrize("width", [8192, 10000, 1 << 15])
+def test_tile_slots_are_a_bijection(width):
+    k = int(width - 1).bit_length()
+    for epoch in range(4):
+        v = amd.tile_slots(width, seed=1, chain=0, epoch=epoch)
+        assert np.array_equal(np.sort(v), np.arange(1 << k, dtype=np.uint64))
+        # tiles are pseudo-random subsets: the atoms of one tile are spread over the whole chain
+        t0 = np.sort(v[: 1 << amd.TILE_BITS].astype(np.int64))
+        assert t0[-1] - t0[0] > (1 << k) // 2
+    assert not np.array_equal(amd.tile_slots(width, 1, 0, 0), amd.tile_slots(width, 1, 0, 1))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -81,6 +93,24 @@ def _worker(rank, world, port, width, q):
         recv = [torch.zeros(len(idx), dtype=torch.int64) for _ in range(world)]
         dist.all_gather(recv, torch.from_numpy(send))
         column = amd.scatter_gathered(column, [r.numpy().astype(np.uint64) for r in recv], width, mask, world)
+    # tile-range sharding (long chains): rank r owns the slots [r * 2^k / world, (r + 1) * 2^k / world) of the epoch's bijection
+    if width >= 64:
+        k = int(width - 1).bit_length()
+        n = (1 << k) // world
+        for epoch in range(3):
+            slots = amd.tile_slots(width, seed=9, chain=0, epoch=epoch)
+            mine = slots[rank * n:(rank + 1) * n]
+            ok = mine < width
+            own = mine[ok].astype(np.int64)
+            vals = column[own]
+            column[own] = vals[np.argsort(other[own] ^ np.uint64(epoch + 7), kind="stable")]
+            send = np.zeros(n, dtype=np.int64)
+            send[ok] = column[own].astype(np.int64)
+            recv = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(recv, torch.from_numpy(send))
+            allv = np.concatenate([r.numpy().astype(np.uint64) for r in recv])
+            okall = slots < width
+            column[slots[okall].astype(np.int64)] = allv[okall]
     q.put((rank, column, original))
     dist.destroy_process_group()
 

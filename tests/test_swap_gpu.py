@@ -157,6 +157,7 @@ def test_tiled_epochs_shard_across_ranks():
     """Two virtual ranks on one GPU: each runs its half of the tiles of an epoch on its own copy of the table, the owned
     slots are packed, concatenated like an all-gather and unpacked: both copies end up identical and improved."""
     import torch
+    from atomorph_b200 import dist as amd
     ea, eb = _big_engine(128), _big_engine(128)
     start = ea.chains()
     eb.import_chains([dict(key=start[0]["key"], words=start[0]["words"], max_surface=start[0]["max_surface"])])
@@ -171,6 +172,9 @@ def test_tiled_epochs_shard_across_ranks():
             torch.cuda.synchronize()
             assert e.pack_tiled(epoch, 1, r, 2, buf.data_ptr()) == W // 2
             e.sync()
+            # the numpy mirror of the bijection (dist.tile_slots) names the same atoms
+            slots = amd.tile_slots(W, 1, 0, epoch)[r * (W // 2):(r + 1) * (W // 2)].astype(np.int64)
+            assert np.array_equal(buf.cpu().numpy().astype(np.uint64), e.chains()[0]["words"][1][slots])
             bufs.append(buf)
         gathered = torch.cat(bufs)
         torch.cuda.synchronize()
