@@ -20,22 +20,29 @@ namespace amx {
 
 int engine_alloc_chains(Engine *E, uint32_t nchains, const uint64_t *keys, const uint64_t *widths, const uint64_t *max_surface, uint32_t height) {
     cudaStreamSynchronize(E->stream);
-    dev_free(E->table); dev_free(E->chain_of); dev_free(E->d_chain_off);
-    E->table = nullptr; E->chain_of = nullptr; E->d_chain_off = nullptr;
-    engine_render_free(E);
+    std::vector<uint64_t> offs(nchains + 1, 0);
+    for (uint32_t c = 0; c < nchains; ++c) offs[c + 1] = offs[c] + widths[c];
+    // same geometry as before (a table re-import): every device buffer, the render buffers included, is kept
+    const bool same = E->table && E->chain_of && E->d_chain_off && E->nchains == nchains && E->h == height && E->chain_off == offs;
+    if (!same) {
+        dev_free(E->table); dev_free(E->chain_of); dev_free(E->d_chain_off);
+        E->table = nullptr; E->chain_of = nullptr; E->d_chain_off = nullptr;
+        engine_render_free(E);
+    }
+    E->render_ready = false;
     E->nchains = nchains; E->h = height;
     E->chain_key.assign(keys, keys + nchains);
     E->chain_max_surface.assign(max_surface, max_surface + nchains);
     E->chain_off.assign(nchains + 1, 0);
     for (uint32_t c = 0; c < nchains; ++c) E->chain_off[c + 1] = E->chain_off[c] + widths[c];
     E->A = E->chain_off[nchains];
-    if (!dev_alloc(E, (void **) &E->table, (size_t) height * E->A * 8, "chain table") ||
-        !dev_alloc(E, (void **) &E->chain_of, E->A * 4, "chain_of") ||
-        !dev_alloc(E, (void **) &E->d_chain_off, (size_t) (nchains + 1) * 8, "chain_off"))
+    if (!same && (!dev_alloc(E, (void **) &E->table, (size_t) height * E->A * 8, "chain table") ||
+                  !dev_alloc(E, (void **) &E->chain_of, E->A * 4, "chain_of") ||
+                  !dev_alloc(E, (void **) &E->d_chain_off, (size_t) (nchains + 1) * 8, "chain_off")))
         return AMX_ERR_NOMEM;
-    std::vector<uint32_t> cof(E->A);
-    for (uint32_t c = 0; c < nchains; ++c) std::fill(cof.begin() + E->chain_off[c], cof.begin() + E->chain_off[c + 1], c);
-    if (E->fail(cudaMemcpyAsync(E->chain_of, cof.data(), E->A * 4, cudaMemcpyHostToDevice, E->stream), "chain_of H2D") ||
+    std::vector<uint32_t> cof(same ? 0 : E->A);
+    for (uint32_t c = 0; c < nchains && !same; ++c) std::fill(cof.begin() + E->chain_off[c], cof.begin() + E->chain_off[c + 1], c);
+    if ((!same && E->fail(cudaMemcpyAsync(E->chain_of, cof.data(), E->A * 4, cudaMemcpyHostToDevice, E->stream), "chain_of H2D")) ||
         E->fail(cudaMemcpyAsync(E->d_chain_off, E->chain_off.data(), (size_t) (nchains + 1) * 8, cudaMemcpyHostToDevice, E->stream), "chain_off H2D") ||
         E->fail(cudaStreamSynchronize(E->stream), "alloc chains"))
         return AMX_ERR_CUDA;

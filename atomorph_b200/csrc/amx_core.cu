@@ -105,6 +105,8 @@ void amx_destroy(amx_ctx *ctx) {
     dev_free(E->d_swapstats);
     dev_free(E->d_out);
     dev_free(E->d_perlin);
+    if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
+    for (int k = 0; k < 4; ++k) if (E->copy_ev[k]) cudaEventDestroy(E->copy_ev[k]);
     if (E->ev0) cudaEventDestroy(E->ev0);
     if (E->ev1) cudaEventDestroy(E->ev1);
     if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);

@@ -80,6 +80,9 @@ struct Engine {
     std::string  err;
     uint64_t     launches = 0;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;    // device -> host frame copies overlap rendering (amx_render with a host buffer)
+    cudaEvent_t  copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t     copy_ev_next = 0;
 
     Params p;
     uint32_t width = 0, height = 0, cw = 0, ch = 0;
@@ -124,6 +127,11 @@ struct Engine {
     uint32_t *ratom = nullptr, *rchain = nullptr;
     uint32_t  rnpt = 0;
     std::vector<uint32_t> r_live;          // live (drawn) atoms per interval
+    uint64_t  rbuf_A = 0, rbuf_cv = 0;     // geometry the render buffers were allocated for
+    uint32_t  rbuf_h = 0, rbuf_nchains = 0;
+    uint32_t *sort_buf = nullptr;          // radix-sort scratch of render prepare
+    void     *sort_tmp = nullptr;
+    size_t    sort_tmp_bytes = 0;
     int32_t  *d_blob_of_chain = nullptr;   // [h][nchains] blob vector index of chain c in frame y
     uint32_t *d_blob_avg = nullptr;        // [h][nchains] blob2pixel colour (AVERAGE) per frame/chain
     uint32_t *d_blob_distinct = nullptr;   // [nchains]   DISTINCT colour per chain (host mt19937(group))
@@ -147,6 +155,8 @@ struct Engine {
     uint32_t *d_ovf_used = nullptr;
     uint32_t *blob_px = nullptr;           // resolved per-(pixel,layer-0) colour for feather / per-blob fetch
     uint32_t *d_out = nullptr;             // staging for host output
+    uint32_t *d_pix = nullptr;             // staging for amx_render_pixels (RGBA + am::pixel records)
+    size_t    d_pix_cap = 0;
     uint64_t  d_out_cap = 0;
     int32_t  *d_perlin = nullptr;          // [2][512] lag / slope permutation tables (host generated)
     unsigned  perlin_seed_loaded = 0xffffffffu;

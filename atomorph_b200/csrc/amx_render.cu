@@ -848,6 +848,15 @@ k_sortkey(const pword *__restrict__ table, uint32_t y, uint32_t yn, size_t A, ui
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(live, (uint32_t) __popc(m));
 }
 
+// frame -> am::pixel records {u16 x, u16 y, r, g, b, a} (atomorph.h:249-254), what morph::get_pixels(t) hands out
+__global__ void __launch_bounds__(256)
+k_to_pixels(const uint32_t *__restrict__ rgba, uint32_t width, size_t np, uint2 *__restrict__ out) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    uint32_t x = (uint32_t) (i % width), y = (uint32_t) (i / width);
+    out[i] = make_uint2(x | (y << 16), rgba[i]);
+}
+
 // prepare: per SORTED atom & interval: key points, end colours with the one-sided alpha rule, Perlin lag/slope
 // (morph.cpp:495-548)
 __global__ void __launch_bounds__(256)
@@ -899,11 +908,13 @@ void engine_render_free(Engine *E) {
     dev_free(E->rc1); dev_free(E->rc2); dev_free(E->rlag); dev_free(E->rslope);
     E->rc1 = E->rc2 = nullptr; E->rlag = E->rslope = nullptr;
     dev_free(E->rpts); dev_free(E->ratom); dev_free(E->rchain);
+    dev_free(E->sort_buf); dev_free(E->sort_tmp); E->sort_buf = nullptr; E->sort_tmp = nullptr; E->sort_tmp_bytes = 0;
     E->rpts = nullptr; E->ratom = E->rchain = nullptr; E->rnpt = 0; E->r_live.clear();
     dev_free(E->d_blob_of_chain); dev_free(E->d_blob_avg); dev_free(E->d_blob_distinct);
     E->d_blob_of_chain = nullptr; E->d_blob_avg = nullptr; E->d_blob_distinct = nullptr;
     dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
     dev_free(E->d_ovf_used); dev_free(E->blob_px);
+    dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
     dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_third); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
@@ -951,6 +962,9 @@ int engine_render_prepare(Engine *E) {
     size_t n = (size_t) E->h * E->A;
     bool perlin = E->p.fading == K_PERLIN;
     const uint32_t npt = E->h >= 3 ? 4u : 2u;
+    // the render buffers are kept across table refreshes as long as the geometry is the same
+    if (E->rc1 && (E->rbuf_A != E->A || E->rbuf_h != E->h || E->rbuf_cv != E->canvas() || E->rbuf_nchains != E->nchains)) engine_render_free(E);
+    E->rbuf_A = E->A; E->rbuf_h = E->h; E->rbuf_cv = E->canvas(); E->rbuf_nchains = E->nchains;
     if (!E->rc1) {
         if (!dev_alloc(E, (void **) &E->rc1, n * 4, "rc1") || !dev_alloc(E, (void **) &E->rc2, n * 4, "rc2") ||
             !dev_alloc(E, (void **) &E->rpts, n * npt * 8, "sorted key points") || !dev_alloc(E, (void **) &E->ratom, n * 4, "sorted atoms"))
@@ -1019,14 +1033,21 @@ int engine_render_prepare(Engine *E) {
     cudaMemcpyAsync(E->d_blob_distinct, distinct.data(), (size_t) E->nchains * 4, cudaMemcpyHostToDevice, E->stream);
 
     RConst rc = make_rconst(E);
-    // sort scratch: keys / atom indices in and out, the live counters and cub's workspace
-    uint32_t *d_key = nullptr, *d_key2 = nullptr, *d_val = nullptr, *d_perm = nullptr, *d_live = nullptr;
-    void *d_tmp = nullptr;
+    // sort scratch (kept with the render buffers): keys / atom indices in and out, the live counters, cub's workspace
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_val, d_perm, (int) E->A, 0, 32, E->stream);
-    bool okay = dev_alloc(E, (void **) &d_key, E->A * 4, "sort keys") && dev_alloc(E, (void **) &d_key2, E->A * 4, "sort keys") &&
-                dev_alloc(E, (void **) &d_val, E->A * 4, "sort values") && dev_alloc(E, (void **) &d_perm, E->A * 4, "sort values") &&
-                dev_alloc(E, (void **) &d_live, (size_t) E->h * 4, "live counters") && dev_alloc(E, &d_tmp, tmp_bytes, "sort workspace");
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (int) E->A, 0, 32, E->stream);
+    bool okay = true;
+    if (!E->sort_buf) {
+        okay = dev_alloc(E, (void **) &E->sort_buf, E->A * 16 + (size_t) E->h * 4 + 256, "sort scratch") && dev_alloc(E, &E->sort_tmp, tmp_bytes, "sort workspace");
+        E->sort_tmp_bytes = okay ? tmp_bytes : 0;
+    }
+    if (okay && E->sort_tmp_bytes < tmp_bytes) {
+        dev_free(E->sort_tmp); E->sort_tmp = nullptr;
+        okay = dev_alloc(E, &E->sort_tmp, tmp_bytes, "sort workspace");
+        E->sort_tmp_bytes = okay ? tmp_bytes : 0;
+    }
+    uint32_t *d_key = E->sort_buf, *d_key2 = d_key + E->A, *d_val = d_key2 + E->A, *d_perm = d_val + E->A, *d_live = d_perm + E->A;
+    void *d_tmp = E->sort_tmp;
     if (okay) {
         cudaMemsetAsync(d_live, 0, (size_t) E->h * 4, E->stream);
         for (uint32_t y = 0; y < E->h; ++y) {
@@ -1042,7 +1063,6 @@ int engine_render_prepare(Engine *E) {
         cudaMemcpyAsync(E->r_live.data(), d_live, (size_t) E->h * 4, cudaMemcpyDeviceToHost, E->stream);
     }
     bool bad = !okay || E->fail(cudaStreamSynchronize(E->stream), "render prepare") || E->check("render prepare");
-    dev_free(d_key); dev_free(d_key2); dev_free(d_val); dev_free(d_perm); dev_free(d_live); dev_free(d_tmp);
     if (bad) return okay ? AMX_ERR_CUDA : AMX_ERR_NOMEM;
     E->render_ready = true;
     return AMX_OK;
@@ -1229,6 +1249,22 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     RBatch rb;
     rb.chain_only = -1;
     uint32_t nb = 0;
+    // Host output: frames travel device -> host on a second stream WHILE the next ones are rendered.  ship(upto) sends
+    // the frames [shipped, upto), all of which have been enqueued on the render stream, behind an event.
+    uint32_t shipped = 0;
+    if (!out_is_device && !E->copy_stream) {
+        if (E->fail(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking), "copy stream")) return AMX_ERR_CUDA;
+        for (int k = 0; k < 4; ++k) cudaEventCreateWithFlags(&E->copy_ev[k], cudaEventDisableTiming);
+    }
+    auto ship = [&](uint32_t upto) {
+        if (out_is_device || upto <= shipped) return;
+        cudaEvent_t ev = E->copy_ev[E->copy_ev_next++ & 3];
+        cudaEventRecord(ev, E->stream);
+        cudaStreamWaitEvent(E->copy_stream, ev, 0);
+        cudaMemcpyAsync(out + (size_t) shipped * np, d_dst + (size_t) shipped * np, (size_t) (upto - shipped) * np * 4, cudaMemcpyDeviceToHost, E->copy_stream);
+        shipped = upto;
+    };
+    const uint32_t ship_every = std::max<uint32_t>(4u, NB);          // frames per D2H chunk
     auto flush_batch = [&]() {
         // feather == 0: nb frames share one scatter and one fused gather/composite launch
         if (nb == 0) return;
@@ -1267,7 +1303,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             if (nb > 0 && rb.f[0].y != rf.y) flush_batch();           // a batch stays inside one key-frame interval
             if (E->p.keep_background) launch_background(E, rc, rf, d_bg + (size_t) nb * np);
             rb.f[nb++] = rf;
-            if (nb == NB) flush_batch();
+            if (nb == NB) { flush_batch(); if (i + 1 - shipped >= ship_every) ship(i + 1); }
             continue;
         }
         if (E->p.keep_background) launch_background(E, rc, rf, d_bg);
@@ -1282,12 +1318,10 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         launch_frame_cleanup(E);
     }
     flush_batch();
+    ship(n);
     int rcode = AMX_OK;
     if (!out_is_device) {
-        if (E->fail(cudaMemcpyAsync(out, d_dst, np * n * 4, cudaMemcpyDeviceToHost, E->stream), "render D2H")) rcode = AMX_ERR_CUDA;
-    }
-    if (!out_is_device) {
-        if (E->fail(cudaStreamSynchronize(E->stream), "render")) rcode = AMX_ERR_CUDA;
+        if (E->fail(cudaStreamSynchronize(E->copy_stream), "render D2H") || E->fail(cudaStreamSynchronize(E->stream), "render")) rcode = AMX_ERR_CUDA;
     }
     if (E->check("render")) rcode = AMX_ERR_CUDA;
     if (rcode == AMX_OK && E->nchains > 1 && !out_is_device && E->d_ovf_used) {
@@ -1398,6 +1432,28 @@ int amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_
     cudaSetDevice(ctx->e.device);
     return engine_render_blob(&ctx->e, blob, t, cap, xy_out, rgba_out, n, group);
 }
+int amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out) {
+    if (!ctx || !pixels_out) return AMX_ERR_ARG;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    const size_t np = (size_t) E->width * E->height;
+    if (np == 0) { E->err = "resolution not set"; return AMX_ERR_STATE; }
+    // staging: [np] packed RGBA followed by [np] 8-byte pixel records
+    if (E->d_pix_cap < np) {
+        dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
+        if (!dev_alloc(E, (void **) &E->d_pix, np * 12 + 8, "pixel staging")) return AMX_ERR_NOMEM;
+        E->d_pix_cap = np;
+    }
+    int rcode = engine_render(E, &t, 1, E->d_pix, 1);
+    if (rcode != AMX_OK) return rcode;
+    uint2 *d_rec = (uint2 *) (E->d_pix + np + (np & 1));          // 8-byte aligned
+    k_to_pixels<<<div_up(np, 256), 256, 0, E->stream>>>(E->d_pix, E->width, np, d_rec);
+    E->launches++;
+    if (E->fail(cudaMemcpyAsync(pixels_out, d_rec, np * 8, cudaMemcpyDeviceToHost, E->stream), "pixels D2H") ||
+        E->fail(cudaStreamSynchronize(E->stream), "render pixels") || E->check("render pixels")) return AMX_ERR_CUDA;
+    return AMX_OK;
+}
+
 int amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]) {
     if (!ctx || !stats3) return AMX_ERR_ARG;
     Engine *E = &ctx->e;

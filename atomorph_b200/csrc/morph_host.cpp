@@ -627,20 +627,22 @@ void morph::get_pixels(double t, std::vector<pixel> *image) {
     image->clear();
     size_t w = p->width, h = p->height;
     image->resize(w * h);
-    std::vector<uint32_t> buf(w * h, 0u);
+    static_assert(sizeof(pixel) == 8, "am::pixel must stay 8 bytes (atomorph.cpp:1017-1023)");
     bool ok = false;
     if (w && h && p->ctx && p->device_identifier == p->identifier) {
+        // the device writes finished am::pixel records: one copy straight into the caller's vector
         std::lock_guard<std::mutex> lk(p->dev);
-        ok = p->ck(amx_render(p->ctx, &t, 1, buf.data(), 0), "render");
+        ok = p->ck(amx_render_pixels(p->ctx, t, reinterpret_cast<uint64_t *>(image->data())), "render");
     }
-    if (!ok) std::fill(buf.begin(), buf.end(), 0u);
-    pixel *dst = image->data();
-    for (size_t y = 0; y < h; ++y)
-        for (size_t x = 0; x < w; ++x) {
-            pixel &px = dst[y * w + x];
-            px.x = (uint16_t) x; px.y = (uint16_t) y;
-            px.c = unpackc(buf[y * w + x]);
-        }
+    if (!ok) {
+        pixel *dst = image->data();
+        for (size_t y = 0; y < h; ++y)
+            for (size_t x = 0; x < w; ++x) {
+                pixel &px = dst[y * w + x];
+                px.x = (uint16_t) x; px.y = (uint16_t) y;
+                px.c = unpackc(0u);
+            }
+    }
 }
 
 const blob *morph::get_pixels(size_t blob_index, double time, std::vector<pixel> *to) {   // morph.cpp:452-678

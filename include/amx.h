@@ -133,6 +133,10 @@ int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_
 int  amx_render_prepare(amx_ctx *ctx);
 /* n frames at times t[i] -> out[i*width*height ...] packed RGBA.  out_is_device: out is a device pointer. */
 int  amx_render(amx_ctx *ctx, const double *times, uint32_t n, uint32_t *out, int out_is_device);
+/* one frame as width*height am::pixel records {u16 x, u16 y, u8 r, g, b, a} in row-major order: exactly what
+ * morph::get_pixels(double, std::vector<pixel>*) returns (morph.cpp:1405-1421), built on the device so that the
+ * host side is one copy into the caller's vector */
+int  amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out);
 /* renderer diagnostics, cumulative since the render buffers were (re)built: [0] pixels resolved by the ordered double
  * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
  * went to an overflow list */
