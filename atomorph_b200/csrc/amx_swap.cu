@@ -39,8 +39,8 @@ struct SwapStats { unsigned long long proposals, accepted, gain; };
 // proposals / accepted / gain: warp shuffle, then shared memory, then ONE set of atomics per block
 // (same-address atomics serialise in L2 at about one per clock: per-warp atomics used to dominate a round)
 __device__ __forceinline__ void warp_add_stats(unsigned long long *stats, unsigned prop, unsigned acc, unsigned long long gain) {
-    __shared__ unsigned s_prop[8], s_acc[8];
-    __shared__ unsigned long long s_gain[8];
+    __shared__ unsigned s_prop[32], s_acc[32];
+    __shared__ unsigned long long s_gain[32];
     for (int o = 16; o > 0; o >>= 1) {
         prop += __shfl_down_sync(0xffffffffu, prop, o);
         acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -130,7 +130,7 @@ k_swap_multi(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
 }
 
 // ---- shared-memory tiled rounds -----------------------------------------------------------------------------
-#define TILE_BITS 11                       // 2048 atoms per tile: 32 KB (h = 2) / 48 KB (h >= 3) of shared memory
+#define TILE_BITS 10                       // 1024 atoms per tile: 16 KB (h = 2) / 24 KB (h >= 3) of shared memory
 #define TILE_ATOMS (1u << TILE_BITS)
 #define TILE_THREADS 256
 #define TILE_MAX_ROUNDS 64                 // rounds per epoch (one load / store of the tile)
@@ -166,9 +166,10 @@ __device__ __forceinline__ pword kp_pack(uint2 p) {
     return pw_make(x >> 8, p.y >> 8, x & 255u, p.y & 255u, f);
 }
 __device__ __forceinline__ unsigned long long kp_dist(uint2 a, uint2 b) {
-    long long dx = (long long) (int) (a.x & 0xffffffu) - (long long) (int) (b.x & 0xffffffu);
-    long long dy = (long long) (int) a.y - (long long) (int) b.y;
-    return (unsigned long long) (dx * dx) + (unsigned long long) (dy * dy);
+    // 24-bit coordinates: the differences fit 32 bits, each square is ONE 32 x 32 -> 64 bit multiply-add
+    const int dx = (int) (a.x & 0xffffffu) - (int) (b.x & 0xffffffu);
+    const int dy = (int) a.y - (int) b.y;
+    return (unsigned long long) ((long long) dx * (long long) dx) + (unsigned long long) ((long long) dy * (long long) dy);
 }
 
 // One CTA = one tile.  `rounds` rounds of TILE_ATOMS / 2 disjoint proposals each, all inside shared memory.

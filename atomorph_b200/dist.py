@@ -96,7 +96,7 @@ def scatter_gathered(column, gathered, width, sel_mask, world):
 
 
 # ------------------------------------------------------------------ tile-range ownership (long chains, amx_swap.cu k_swap_tiled)
-TILE_BITS = 11
+TILE_BITS = 10
 _M64 = (1 << 64) - 1
 
 
