@@ -139,7 +139,7 @@ struct Engine {
     uint32_t *ab_cnt = nullptr;            // two buffers (ping-pong), each [RBATCH][canvas]
     uint32_t  ab_parity = 0, ab_dirty[2] = {0, 0};
     void     *d_render_stats = nullptr;
-    uint4    *ab_pair = nullptr, *ab_third = nullptr;
+    uint4    *ab_pair = nullptr, *ab_pair2 = nullptr;
     uint32_t *ab_cnt_base = nullptr;       // allocations behind ab_cnt / ab_pair (guard in front)
     uint4    *ab_pair_base = nullptr;
     uint32_t *ab_ovf_head = nullptr;

@@ -47,7 +47,7 @@
 namespace amx {
 
 #define MAXK 32
-#define K_SLOTS 3          // direct A-buffer slots per pixel
+#define K_SLOTS 4          // direct A-buffer slots per pixel (two 32-byte pairs)
 #define RBATCH 2           // frames per launch (all of one key-frame interval)
 
 struct RConst {
@@ -78,17 +78,17 @@ struct RBatch {
 };
 
 // Per-pixel A-buffer of one batch slot.  cnt[home] counts the atoms whose top-left splat target is `home`; the first
-// two of them sit side by side in pair[home] (one 32-byte sector per pixel), the third in third[home], the others
+// two of them sit side by side in pair[home] (one 32-byte sector per pixel), the next two in pair2[home], the others
 // hang off ovf_head[home] as a list through ovf_rec[atom].z.  Only cnt is ever cleared: a list is walked for exactly
 // cnt - K_SLOTS nodes.
 // Record: x = colour, y = x_fract | y_fract << 8 | (chain & 0xffff) << 16, z = atom (direct) / next (overflow).
 struct ABuf {
     uint32_t *cnt;
     uint4    *pair;               // [RBATCH][canvas][2]
-    uint4    *third;              // [RBATCH][canvas]
+    uint4    *pair2;              // [RBATCH][canvas][2], sparsely used
     uint32_t *ovf_head;
     uint4    *ovf_rec;
-    size_t    canvas;             // stride between batch slots (cnt, pair/2, third, ovf_head)
+    size_t    canvas;             // stride between batch slots (cnt, pair/2, pair2/2, ovf_head)
     size_t    A;                  // stride between batch slots (ovf_rec)
 };
 
@@ -278,7 +278,7 @@ __device__ __forceinline__ void store_pending(const Pending &p, const ABuf &ab, 
         const size_t hp = (size_t) s * ab.canvas + p.home[s];
         const uint4 rec = make_uint4(p.col[s], p.meta[s], p.who, 0u);
         if (p.k[s] < 2u) ab.pair[2 * hp + p.k[s]] = rec;
-        else if (p.k[s] == 2u) ab.third[hp] = rec;
+        else if (p.k[s] < 4u) ab.pair2[2 * hp + (p.k[s] - 2u)] = rec;
         else {
             // overflow: list through ovf_rec, indexed by the ORIGINAL atom (unique per frame)
             uint32_t next = atomicExch(&ab.ovf_head[hp], p.who);
@@ -366,7 +366,8 @@ __device__ __forceinline__ void visit_contributions(const ABuf &ab, const RConst
         };
         if (cn > 0) { uint4 r = ab.pair[2 * hp]; emit(r.z, r); }
         if (cn > 1) { uint4 r = ab.pair[2 * hp + 1]; emit(r.z, r); }
-        if (cn > 2) { uint4 r = ab.third[hp]; emit(r.z, r); }
+        if (cn > 2) { uint4 r = ab.pair2[2 * hp]; emit(r.z, r); }
+        if (cn > 3) { uint4 r = ab.pair2[2 * hp + 1]; emit(r.z, r); }
         if (cn > K_SLOTS) {
             uint32_t i = ab.ovf_head[hp];
             for (uint32_t j = K_SLOTS; j < cn; ++j) { uint4 r = ab.ovf_rec[i]; emit(i, r); i = r.z; }
@@ -516,7 +517,7 @@ __device__ __forceinline__ uint32_t rdiv_small(uint32_t num, uint32_t den, float
 // the A-buffer of batch slot `slot`
 __device__ __forceinline__ ABuf ab_at(ABuf ab, uint32_t slot) {
     size_t o = (size_t) slot * ab.canvas;
-    ab.cnt += o; ab.pair += 2 * o; ab.third += o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
+    ab.cnt += o; ab.pair += 2 * o; ab.pair2 += 2 * o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
     return ab;
 }
 
@@ -614,14 +615,19 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
     bool generic = csum > MAXK;
     const uint32_t cmax = max(max(c0, c1), max(c2, c3));
     if (cmax > 2u) {
-        // third records: loaded only by the lanes that have one, folded in by every lane with weight 0 / 1
-        uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
-        if (c0 > 2u) t0 = ab.third[h0];
-        if (c1 > 2u) t1 = ab.third[h1];
-        if (c2 > 2u) t2 = ab.third[h2];
-        if (c3 > 2u) t3 = ab.third[h3];
+        // third and fourth records: loaded only by the lanes that have them, folded in by every lane with weight 0 / 1
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 t0 = z, t1 = z, t2 = z, t3 = z, u0 = z, u1 = z, u2 = z, u3 = z;
+        if (c0 > 2u) { t0 = ab.pair2[2 * (size_t) h0]; u0 = ab.pair2[2 * (size_t) h0 + 1]; }
+        if (c1 > 2u) { t1 = ab.pair2[2 * (size_t) h1]; u1 = ab.pair2[2 * (size_t) h1 + 1]; }
+        if (c2 > 2u) { t2 = ab.pair2[2 * (size_t) h2]; u2 = ab.pair2[2 * (size_t) h2 + 1]; }
+        if (c3 > 2u) { t3 = ab.pair2[2 * (size_t) h3]; u3 = ab.pair2[2 * (size_t) h3 + 1]; }
         fold<SINGLE, COUNTED, 0, 0>(P, t0, c0 > 2u); fold<SINGLE, COUNTED, 1, 0>(P, t1, c1 > 2u);
         fold<SINGLE, COUNTED, 0, 1>(P, t2, c2 > 2u); fold<SINGLE, COUNTED, 1, 1>(P, t3, c3 > 2u);
+        if (max(max(c0, c1), max(c2, c3)) > 3u) {
+            fold<SINGLE, COUNTED, 0, 0>(P, u0, c0 > 3u); fold<SINGLE, COUNTED, 1, 0>(P, u1, c1 > 3u);
+            fold<SINGLE, COUNTED, 0, 1>(P, u2, c2 > 3u); fold<SINGLE, COUNTED, 1, 1>(P, u3, c3 > 3u);
+        }
         if (!generic && cmax > K_SLOTS) {
             // overflow lists: rare
             const uint32_t hh[4] = {h0, h1, h2, h3}, cc[4] = {c0, c1, c2, c3};
@@ -915,10 +921,10 @@ void engine_render_free(Engine *E) {
     dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
     dev_free(E->d_ovf_used); dev_free(E->blob_px);
     dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
-    dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_third); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
+    dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
-    E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_third = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
+    E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
 
@@ -985,7 +991,7 @@ int engine_render_prepare(Engine *E) {
         if (!dev_alloc(E, (void **) &E->ab_cnt_base, (2 * RBATCH * cv + guard) * 4, "abuf counters") ||
             !dev_alloc(E, (void **) &E->d_render_stats, sizeof(RenderStats), "render stats") ||
             !dev_alloc(E, (void **) &E->ab_pair_base, ((size_t) 2 * RBATCH * cv + 2 * guard) * 16, "abuf record pairs") ||
-            !dev_alloc(E, (void **) &E->ab_third, (size_t) RBATCH * cv * 16, "abuf third records") ||
+            !dev_alloc(E, (void **) &E->ab_pair2, (size_t) 2 * RBATCH * cv * 16, "abuf second record pairs") ||
             !dev_alloc(E, (void **) &E->ab_ovf_head, RBATCH * cv * 4, "abuf overflow heads") ||
             !dev_alloc(E, (void **) &E->ab_ovf_rec, RBATCH * E->A * 16, "abuf overflow records"))
             return AMX_ERR_NOMEM;
@@ -1156,7 +1162,7 @@ static KTime g_ktime;
 static ABuf make_abuf(Engine *E) {
     ABuf ab;
     size_t cv = E->canvas();
-    ab.cnt = E->ab_cnt + (size_t) E->ab_parity * RBATCH * cv; ab.pair = E->ab_pair; ab.third = E->ab_third; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
+    ab.cnt = E->ab_cnt + (size_t) E->ab_parity * RBATCH * cv; ab.pair = E->ab_pair; ab.pair2 = E->ab_pair2; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
     ab.canvas = cv; ab.A = E->A;
     return ab;
 }
