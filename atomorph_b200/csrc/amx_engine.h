@@ -191,6 +191,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
 int engine_render_blob(Engine *E, uint32_t blob, double t, uint64_t cap, uint16_t *xy, uint32_t *rgba, int64_t *n, uint64_t *group);
 int engine_background(Engine *E, double t, uint32_t *out, int out_is_device);               // amx_render.cu
 void engine_render_free(Engine *E);
+int engine_render_fluid(Engine *E, double time, uint32_t f, double tl, const uint32_t *d_bg, uint32_t *d_dst);   // amx_fluiddraw.cu
 void engine_fluid_free(Engine *E);
 
 } // namespace amx

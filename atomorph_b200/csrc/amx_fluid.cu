@@ -17,20 +17,9 @@
  * Wall clamping uses the counter-based RNG where the reference calls rand() (fluidmodel.cpp:553-566).
  */
 #include "amx_engine.h"
+#include "amx_fluid.h"
 
 namespace amx {
-
-enum { PF_X, PF_Y, PF_U, PF_V, PF_GX, PF_GY, PF_FREE, PF_RI, PF_GI, PF_BI, PF_AI, PF_R, PF_G, PF_B, PF_A, PF_STRENGTH, PF_COUNT };
-enum { NF_M, NF_D, NF_GX, NF_GY, NF_U, NF_V, NF_AX, NF_AY, NF_R, NF_G, NF_B, NF_A, NF_W, NF_COUNT };
-
-struct Fluid {
-    uint32_t gx = 0, gy = 0, n = 0;
-    double *pf = nullptr;        // [PF_COUNT][n]
-    uint8_t *active = nullptr, *mature = nullptr, *owner = nullptr;
-    double *aux = nullptr;       // [3][n] frame_key, source_pos, destination_pos (driver bookkeeping)
-    double *nf = nullptr;        // [NF_COUNT][gx*gy]
-    uint64_t step_counter = 0;
-};
 
 struct PW { int cx, cy; double px[3], py[3], gx[3], gy[3]; };
 
@@ -254,12 +243,13 @@ k_fluid_g2p(double *__restrict__ pf, const uint8_t *__restrict__ active, const u
 void engine_fluid_free(Engine *E) {
     if (!E->fluid) return;
     Fluid *F = E->fluid;
+    fluid_draw_free(F);
     dev_free(F->pf); dev_free(F->active); dev_free(F->mature); dev_free(F->owner); dev_free(F->aux); dev_free(F->nf);
     delete F;
     E->fluid = nullptr;
 }
 
-static int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
+int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
     Fluid *F = E->fluid;
     size_t ng = (size_t) F->gx * F->gy;
     uint32_t n = F->n;
@@ -277,15 +267,7 @@ static int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
     return E->check("fluid step") ? AMX_ERR_CUDA : AMX_OK;
 }
 
-} // namespace amx
-
-using namespace amx;
-extern "C" {
-
-int amx_fluid_create(amx_ctx *ctx, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle_count) {
-    if (!ctx || gsize_x < 8 || gsize_y < 8) return AMX_ERR_ARG;
-    Engine *E = &ctx->e;
-    cudaSetDevice(E->device);
+int fluid_alloc(Engine *E, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle_count) {
     engine_fluid_free(E);
     Fluid *F = new Fluid();
     F->gx = gsize_x; F->gy = gsize_y; F->n = particle_count;
@@ -304,6 +286,17 @@ int amx_fluid_create(amx_ctx *ctx, uint32_t gsize_x, uint32_t gsize_y, uint32_t 
     cudaMemsetAsync(F->aux, 0, n * 3 * 8, E->stream);
     cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream);
     return E->fail(cudaStreamSynchronize(E->stream), "fluid create") ? AMX_ERR_CUDA : AMX_OK;
+}
+
+} // namespace amx
+
+using namespace amx;
+extern "C" {
+
+int amx_fluid_create(amx_ctx *ctx, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle_count) {
+    if (!ctx || gsize_x < 8 || gsize_y < 8) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    return fluid_alloc(&ctx->e, gsize_x, gsize_y, particle_count);
 }
 
 // record field -> SoA slot

@@ -1305,6 +1305,14 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             else cudaMemsetAsync(dst, 0, np * 4, E->stream);
             continue;
         }
+        if (E->p.fluid > 0) {
+            // morph.cpp:1417-1418: with fluid the frame is drawn from the particles, one (stateful) frame at a time
+            flush_batch();
+            if (E->p.keep_background) launch_background(E, rc, rf, d_bg);
+            int frc = engine_render_fluid(E, time, f, tl, d_bg, dst);
+            if (frc != AMX_OK) return frc;
+            continue;
+        }
         if (rc.feather == 0) {
             if (nb > 0 && rb.f[0].y != rf.y) flush_batch();           // a batch stays inside one key-frame interval
             if (E->p.keep_background) launch_background(E, rc, rf, d_bg + (size_t) nb * np);

@@ -317,8 +317,9 @@ class Engine:
         rec = np.ascontiguousarray(rec, dtype=np.float64)
         self._ck(self.L.amx_fluid_set_particles(self.h, rec.shape[0], _p(rec)), "fluid_set_particles")
 
-    def fluid_get_particles(self):
-        rec = np.zeros((self._fluid[2], FP_STRIDE))
+    def fluid_get_particles(self, n=None):
+        """Particle records; after a fluid frame was rendered the model belongs to the engine and n = total atoms."""
+        rec = np.zeros((self._fluid[2] if n is None else int(n), FP_STRIDE))
         self._ck(self.L.amx_fluid_get_particles(self.h, rec.shape[0], _p(rec)), "fluid_get_particles")
         return rec
 
