@@ -124,3 +124,41 @@ def test_facade_setters_restart_and_errors(reflib):
     m.synchronize()
     m.iterate(1); m.wait(); m.suspend(); m.synchronize()
     assert m.get_state() == eng.STATE_DONE
+
+
+def test_facade_fluid_frames(reflib):
+    """set_fluid(n > 0): get_pixels(t) comes from the particle path (morph.cpp:1417-1418).  The first frame of an interval
+    (one particle per source, on its attractor) is the reference's image fed with OUR tables."""
+    images = scenes.ellipses(40, 2, seed=64)
+    m = Morph()
+    m.set_seed(1)
+    m.set_motion(eng.LINEAR)
+    m.set_fading(eng.LINEAR)
+    m.set_fluid(3)
+    m.set_threads(0)
+    m.set_cycle_length(200)
+    for k, im in enumerate(images):
+        m.add_image(k, im)
+    m.set_resolution(40, 40)
+    _drive(m, eng.STATE_ATOM_MORPHING)
+    m.iterate(20); m.wait(); m.suspend(); m.synchronize()
+    from atomorph_b200.engine import Engine
+    e = Engine.__new__(Engine)
+    e.L = m.L; e.h = m.device_context()
+    chains = Engine.chains(e)
+    e.h = None
+    ref = reflib.RefMorph(seed=1, motion=eng.LINEAR, fading=eng.LINEAR, fluid=3)
+    for k, im in enumerate(images):
+        ref.add_image(k, im)
+    ref.set_resolution(40, 40)
+    for k in range(2):
+        ref.import_blobs(k, [m.get_blob(k, 0)])
+    for c in chains:
+        ref.import_chain(c["key"], c["words"], c["max_surface"])
+    ref.finish_import()
+    ref.sync()
+    ref.fluid_sanitize()
+    n, mx = diff_stats(ref.render(0.0), m.get_pixels(0.0))
+    assert mx <= 2 and n <= 0.02 * 40 * 40, (n, mx)
+    later = m.get_pixels(0.25)
+    assert ((later >> 24) != 0).sum() > 0
