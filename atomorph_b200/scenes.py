@@ -100,3 +100,22 @@ def random_cloud(n=48, frames=3, fill=0.6, seed=3, margin=6):
         img[~m] = 0
         out.append(img)
     return out
+
+
+def rotating_shapes(n=4096, frames=8, seed=21, coverage=0.85):
+    """BASELINE.json config 5: `frames` cyclic key frames of one shape (a rounded super-ellipse) that rotates and
+    scales per key frame and covers >= 80 % of the n x n canvas; textured RGBA."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    c = (n - 1) / 2.0
+    out = []
+    for k in range(frames):
+        ang = np.pi * k / frames
+        s = 1.0 - 0.06 * (1 + np.cos(2 * np.pi * k / frames)) / 2.0
+        xr = ((xx - c) * np.cos(ang) + (yy - c) * np.sin(ang)) / (c * s)
+        yr = (-(xx - c) * np.sin(ang) + (yy - c) * np.cos(ang)) / (c * s)
+        inside = (np.abs(xr) ** 6 + np.abs(yr) ** 6) <= 1.0          # rounded square: ~ 93 % of its bounding box
+        img = _texture(n, n, rng, 0.5 * k)
+        img[~inside] = 0
+        out.append(img)
+    return out
