@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SWAP_ROUNDS = 64          # rounds per step; one round = W/2 proposals on a power-of-two chain
+SWAP_ROUNDS = 256         # rounds per step = per exchange on N > 1 GPUs (4 tiled launches of 64 rounds on the same tiles)
 HBM_FALLBACK_GBS = 6650.0
 
 
