@@ -89,6 +89,7 @@ int amx_create(amx_ctx **out, int device) {
     c->e.own_stream = true;
     if (const char *nb = getenv("AMX_RENDER_BATCH")) c->e.render_batch = (uint32_t) std::max(1, atoi(nb));   // tuning knob (frames per launch pair)
     c->e.swap_global_only = getenv("AMX_SWAP_GLOBAL") != nullptr;
+    if (const char *tl = getenv("AMX_RENDER_TILED")) c->e.tiled_enabled = atoi(tl) != 0;                      // 0: general A-buffer render path only
     cudaEventCreate(&c->e.ev0);
     cudaEventCreate(&c->e.ev1);
     if (!dev_alloc(&c->e, (void **) &c->e.d_swapstats, 3 * sizeof(uint64_t), "swapstats")) { delete c; return AMX_ERR_NOMEM; }

@@ -145,6 +145,16 @@ struct Engine {
     uint32_t *ab_ovf_head = nullptr;
     uint4    *ab_ovf_rec = nullptr;
     uint32_t  render_batch = 2;            // frames per scatter/gather launch pair
+    // tiled path (amx_render.cu: Bins): record bins per (frame slot of a batch, 32x32-pixel tile)
+    uint2    *tb_rec = nullptr;
+    uint32_t *tb_atom = nullptr, *tb_chain = nullptr;
+    uint32_t *tb_cnt = nullptr;            // two counter buffers (ping-pong), each [RBATCH][tiles][4]
+    uint32_t *tb_flag = nullptr;           // raised by the kernels when a bin / tile overflows
+    uint32_t  tb_tiles_x = 0, tb_tiles_y = 0, tb_parity = 0, tb_dirty[2] = {0, 0};
+    bool      tb_has_chain = false;
+    bool      tiled_enabled = true;        // AMX_RENDER_TILED=0: general A-buffer path only (for comparisons)
+    bool      tiled_blocked = false;       // a bin overflowed with the current table: general path until the next refresh
+    uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_stats)
     uint32_t *d_bg = nullptr;              // background images of one batch (keep_background)
     size_t    d_bg_cap = 0;
     // per-(pixel, blob) entries for the feather / per-blob paths (canvas sized + overflow hash)

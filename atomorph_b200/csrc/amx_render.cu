@@ -180,7 +180,7 @@ enum : int { M_NONE = 0, M_LINEAR = 1, M_SPLINE = 2 };
 // position + colour of one atom in one frame; false when the atom is clipped away
 template <int MOTION, bool PERLIN, bool H2>
 __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, const RFrame &rf, const AtomIn &in, size_t i, uint32_t atom,
-                                            uint32_t *home, uint32_t *col, uint32_t *fract) {
+                                            uint32_t *hx, uint32_t *hy, uint32_t *col, uint32_t *fract) {
     const size_t A = rc.A;
     const double inv256 = 0.00390625;
     // trajectory (morph.cpp:523-531)
@@ -243,7 +243,7 @@ __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, con
     if (PERLIN) str = ease_strength(in.lag, in.slope, rf.w, DevCos());
     if (str >= 0.0 && str <= 1.0) *col = lerp_color_d(in.c1, in.c2, str);
     else *col = lerp_color(in.rc1, in.rc2, str);
-    *home = y * rc.cw + x;
+    *hx = x; *hy = y;
     *fract = xf | (yf << 8);
     return true;
 }
@@ -327,8 +327,9 @@ k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, R
 #pragma unroll
             for (uint32_t s = 0; s < RBATCH; ++s) {
                 if (s >= nb) continue;
-                uint32_t fr;
-                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &cur.home[s], &cur.col[s], &fr)) {
+                uint32_t fr, hx, hy;
+                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &cur.col[s], &fr)) {
+                    cur.home[s] = hy * rc.cw + hx;
                     cur.meta[s] = fr | meta_chain;
                     cur.okmask |= 1u << s;
                 }
@@ -449,15 +450,15 @@ struct Over {
     }
 };
 
-// Emits the resolved blob pixels of one position in ascending blob order: emit(chain, px)
-template <bool SINGLE, typename E>
-__device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &rc,
-                                                 const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc,
-                                                 uint32_t px, uint32_t py, E emit) {
+// Emits the resolved blob pixels of one position in ascending blob order: emit(chain, px).  visit(f) calls
+// f(atom, colour, n, chain16) for every contribution to the position (it may be invoked several times).
+template <bool SINGLE, typename V, typename E>
+__device__ __forceinline__ void resolve_contributions(V visit, const RConst &rc,
+                                                      const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc, E emit) {
     unsigned long long key[MAXK];
     uint32_t cc[MAXK], cn[MAXK];
     int count = 0;
-    visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
+    visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
         if (count < MAXK) {
             unsigned long long k = a;
             if (!SINGLE) k |= (unsigned long long) (uint32_t) boc[chain_of[a]] << 32;
@@ -487,20 +488,27 @@ __device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &r
         long long best = LLONG_MAX;
         uint32_t bchain = 0;
         if (SINGLE) { if (prev < 0) best = 0; }
-        else visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t, uint32_t, uint32_t) {
+        else visit([&](uint32_t a, uint32_t, uint32_t, uint32_t) {
             uint32_t c = chain_of[a];
             long long k = boc[c];
             if (k > prev && k < best) { best = k; bchain = c; }
         });
         if (best == LLONG_MAX) break;
         unsigned long long R = 0, G = 0, B = 0, Av = 0, N = 0, cnt = 0;
-        visit_contributions(ab, rc, px, py, [&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
+        visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
             if (!SINGLE && chain_of[a] != bchain) return;
             R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
         });
         emit(bchain, resolve_int(R, G, B, Av, N, cnt, rc.density));
         prev = best;
     }
+}
+
+template <bool SINGLE, typename E>
+__device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &rc,
+                                                 const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc,
+                                                 uint32_t px, uint32_t py, E emit) {
+    resolve_contributions<SINGLE>([&](auto f) { visit_contributions(ab, rc, px, py, f); }, rc, chain_of, boc, emit);
 }
 
 // exact round(num/den) (half up) for 2*num + den < 2^32, quotient <= 255: float estimate + integer fix-up.
@@ -682,6 +690,387 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
     // generic path: several blobs at the position, an exact tie, or a very long list
     if (stats) atomicAdd(&stats->generic, 1ull);
     out[i] = resolve_generic<SINGLE>(&abuf, slot, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct, y_frame, px, py, bgc);
+}
+
+// ---------------------------------------------------------------------------------------- tiled path (feather == 0)
+// The frame is cut into 32x32-pixel tiles.  Instead of claiming a slot of a per-pixel A-buffer in global memory
+// (one atomic with return and one scattered 16-byte store per atom and frame), an atom's sample is appended to the BIN
+// of the tile its home pixel lies in: the 32 atoms of a warp are neighbours (they are sorted by the tile of their
+// mid-interval position), so a warp usually needs ONE atomicAdd per frame (__match_any_sync groups the lanes by bin)
+// and its records leave as coalesced 256-byte runs.  One CTA per tile then pulls the tile's records into shared
+// memory, orders them by home pixel there and resolves its 1024 pixels -- the per-pixel lists never exist in global
+// memory.  A batch's bins (12 B per atom and frame) stay in L2 between the two kernels.
+//
+// A home in the last column / row of its tile also reaches pixels of the next tile(s).  Records are therefore
+// appended to one of FOUR bins of their tile -- class 0: interior, 1: last column, 2: last row, 3: corner -- and a tile
+// reads nine bins: its own four, classes 1 and 3 of its western neighbour, 2 and 3 of the northern one and 3 of the
+// north-western one.  Every record is written once.
+//
+// Ordering by home inside the tile without atomics (ATOMS is 2 cycles per lane): every home has T_NLEV slots; in round
+// r all still unplaced records STORE their index into slot r of their home, after a barrier the one whose index
+// survived owns the slot and the others go on to round r + 1.  Records left after T_NLEV rounds go to a short overflow
+// list.  Pixels then fold the slots of the homes that reach them into exact integer sums exactly like
+// k_gather_pixel; ties, several blobs at a pixel, homes with overflow records take the ordered double replay
+// (resolve_contributions).
+//
+// Capacity: a tile takes T_SREC records per frame (3.5 atoms per pixel).  A bin or tile that would need more raises
+// bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
+// are identical, both being exact).
+#define T_TILE   32u
+#define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
+#define T_SWW    1090u                  // 33 * 33 homes, padded to a whole number of 32-bit words
+#define T_NLEV   6u                     // direct record slots per home
+#define T_SREC   4096u                  // records of one tile and frame (own four bins + five neighbour bins)
+#define T_OVF    512u                   // records beyond the T_NLEV-th of their home
+#define T_EMPTY  0xffffu
+#define T_CAP0   3584u                  // bin capacities per class; T_CAP0 + 4 * T_CAP1 + 4 * T_CAP3 == T_SREC
+#define T_CAP1   96u
+#define T_CAP3   32u
+#define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
+#define T_KEY_NONE 0xffffffffu
+static_assert(T_CAP0 + 4u * T_CAP1 + 4u * T_CAP3 == T_SREC, "bin capacities must add up to the tile capacity");
+
+struct Bins {
+    uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | lx << 16 | ly << 22}
+    uint32_t *atom;       // same layout: original atom index (the reference's summation order)
+    uint32_t *chain;      // same layout: chain of the atom; nullptr for a single chain
+    uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
+    uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
+    uint32_t *flag;       // != 0: something overflowed, the frames must be rendered again by the general path
+    uint32_t  tiles_x, tiles_y;
+};
+__device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls == 0u ? 0u : cls == 1u ? T_CAP0 : cls == 2u ? T_CAP0 + T_CAP1 : T_CAP0 + 2u * T_CAP1; }
+__device__ __forceinline__ uint32_t bin_cap(uint32_t cls) { return cls == 0u ? T_CAP0 : cls == 3u ? T_CAP3 : T_CAP1; }
+
+// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile
+template <int MOTION, bool PERLIN, bool H2>
+__global__ void __launch_bounds__(256, 3)
+k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t A = rc.A;
+    const double inv256 = 0.00390625;
+    const uint32_t y = rb.f[0].y;
+    const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    RawIn next = RawIn();
+    if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
+    // warp-uniform trip count: claiming bin slots is a warp collective
+    for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
+        const bool valid = i < n_live;
+        const RawIn raw = next;
+        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
+
+        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) key[s] = T_KEY_NONE;
+        bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
+        if (use) {
+            AtomIn in;
+            in.pt1 = raw.pt1; in.pt2 = raw.pt2;
+            in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
+            in.x2 = u2d((uint32_t) pw_x256(raw.pt2)) * inv256; in.y2 = u2d((uint32_t) pw_y256(raw.pt2)) * inv256;
+            in.rc1 = raw.c1; in.rc2 = raw.c2;
+            in.c1 = col_d(raw.c1); in.c2 = col_d(raw.c2);
+            in.lag = raw.lag; in.slope = raw.slope;
+#pragma unroll
+            for (uint32_t s = 0; s < RBATCH; ++s) {
+                if (s >= nb) continue;
+                uint32_t fr, hx, hy;
+                // a home at x >= width or y >= height reaches no pixel of the image
+                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr) && hx < rc.width && hy < rc.height) {
+                    const uint32_t lx = hx & 31u, ly = hy & 31u;
+                    const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
+                    key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
+                    meta[s] = fr | (lx << 16) | (ly << 22);
+                }
+            }
+        }
+        // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots
+        uint32_t base[RBATCH], who[RBATCH];
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            base[s] = 0u; who[s] = 0u;
+            if (s >= nb) continue;
+            const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
+            const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
+            who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
+            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
+        }
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            if (s >= nb) continue;
+            const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));
+            if (key[s] == T_KEY_NONE) continue;
+            const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
+            if (pos >= bin_cap(cls)) continue;                    // dropped: k_tile sees the counter beyond the capacity and raises the flag
+            const size_t o = ((size_t) s * ntiles + (key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
+            bn.rec[o] = make_uint2(col[s], meta[s]);
+            bn.atom[o] = raw.atom;
+            if (bn.chain) bn.chain[o] = raw.chain;
+        }
+    }
+}
+
+struct TPart { uint32_t R, G, B, A, N, cnt, chain, vis; };
+
+// what the out-of-line replay needs to find the records of a pixel again (lives in shared memory)
+struct TileCtx {
+    uint32_t segstart[10];    // prefix sums of the nine segment lengths: tile-local record index -> segment
+    uint32_t segfirst[9];     // global index of a segment's first record
+    uint32_t novf;
+    uint32_t pad[4];
+};
+#define T_SMEM_REC   0u
+#define T_SMEM_SLOT  (T_SREC * 8u)
+#define T_SMEM_OVF   (T_SMEM_SLOT + T_NLEV * T_SWW * 2u)
+#define T_SMEM_CTX   (T_SMEM_OVF + T_OVF * 2u)
+#define T_SMEM_CHAIN (T_SMEM_CTX + (uint32_t) sizeof(TileCtx))
+#define T_SMEM_BYTES(SINGLE) (T_SMEM_CHAIN + ((SINGLE) ? 0u : T_SREC * 2u))
+
+__device__ __forceinline__ uint32_t t_home(uint32_t meta) { return ((meta >> 22) & 63u) * T_SW + ((meta >> 16) & 63u); }
+
+// Fold the records of home h (shared-memory coordinates) into the pixel it reaches with dy = 0 (Pa) and the one with
+// dy = 1 (Pb); DX selects the x weight.  Returns true when every slot of the home is taken (there may be overflow
+// records).  Slots 0 and 1 are folded branch-free by the whole warp, the others behind a vote.
+template <bool SINGLE, bool COUNTED, int DX, bool HAS_A, bool HAS_B>
+__device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_slot, const uint16_t *__restrict__ s_chain,
+                                          uint32_t h, TPart &Pa, TPart &Pb) {
+    bool has = true;
+#pragma unroll
+    for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
+        const uint32_t idx = s_slot[lev * T_SWW + h];
+        has = has && idx != T_EMPTY;
+        if (lev >= 2u && !__any_sync(0xffffffffu, has)) break;
+        const uint32_t j = has ? idx : 0u;
+        const uint2 r = s_rec[j];
+        const uint32_t fx = DX ? r.y : r.y ^ 0xffu;                           // DX ? x_fract : 255 - x_fract
+        const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
+        const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
+        const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
+        uint32_t tag = 0u;
+        if (!SINGLE) tag = s_chain[j];
+        if (HAS_A) {
+            const uint32_t n = wx * (255u - yf);
+            Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n; Pa.vis += has ? 1u : 0u;
+            if (COUNTED) Pa.cnt += (n != 0u);
+            if (!SINGLE) { if (n) Pa.chain = merge_chain(Pa.chain, tag); }
+        }
+        if (HAS_B) {
+            const uint32_t n = wx * yf;
+            Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n; Pb.vis += has ? 1u : 0u;
+            if (COUNTED) Pb.cnt += (n != 0u);
+            if (!SINGLE) { if (n) Pb.chain = merge_chain(Pb.chain, tag); }
+        }
+    }
+    return has;
+}
+
+// the ordered double replay of one pixel of a tile (local pixel lx, ly): ties, several blobs, overflowing homes
+template <bool SINGLE>
+__device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem, const Bins *bnp, const RConst *rcp, const uint32_t *__restrict__ chain_of,
+                                                      const int32_t *__restrict__ boc, const uint32_t *__restrict__ blob_avg,
+                                                      const uint32_t *__restrict__ blob_distinct, uint32_t y_frame, uint32_t lx, uint32_t ly, uint32_t bgc) {
+    const uint2 *s_rec = (const uint2 *) (smem + T_SMEM_REC);
+    const uint16_t *s_slot = (const uint16_t *) (smem + T_SMEM_SLOT);
+    const uint16_t *s_ovf = (const uint16_t *) (smem + T_SMEM_OVF);
+    const TileCtx *cx = (const TileCtx *) (smem + T_SMEM_CTX);
+    const uint32_t *g_atom = bnp->atom;
+    const RConst rc = *rcp;
+    auto visit = [&](auto f) {
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t dx = k & 1u, dy = k >> 1;
+            const uint32_t h = (ly + 1u - dy) * T_SW + (lx + 1u - dx);
+            auto emit = [&](uint32_t j) {
+                const uint2 r = s_rec[j];
+                const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
+                const uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
+                if (!n) return;
+                uint32_t s = 0;
+                while (s < 8u && j >= cx->segstart[s + 1u]) ++s;
+                f(g_atom[(size_t) cx->segfirst[s] + (j - cx->segstart[s])], r.x, n, 0u);
+            };
+            uint32_t lev = 0;
+            for (; lev < T_NLEV; ++lev) {
+                const uint32_t idx = s_slot[lev * T_SWW + h];
+                if (idx == T_EMPTY) break;
+                emit(idx);
+            }
+            if (lev == T_NLEV) {
+                const uint32_t nov = min(cx->novf, T_OVF);
+                for (uint32_t q = 0; q < nov; ++q) { const uint32_t j = s_ovf[q]; if (t_home(s_rec[j].y) == h) emit(j); }
+            }
+        }
+    };
+    Over ov;
+    resolve_contributions<SINGLE>(visit, rc, chain_of, boc, [&](uint32_t ch, uint32_t p) {
+        ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
+    });
+    return ov.finish(bgc, rc.keep_background != 0);
+}
+
+// pass 2: one CTA per (tile, frame of the batch); thread = pixel column lx of a band of four rows
+template <bool SINGLE, bool COUNTED>
+__global__ void __launch_bounds__(256)
+k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+       const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+       const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+       const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint2 *s_rec = (uint2 *) (smem + T_SMEM_REC);
+    uint16_t *s_slot = (uint16_t *) (smem + T_SMEM_SLOT);
+    uint16_t *s_ovf = (uint16_t *) (smem + T_SMEM_OVF);
+    TileCtx *cx = (TileCtx *) (smem + T_SMEM_CTX);
+    uint16_t *s_chain = (uint16_t *) (smem + T_SMEM_CHAIN);
+
+    const uint32_t tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y, slot = blockIdx.z;
+    const uint32_t ntiles = bn.tiles_x * bn.tiles_y, tile = ty * bn.tiles_x + tx;
+    const uint32_t y_frame = rb.f[slot].y;
+
+    // the nine segments: 0..3 own bins; 4, 5 western neighbour (last column, corner); 6, 7 northern one (last row, corner);
+    // 8 north-western one (corner)
+    if (tid < 9u) {
+        const int dtx = (tid == 4u || tid == 5u || tid == 8u) ? -1 : 0, dty = tid >= 6u ? -1 : 0;
+        const uint32_t cls = tid < 4u ? tid : tid == 4u ? 1u : tid == 6u ? 2u : 3u;
+        uint32_t n = 0, first = 0;
+        if ((int) tx + dtx >= 0 && (int) ty + dty >= 0) {
+            const uint32_t t2 = (uint32_t) ((int) ty + dty) * bn.tiles_x + (uint32_t) ((int) tx + dtx);
+            n = bn.cnt[((size_t) slot * ntiles + t2) * 4u + cls];
+            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); }
+            first = (slot * ntiles + t2) * T_STRIDE + bin_off(cls);
+        }
+        cx->segstart[tid + 1u] = n;                              // lengths first, prefix sums below
+        cx->segfirst[tid] = first;
+    }
+    // this tile's counters in the OTHER counter buffer (dirty from the previous batch) are cleared for the next batch
+    if (tid >= 32u && tid < 36u) bn.cnt_other[((size_t) slot * ntiles + tile) * 4u + (tid - 32u)] = 0u;
+    for (uint32_t w = tid; w < T_SWW / 2u; w += 256u) ((uint32_t *) s_slot)[w] = 0xffffffffu;        // level 0
+    __syncthreads();
+    if (tid == 0u) {
+        uint32_t acc = 0;
+        cx->segstart[0] = 0u;
+        for (uint32_t s = 1; s <= 9u; ++s) { acc += cx->segstart[s]; cx->segstart[s] = acc; }
+        cx->novf = 0u;
+    }
+    __syncthreads();
+    const uint32_t m = cx->segstart[9];
+
+    const uint32_t lx = tid & 31u, band = tid >> 5;
+    const uint32_t px = tx * T_TILE + lx, py0 = ty * T_TILE + band * 4u;
+    const size_t np = (size_t) rc.width * rc.height;
+    uint32_t *outf = out + (size_t) rb.f[slot].dst * np;
+    if (m == 0u) {
+        // nothing lands here: background (or nothing) only
+        if (px < rc.width) {
+#pragma unroll
+            for (uint32_t p = 0; p < 4u; ++p) {
+                const uint32_t py = py0 + p;
+                if (py >= rc.height) continue;
+                const size_t i = (size_t) py * rc.width + px;
+                outf[i] = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+            }
+        }
+        return;
+    }
+
+    // ---- stage the records in shared memory, home coordinates made tile-local (+1: halo column / row at 0)
+    for (uint32_t s = 0; s < 9u; ++s) {
+        const uint32_t j0 = cx->segstart[s], n = cx->segstart[s + 1u] - j0, first = cx->segfirst[s];
+        const bool west = s == 4u || s == 5u || s == 8u, north = s >= 6u;
+        for (uint32_t i = tid; i < n; i += 256u) {
+            const uint2 r = bn.rec[(size_t) first + i];
+            const uint32_t sx = west ? 0u : ((r.y >> 16) & 31u) + 1u, sy = north ? 0u : ((r.y >> 22) & 31u) + 1u;
+            s_rec[j0 + i] = make_uint2(r.x, (r.y & 0xffffu) | (sx << 16) | (sy << 22));
+            if (!SINGLE) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
+        }
+    }
+    __syncthreads();
+
+    // ---- order by home: store-and-check rounds
+    const uint32_t nq = (m + 255u) >> 8;                         // records per thread, <= 16
+    uint32_t act = 0;
+    for (uint32_t q = 0; q < nq; ++q) if (tid + (q << 8) < m) act |= 1u << q;
+    for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
+        uint16_t *sl = s_slot + lev * T_SWW;
+        if (lev + 1u < T_NLEV) for (uint32_t w = tid; w < T_SWW / 2u; w += 256u) ((uint32_t *) (sl + T_SWW))[w] = 0xffffffffu;
+        for (uint32_t q = 0; q < nq; ++q)
+            if ((act >> q) & 1u) { const uint32_t j = tid + (q << 8); sl[t_home(s_rec[j].y)] = (uint16_t) j; }
+        if (!__syncthreads_or(act != 0u)) break;                 // nobody stored anything in this round
+        for (uint32_t q = 0; q < nq; ++q)
+            if ((act >> q) & 1u) { const uint32_t j = tid + (q << 8); if (sl[t_home(s_rec[j].y)] == j) act &= ~(1u << q); }
+    }
+    for (uint32_t q = 0; q < nq; ++q)
+        if ((act >> q) & 1u) { const uint32_t k = atomicAdd(&cx->novf, 1u); if (k < T_OVF) s_ovf[k] = (uint16_t) (tid + (q << 8)); }
+    __syncthreads();
+    if (tid == 0u && cx->novf > T_OVF) atomicOr(bn.flag, 1u);
+
+    // ---- fold: home rows band*4 .. band*4 + 4 (shared-memory coordinates), home columns lx + 1 (dx = 0) and lx (dx = 1)
+    TPart P[4];
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) { P[p].R = P[p].G = P[p].B = P[p].A = P[p].N = P[p].cnt = P[p].vis = 0u; P[p].chain = PART_NONE; }
+    uint32_t fullmask = 0;
+    {
+        const uint32_t hb = band * 4u * T_SW + lx;
+        TPart dummy;
+        dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = dummy.vis = 0u; dummy.chain = PART_NONE;
+        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
+        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_slot, s_chain, hb + 1u, dummy, P[0])) fullmask |= 1u;
+        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_slot, s_chain, hb, dummy, P[0])) fullmask |= 1u;
+#pragma unroll
+        for (uint32_t hr = 1; hr < 4u; ++hr) {
+            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_slot, s_chain, hb + hr * T_SW + 1u, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_slot, s_chain, hb + hr * T_SW, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+        }
+        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_slot, s_chain, hb + 4u * T_SW + 1u, P[3], dummy)) fullmask |= 8u;
+        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_slot, s_chain, hb + 4u * T_SW, P[3], dummy)) fullmask |= 8u;
+    }
+
+    // ---- resolve (the tail of k_gather_pixel)
+    if (px >= rc.width) return;
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) {
+        const uint32_t py = py0 + p;
+        if (py >= rc.height) continue;
+        const size_t i = (size_t) py * rc.width + px;
+        const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+        TPart &Q = P[p];
+        bool generic = Q.vis > MAXK || ((fullmask >> p) & 1u);
+        if (!generic && Q.N == 0u) { outf[i] = bgc; continue; }
+        if (!COUNTED) Q.cnt = Q.vis;
+        if (!SINGLE) generic = generic || Q.chain == PART_GENERIC || rc.nchains > 65536u;
+        uint32_t pxl = 0;
+        if (!generic) {
+            bool tie = false;
+            const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * Q.N));
+            uint32_t cr = rdiv_small(Q.R, Q.N, rcp_d2, &tie), cg = rdiv_small(Q.G, Q.N, rcp_d2, &tie), cb = rdiv_small(Q.B, Q.N, rcp_d2, &tie), ca;
+            if (!COUNTED) ca = rc.density == 0 ? 0u : rdiv_small(Q.A, Q.N, rcp_d2, &tie);
+            else if (Q.cnt >= rc.density) ca = rdiv_small(Q.A, Q.N, rcp_d2, &tie);
+            else {
+                unsigned long long num = (unsigned long long) Q.A * Q.cnt, den = (unsigned long long) Q.N * rc.density;
+                unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
+                unsigned long long q = n2 / d2;
+                tie |= (n2 - q * d2 == 0ull);
+                ca = (uint32_t) q;
+            }
+            pxl = c_make(cr, cg, cb, ca);
+            generic = tie;
+            if (tie && stats) atomicAdd(&stats->ties, 1ull);
+        }
+        if (!generic) {
+            const uint32_t chain = SINGLE ? 0u : Q.chain;
+            uint32_t colr = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
+            if (!rc.keep_background) { outf[i] = c_a(colr) ? colr : 0u; continue; }
+            Over ov;
+            ov.add(colr);
+            outf[i] = ov.finish(bgc, true);
+            continue;
+        }
+        if (stats) atomicAdd(&stats->generic, 1ull);
+        outf[i] = resolve_generic_tile<SINGLE>(smem, &bn, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
+                                               y_frame, lx, band * 4u + p, bgc);
+    }
 }
 
 // gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
@@ -924,6 +1313,8 @@ void engine_render_free(Engine *E) {
     dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
@@ -1071,6 +1462,7 @@ int engine_render_prepare(Engine *E) {
     bool bad = !okay || E->fail(cudaStreamSynchronize(E->stream), "render prepare") || E->check("render prepare");
     if (bad) return okay ? AMX_ERR_CUDA : AMX_ERR_NOMEM;
     E->render_ready = true;
+    E->tiled_blocked = false;                 // a new table gets a new chance on the tiled path
     return AMX_OK;
 }
 
@@ -1195,6 +1587,88 @@ static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32
     E->launches++;
 }
 
+// ---- tiled path: bins for RBATCH frames of the current resolution; false when the path cannot be used
+static bool ensure_bins(Engine *E) {
+    const uint32_t tx = div_up(E->width, T_TILE), ty = div_up(E->height, T_TILE);
+    const bool want_chain = E->nchains > 1;
+    if (E->tb_rec && E->tb_tiles_x == tx && E->tb_tiles_y == ty && E->tb_has_chain == want_chain) return true;
+    const uint64_t ntiles = (uint64_t) tx * ty, nrec = (uint64_t) RBATCH * ntiles * T_STRIDE;
+    if (ntiles == 0 || nrec >= (1ull << 32)) return false;               // record indices are 32-bit
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
+    const size_t cnt_bytes = (size_t) 2 * RBATCH * ntiles * 4 * sizeof(uint32_t);
+    if (!dev_alloc(E, (void **) &E->tb_rec, nrec * 8, "bin records") || !dev_alloc(E, (void **) &E->tb_atom, nrec * 4, "bin atoms") ||
+        (want_chain && !dev_alloc(E, (void **) &E->tb_chain, nrec * 4, "bin chains")) ||
+        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 4, "bin flag")) {
+        E->err.clear();                                                   // not an error: the general path needs none of this
+        dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+        E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr;
+        return false;
+    }
+    cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
+    cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
+    E->tb_tiles_x = tx; E->tb_tiles_y = ty; E->tb_has_chain = want_chain;
+    E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
+    return true;
+}
+
+static Bins make_bins(Engine *E) {
+    Bins bn;
+    const size_t per = (size_t) RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4;
+    bn.rec = E->tb_rec; bn.atom = E->tb_atom; bn.chain = E->tb_chain;
+    bn.cnt = E->tb_cnt + (size_t) E->tb_parity * per;
+    bn.cnt_other = E->tb_cnt + (size_t) (E->tb_parity ^ 1u) * per;
+    bn.flag = E->tb_flag;
+    bn.tiles_x = E->tb_tiles_x; bn.tiles_y = E->tb_tiles_y;
+    return bn;
+}
+
+// one batch (<= RBATCH frames of one interval) through k_bin + k_tile
+static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb, const uint32_t *d_bg, uint32_t *d_dst) {
+    RIn ri;
+    ri.pts = E->rpts; ri.c1 = E->rc1; ri.c2 = E->rc2; ri.atom = E->ratom; ri.chain = E->rchain;
+    ri.lag = E->rlag; ri.slope = E->rslope; ri.npt = E->rnpt; ri.table = E->table;
+    const uint32_t n_live = E->r_live[rb.f[0].y];
+    const Bins bn = make_bins(E);
+    const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
+    g_ktime.begin(E->stream);
+    if (n_live > 0) {
+#define AMX_BIN(M, P, H) do { \
+        static int per_sm = 0; \
+        if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
+        const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
+        k_bin<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
+#define AMX_BIN_M(M) do { if (perlin) { if (h2) AMX_BIN(M, true, true); else AMX_BIN(M, true, false); } \
+                          else        { if (h2) AMX_BIN(M, false, true); else AMX_BIN(M, false, false); } } while (0)
+        if (rc.motion == K_LINEAR) AMX_BIN_M(M_LINEAR);
+        else if (rc.motion == K_SPLINE) AMX_BIN_M(M_SPLINE);
+        else AMX_BIN_M(M_NONE);
+#undef AMX_BIN_M
+#undef AMX_BIN
+        E->launches++;
+    }
+    g_ktime.end(E->stream, 0, nb);
+    // k_tile clears slots [0, nb) of the other counter buffer; a longer dirty tail (previous batch was larger) is memset
+    const uint32_t p = E->tb_parity, q = p ^ 1u;
+    const size_t per_slot = (size_t) E->tb_tiles_x * E->tb_tiles_y * 4;
+    if (E->tb_dirty[q] > nb) cudaMemsetAsync(bn.cnt_other + (size_t) nb * per_slot, 0, (size_t) (E->tb_dirty[q] - nb) * per_slot * 4, E->stream);
+    RenderStats *st = (RenderStats *) E->d_render_stats;
+    const dim3 grid(E->tb_tiles_x, E->tb_tiles_y, nb);
+#define AMX_TILE(S, C) do { \
+        static bool attr = false; \
+        if (!attr) { cudaFuncSetAttribute(k_tile<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T_SMEM_BYTES(S)); attr = true; } \
+        k_tile<S, C><<<grid, 256, T_SMEM_BYTES(S), E->stream>>>(bn, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
+    const bool single = E->nchains == 1, counted = rc.density > 1;
+    g_ktime.begin(E->stream);
+    if (single) { if (counted) AMX_TILE(true, true); else AMX_TILE(true, false); }
+    else        { if (counted) AMX_TILE(false, true); else AMX_TILE(false, false); }
+#undef AMX_TILE
+    g_ktime.end(E->stream, 1, nb);
+    E->launches++;
+    E->tb_dirty[q] = 0; E->tb_dirty[p] = nb; E->tb_parity = q;
+    E->tiled_frames += nb;
+}
+
 // scatter + gather into entries + feather of one frame; leaves entries (px/layer) valid and ownership set
 static void launch_frame_entries(Engine *E, const RConst &rc, const RFrame &rf, int32_t chain_only, const Acc &ac) {
     size_t cv = E->canvas();
@@ -1252,6 +1726,9 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     Acc ac = make_acc(E);
     size_t cv = E->canvas();
     const bool single = E->nchains == 1;
+    // feather == 0 without fluid: the tiled path, unless it is switched off / has overflowed with this table
+    const bool tiled = have_chains && E->tiled_enabled && !E->tiled_blocked && rc.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
+    bool tiled_used = false;
     RBatch rb;
     rb.chain_only = -1;
     uint32_t nb = 0;
@@ -1274,6 +1751,8 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     auto flush_batch = [&]() {
         // feather == 0: nb frames share one scatter and one fused gather/composite launch
         if (nb == 0) return;
+        if (tiled) { launch_tiled(E, rc, rb, nb, d_bg, d_dst); tiled_used = true; nb = 0; return; }
+        E->general_frames += nb;
         launch_scatter(E, rc, rb, nb);
         const uint32_t p = E->ab_parity, q = p ^ 1u;
         uint32_t *cnt_other = E->ab_cnt + (size_t) q * RBATCH * cv;
@@ -1338,6 +1817,20 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         if (E->fail(cudaStreamSynchronize(E->copy_stream), "render D2H") || E->fail(cudaStreamSynchronize(E->stream), "render")) rcode = AMX_ERR_CUDA;
     }
     if (E->check("render")) rcode = AMX_ERR_CUDA;
+    if (rcode == AMX_OK && tiled_used) {
+        // did every bin hold its records?  If not, the same frames go through the general path (identical results)
+        uint32_t flag = 0;
+        if (E->fail(cudaMemcpyAsync(&flag, E->tb_flag, 4, cudaMemcpyDeviceToHost, E->stream), "bin flag") ||
+            E->fail(cudaStreamSynchronize(E->stream), "render")) return AMX_ERR_CUDA;
+        if (flag) {
+            const size_t cnt_bytes = (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t);
+            cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
+            cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
+            E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
+            E->tiled_blocked = true;
+            return engine_render(E, times, n, out, out_is_device);
+        }
+    }
     if (rcode == AMX_OK && E->nchains > 1 && !out_is_device && E->d_ovf_used) {
         uint32_t used = 0;
         cudaMemcpy(&used, E->d_ovf_used, 4, cudaMemcpyDeviceToHost);
@@ -1478,6 +1971,11 @@ int amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]) {
     if (E->fail(cudaMemcpyAsync(h, E->d_render_stats, sizeof h, cudaMemcpyDeviceToHost, E->stream), "render stats") ||
         E->fail(cudaStreamSynchronize(E->stream), "render stats")) return AMX_ERR_CUDA;
     for (int i = 0; i < 3; ++i) stats3[i] = h[i];
+    return AMX_OK;
+}
+int amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]) {
+    if (!ctx || !frames2) return AMX_ERR_ARG;
+    frames2[0] = ctx->e.tiled_frames; frames2[1] = ctx->e.general_frames;
     return AMX_OK;
 }
 int amx_background(amx_ctx *ctx, double t, uint32_t *out, int out_is_device) {

@@ -292,6 +292,12 @@ class Engine:
         self._ck(self.L.amx_render_stats(self.h, _p(st)), "render_stats")
         return dict(generic=int(st[0]), ties=int(st[1]), overflow=int(st[2]))
 
+    def render_path_frames(self):
+        """Frames rendered by the tiled path / by the general A-buffer path so far."""
+        st = np.zeros(2, dtype=np.uint64)
+        self._ck(self.L.amx_render_path_frames(self.h, _p(st)), "render_path_frames")
+        return dict(tiled=int(st[0]), general=int(st[1]))
+
     def render_blob(self, b, t):
         cap = self.cw * self.ch + 16
         xy = np.zeros((cap, 2), dtype=np.uint16)

@@ -141,6 +141,9 @@ int  amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out);
  * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
  * went to an overflow list */
 int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
+/* frames rendered so far by [0] the tiled path (shared-memory tiles, feather == 0 without fluid) and [1] the general
+ * A-buffer path (feather, per-blob fetch, or more than 3.5 atoms per pixel over a 32x32 tile); both are exact */
+int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
 /* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
  * returns count via *n (pixels in reference emission order), -1 in *n when the blob index is out of range */
 int  amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_t *xy_out, uint32_t *rgba_out, int64_t *n, uint64_t *group);

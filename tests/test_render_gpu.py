@@ -44,6 +44,12 @@ def test_render_matches_reference(reflib, name, scene, params):
         ndiff += n
         total += ref.size
     assert ndiff <= 0.01 * total, "%s: %d of %d pixels differ" % (name, ndiff, total)
+    # feather == 0 goes through the tiled path (shared-memory tiles), feather > 0 through the general A-buffer path
+    paths = e.render_path_frames()
+    if params.get("feather", 0) == 0:
+        assert paths["tiled"] == len(TIMES) and paths["general"] == 0, paths
+    else:
+        assert paths["tiled"] == 0, paths
 
 
 def test_render_multi_blob_order_and_show_blobs(reflib):
@@ -67,3 +73,41 @@ def test_batch_equals_single(reflib):
     batch = e.render(ts)
     for i, t in enumerate(ts):
         assert np.array_equal(batch[i], e.render([t])[0])
+
+
+def test_tiled_path_equals_general_path(reflib, monkeypatch):
+    """The two render paths (tiled / general A-buffer) are both exact: identical frames, 2x2 and 3x3 tiles, partial edge tiles."""
+    for size, k, params in ((64, 2, dict(motion=eng.SPLINE, fading=eng.COSINE)), (80, 3, dict(motion=eng.LINEAR, fading=eng.PERLIN, density=2)),
+                            (72, 2, dict(motion=eng.SPLINE, fading=eng.LINEAR, keep_background=1))):
+        images = scenes.ellipses(size, k, seed=31 + size)
+        m = build_ref(reflib, images, seed=3, **params)
+        m.set(cycle_length=2000)
+        m.sync()
+        m.iterate(30)
+        m.sync()
+        ts = [m.get_time(f, 12) for f in range(12)]
+        monkeypatch.setenv("AMX_RENDER_TILED", "1")
+        e1 = engine_from_ref(m, images, seed=3, **params)
+        a = e1.render(ts)
+        assert e1.render_path_frames() == dict(tiled=12, general=0)
+        monkeypatch.setenv("AMX_RENDER_TILED", "0")
+        e0 = engine_from_ref(m, images, seed=3, **params)
+        b = e0.render(ts)
+        assert e0.render_path_frames() == dict(tiled=0, general=12)
+        assert np.array_equal(a, b)
+        for i in (0, 5, 11):
+            n, mx = diff_stats(m.render(ts[i]), a[i])
+            assert mx <= 1 and n <= 0.01 * a[i].size
+
+
+def test_tiled_path_overflow_falls_back(reflib):
+    """More atoms than a tile's bins take (density 6 = 6 atoms per pixel): the frames are rendered again by the general path."""
+    images = scenes.ellipses(96, 2, seed=17)             # the middle tile is covered completely: 6144 records > 3584
+    params = dict(motion=eng.LINEAR, fading=eng.LINEAR, density=6)
+    m = build_ref(reflib, images, seed=1, **params)
+    e = engine_from_ref(m, images, seed=1, **params)
+    for t in (0.0, 0.4, 0.9):
+        n, mx = diff_stats(m.render(t), e.render([t])[0])
+        assert mx <= 1 and n <= 0.01 * 96 * 96
+    paths = e.render_path_frames()
+    assert paths["general"] >= 3 and paths["tiled"] <= 1, paths
