@@ -154,7 +154,9 @@ struct Engine {
     bool      tb_has_chain = false;
     bool      tiled_enabled = true;        // AMX_RENDER_TILED=0: general A-buffer path only (for comparisons)
     bool      tiled_blocked = false;       // a bin overflowed with the current table: general path until the next refresh
-    uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_stats)
+    uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_path_frames)
+    uint32_t  tb_demand[6] = {0, 0, 0, 0, 0, 0};       // largest bin counts per class, tile total, overflow list seen (amx_render_tiled_stats)
+    uint64_t  tiled_fallbacks = 0;                    // render calls that were repeated on the general path
     uint32_t *d_bg = nullptr;              // background images of one batch (keep_background)
     size_t    d_bg_cap = 0;
     // per-(pixel, blob) entries for the feather / per-blob paths (canvas sized + overflow hash)

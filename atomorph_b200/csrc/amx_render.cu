@@ -713,22 +713,21 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // k_gather_pixel; ties, several blobs at a pixel, homes with overflow records take the ordered double replay
 // (resolve_contributions).
 //
-// Capacity: a tile takes T_SREC records per frame (3.5 atoms per pixel).  A bin or tile that would need more raises
-// bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
+// Capacity: a tile takes T_SREC records per frame (its nine bins together; an interior bin holds 3.5 atoms per pixel).
+// A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
 // are identical, both being exact).
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
 #define T_SWW    1090u                  // 33 * 33 homes, padded to a whole number of 32-bit words
-#define T_NLEV   6u                     // direct record slots per home
-#define T_SREC   4096u                  // records of one tile and frame (own four bins + five neighbour bins)
+#define T_NLEV   8u                     // direct record slots per home
+#define T_SREC   4096u                  // records a tile takes in one frame (own four bins + five neighbour bins)
 #define T_OVF    512u                   // records beyond the T_NLEV-th of their home
 #define T_EMPTY  0xffffu
-#define T_CAP0   3584u                  // bin capacities per class; T_CAP0 + 4 * T_CAP1 + 4 * T_CAP3 == T_SREC
-#define T_CAP1   96u
-#define T_CAP3   32u
+#define T_CAP0   3584u                  // bin capacities per class (interior / last column or row / corner)
+#define T_CAP1   256u
+#define T_CAP3   64u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
 #define T_KEY_NONE 0xffffffffu
-static_assert(T_CAP0 + 4u * T_CAP1 + 4u * T_CAP3 == T_SREC, "bin capacities must add up to the tile capacity");
 
 struct Bins {
     uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | lx << 16 | ly << 22}
@@ -736,13 +735,33 @@ struct Bins {
     uint32_t *chain;      // same layout: chain of the atom; nullptr for a single chain
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
     uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
-    uint32_t *flag;       // != 0: something overflowed, the frames must be rendered again by the general path
+    uint32_t *flag;       // [0] != 0: something overflowed, the frames must be rendered again by the general path;
+                          // [1..4] largest bin count seen per class, [5] largest tile total, [6] longest overflow list (diagnostics)
     uint32_t  tiles_x, tiles_y;
 };
 __device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls == 0u ? 0u : cls == 1u ? T_CAP0 : cls == 2u ? T_CAP0 + T_CAP1 : T_CAP0 + 2u * T_CAP1; }
 __device__ __forceinline__ uint32_t bin_cap(uint32_t cls) { return cls == 0u ? T_CAP0 : cls == 3u ? T_CAP3 : T_CAP1; }
 
-// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile
+// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile.
+// Software-pipelined like k_scatter: the records of an atom are stored one iteration after their slots were claimed, so
+// the claiming atomics have a whole iteration of arithmetic to come back.
+struct BinPend { uint32_t key[RBATCH], col[RBATCH], meta[RBATCH], who[RBATCH], base[RBATCH], atom, chain; };
+
+__device__ __forceinline__ void bin_store(const BinPend &p, const Bins &bn, uint32_t nb, uint32_t ntiles) {
+#pragma unroll
+    for (uint32_t s = 0; s < RBATCH; ++s) {
+        if (s >= nb) continue;
+        const uint32_t b = __shfl_sync(0xffffffffu, p.base[s], (int) (p.who[s] & 255u));      // the leader's claim
+        if (p.key[s] == T_KEY_NONE) continue;
+        const uint32_t cls = p.key[s] & 3u, pos = b + (p.who[s] >> 8);
+        if (pos >= bin_cap(cls)) continue;                        // dropped: k_tile sees the counter beyond the capacity and raises the flag
+        const size_t o = ((size_t) s * ntiles + (p.key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
+        bn.rec[o] = make_uint2(p.col[s], p.meta[s]);
+        bn.atom[o] = p.atom;
+        if (bn.chain) bn.chain[o] = p.chain;
+    }
+}
+
 template <int MOTION, bool PERLIN, bool H2>
 __global__ void __launch_bounds__(256, 3)
 k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
@@ -756,16 +775,21 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     RawIn next = RawIn();
     if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
+    BinPend pend;
+#pragma unroll
+    for (uint32_t s = 0; s < RBATCH; ++s) { pend.key[s] = T_KEY_NONE; pend.col[s] = pend.meta[s] = pend.who[s] = pend.base[s] = 0u; }
+    pend.atom = pend.chain = 0u;
     // warp-uniform trip count: claiming bin slots is a warp collective
     for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
         const bool valid = i < n_live;
         const RawIn raw = next;
         if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
 
-        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
+        BinPend cur;
+        cur.atom = raw.atom; cur.chain = raw.chain;
 #pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) key[s] = T_KEY_NONE;
-        bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
+        for (uint32_t s = 0; s < RBATCH; ++s) { cur.key[s] = T_KEY_NONE; cur.col[s] = cur.meta[s] = 0u; }
+        const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
         if (use) {
             AtomIn in;
             in.pt1 = raw.pt1; in.pt2 = raw.pt2;
@@ -779,51 +803,44 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
                 if (s >= nb) continue;
                 uint32_t fr, hx, hy;
                 // a home at x >= width or y >= height reaches no pixel of the image
-                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr) && hx < rc.width && hy < rc.height) {
+                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &cur.col[s], &fr) && hx < rc.width && hy < rc.height) {
                     const uint32_t lx = hx & 31u, ly = hy & 31u;
                     const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
-                    key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
-                    meta[s] = fr | (lx << 16) | (ly << 22);
+                    cur.key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
+                    cur.meta[s] = fr | (lx << 16) | (ly << 22);
                 }
             }
         }
+        bin_store(pend, bn, nb, ntiles);
         // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots
-        uint32_t base[RBATCH], who[RBATCH];
 #pragma unroll
         for (uint32_t s = 0; s < RBATCH; ++s) {
-            base[s] = 0u; who[s] = 0u;
+            cur.base[s] = 0u; cur.who[s] = 0u;
             if (s >= nb) continue;
-            const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
+            const uint32_t peers = __match_any_sync(0xffffffffu, cur.key[s]);
             const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
-            who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
+            cur.who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
+            if (lane == leader && cur.key[s] != T_KEY_NONE) cur.base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + cur.key[s]], (uint32_t) __popc(peers));
         }
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) {
-            if (s >= nb) continue;
-            const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));
-            if (key[s] == T_KEY_NONE) continue;
-            const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
-            if (pos >= bin_cap(cls)) continue;                    // dropped: k_tile sees the counter beyond the capacity and raises the flag
-            const size_t o = ((size_t) s * ntiles + (key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
-            bn.rec[o] = make_uint2(col[s], meta[s]);
-            bn.atom[o] = raw.atom;
-            if (bn.chain) bn.chain[o] = raw.chain;
-        }
+        pend = cur;
     }
+    bin_store(pend, bn, nb, ntiles);
 }
 
-struct TPart { uint32_t R, G, B, A, N, cnt, chain, vis; };
+struct TPart { uint32_t R, G, B, A, N, cnt, chain; };
+static_assert(4u * T_NLEV <= MAXK, "the fast path folds at most MAXK records into a pixel (32-bit sums)");
 
 // what the out-of-line replay needs to find the records of a pixel again (lives in shared memory)
 struct TileCtx {
     uint32_t segstart[10];    // prefix sums of the nine segment lengths: tile-local record index -> segment
     uint32_t segfirst[9];     // global index of a segment's first record
     uint32_t novf;
-    uint32_t pad[4];
+    uint32_t n_generic, n_ties;   // per-tile diagnostics, flushed with one atomic each
+    uint32_t pad[2];
 };
 #define T_SMEM_REC   0u
-#define T_SMEM_SLOT  (T_SREC * 8u)
+#define T_SMEM_ATOM  (T_SREC * 8u)
+#define T_SMEM_SLOT  (T_SMEM_ATOM + T_SREC * 4u)
 #define T_SMEM_OVF   (T_SMEM_SLOT + T_NLEV * T_SWW * 2u)
 #define T_SMEM_CTX   (T_SMEM_OVF + T_OVF * 2u)
 #define T_SMEM_CHAIN (T_SMEM_CTX + (uint32_t) sizeof(TileCtx))
@@ -853,13 +870,13 @@ __device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const
         if (!SINGLE) tag = s_chain[j];
         if (HAS_A) {
             const uint32_t n = wx * (255u - yf);
-            Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n; Pa.vis += has ? 1u : 0u;
+            Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n;
             if (COUNTED) Pa.cnt += (n != 0u);
             if (!SINGLE) { if (n) Pa.chain = merge_chain(Pa.chain, tag); }
         }
         if (HAS_B) {
             const uint32_t n = wx * yf;
-            Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n; Pb.vis += has ? 1u : 0u;
+            Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n;
             if (COUNTED) Pb.cnt += (n != 0u);
             if (!SINGLE) { if (n) Pb.chain = merge_chain(Pb.chain, tag); }
         }
@@ -869,14 +886,14 @@ __device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const
 
 // the ordered double replay of one pixel of a tile (local pixel lx, ly): ties, several blobs, overflowing homes
 template <bool SINGLE>
-__device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem, const Bins *bnp, const RConst *rcp, const uint32_t *__restrict__ chain_of,
+__device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem, const RConst *rcp, const uint32_t *__restrict__ chain_of,
                                                       const int32_t *__restrict__ boc, const uint32_t *__restrict__ blob_avg,
                                                       const uint32_t *__restrict__ blob_distinct, uint32_t y_frame, uint32_t lx, uint32_t ly, uint32_t bgc) {
     const uint2 *s_rec = (const uint2 *) (smem + T_SMEM_REC);
     const uint16_t *s_slot = (const uint16_t *) (smem + T_SMEM_SLOT);
     const uint16_t *s_ovf = (const uint16_t *) (smem + T_SMEM_OVF);
     const TileCtx *cx = (const TileCtx *) (smem + T_SMEM_CTX);
-    const uint32_t *g_atom = bnp->atom;
+    const uint32_t *s_atom = (const uint32_t *) (smem + T_SMEM_ATOM);
     const RConst rc = *rcp;
     auto visit = [&](auto f) {
 #pragma unroll
@@ -887,10 +904,7 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
                 const uint2 r = s_rec[j];
                 const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
                 const uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
-                if (!n) return;
-                uint32_t s = 0;
-                while (s < 8u && j >= cx->segstart[s + 1u]) ++s;
-                f(g_atom[(size_t) cx->segfirst[s] + (j - cx->segstart[s])], r.x, n, 0u);
+                if (n) f(s_atom[j], r.x, n, 0u);
             };
             uint32_t lev = 0;
             for (; lev < T_NLEV; ++lev) {
@@ -920,6 +934,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
        const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint2 *s_rec = (uint2 *) (smem + T_SMEM_REC);
+    uint32_t *s_atom = (uint32_t *) (smem + T_SMEM_ATOM);
     uint16_t *s_slot = (uint16_t *) (smem + T_SMEM_SLOT);
     uint16_t *s_ovf = (uint16_t *) (smem + T_SMEM_OVF);
     TileCtx *cx = (TileCtx *) (smem + T_SMEM_CTX);
@@ -938,6 +953,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         if ((int) tx + dtx >= 0 && (int) ty + dty >= 0) {
             const uint32_t t2 = (uint32_t) ((int) ty + dty) * bn.tiles_x + (uint32_t) ((int) tx + dtx);
             n = bn.cnt[((size_t) slot * ntiles + t2) * 4u + cls];
+            if (tid < 4u && n > bn.flag[1u + cls]) atomicMax(&bn.flag[1u + cls], n);
             if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); }
             first = (slot * ntiles + t2) * T_STRIDE + bin_off(cls);
         }
@@ -952,7 +968,13 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         uint32_t acc = 0;
         cx->segstart[0] = 0u;
         for (uint32_t s = 1; s <= 9u; ++s) { acc += cx->segstart[s]; cx->segstart[s] = acc; }
-        cx->novf = 0u;
+        if (acc > bn.flag[5]) atomicMax(&bn.flag[5], acc);
+        if (acc > T_SREC) {
+            // more records than the tile's shared memory takes: truncate (memory safety) and have the frames rendered again
+            atomicOr(bn.flag, 1u);
+            for (uint32_t s = 1; s <= 9u; ++s) cx->segstart[s] = min(cx->segstart[s], T_SREC);
+        }
+        cx->novf = 0u; cx->n_generic = 0u; cx->n_ties = 0u;
     }
     __syncthreads();
     const uint32_t m = cx->segstart[9];
@@ -983,38 +1005,48 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             const uint2 r = bn.rec[(size_t) first + i];
             const uint32_t sx = west ? 0u : ((r.y >> 16) & 31u) + 1u, sy = north ? 0u : ((r.y >> 22) & 31u) + 1u;
             s_rec[j0 + i] = make_uint2(r.x, (r.y & 0xffffu) | (sx << 16) | (sy << 22));
+            s_atom[j0 + i] = bn.atom[(size_t) first + i];
             if (!SINGLE) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
         }
     }
     __syncthreads();
 
-    // ---- order by home: store-and-check rounds
+    // ---- order by home: store-and-check rounds (a thread walks only the records it still has to place)
     const uint32_t nq = (m + 255u) >> 8;                         // records per thread, <= 16
-    uint32_t act = 0;
-    for (uint32_t q = 0; q < nq; ++q) if (tid + (q << 8) < m) act |= 1u << q;
+    uint32_t act = nq >= 1u ? (1u << (nq - 1u)) - 1u : 0u;      // q < nq - 1: always a record
+    if (nq >= 1u && tid + ((nq - 1u) << 8) < m) act |= 1u << (nq - 1u);
     for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
         uint16_t *sl = s_slot + lev * T_SWW;
         if (lev + 1u < T_NLEV) for (uint32_t w = tid; w < T_SWW / 2u; w += 256u) ((uint32_t *) (sl + T_SWW))[w] = 0xffffffffu;
-        for (uint32_t q = 0; q < nq; ++q)
-            if ((act >> q) & 1u) { const uint32_t j = tid + (q << 8); sl[t_home(s_rec[j].y)] = (uint16_t) j; }
+        for (uint32_t a = act; a; a &= a - 1u) {
+            const uint32_t j = tid + (((uint32_t) __ffs((int) a) - 1u) << 8);
+            sl[t_home(s_rec[j].y)] = (uint16_t) j;
+        }
         if (!__syncthreads_or(act != 0u)) break;                 // nobody stored anything in this round
-        for (uint32_t q = 0; q < nq; ++q)
-            if ((act >> q) & 1u) { const uint32_t j = tid + (q << 8); if (sl[t_home(s_rec[j].y)] == j) act &= ~(1u << q); }
+        for (uint32_t a = act; a; a &= a - 1u) {
+            const uint32_t q = (uint32_t) __ffs((int) a) - 1u, j = tid + (q << 8);
+            if (sl[t_home(s_rec[j].y)] == j) act &= ~(1u << q);
+        }
     }
-    for (uint32_t q = 0; q < nq; ++q)
-        if ((act >> q) & 1u) { const uint32_t k = atomicAdd(&cx->novf, 1u); if (k < T_OVF) s_ovf[k] = (uint16_t) (tid + (q << 8)); }
+    for (uint32_t a = act; a; a &= a - 1u) {
+        const uint32_t k = atomicAdd(&cx->novf, 1u);
+        if (k < T_OVF) s_ovf[k] = (uint16_t) (tid + (((uint32_t) __ffs((int) a) - 1u) << 8));
+    }
     __syncthreads();
-    if (tid == 0u && cx->novf > T_OVF) atomicOr(bn.flag, 1u);
+    if (tid == 0u && cx->novf > 0u) {
+        if (cx->novf > bn.flag[6]) atomicMax(&bn.flag[6], cx->novf);
+        if (cx->novf > T_OVF) atomicOr(bn.flag, 1u);
+    }
 
     // ---- fold: home rows band*4 .. band*4 + 4 (shared-memory coordinates), home columns lx + 1 (dx = 0) and lx (dx = 1)
     TPart P[4];
 #pragma unroll
-    for (uint32_t p = 0; p < 4u; ++p) { P[p].R = P[p].G = P[p].B = P[p].A = P[p].N = P[p].cnt = P[p].vis = 0u; P[p].chain = PART_NONE; }
+    for (uint32_t p = 0; p < 4u; ++p) { P[p].R = P[p].G = P[p].B = P[p].A = P[p].N = P[p].cnt = 0u; P[p].chain = PART_NONE; }
     uint32_t fullmask = 0;
     {
         const uint32_t hb = band * 4u * T_SW + lx;
         TPart dummy;
-        dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = dummy.vis = 0u; dummy.chain = PART_NONE;
+        dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = 0u; dummy.chain = PART_NONE;
         // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
         if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_slot, s_chain, hb + 1u, dummy, P[0])) fullmask |= 1u;
         if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_slot, s_chain, hb, dummy, P[0])) fullmask |= 1u;
@@ -1028,17 +1060,15 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     }
 
     // ---- resolve (the tail of k_gather_pixel)
-    if (px >= rc.width) return;
 #pragma unroll
     for (uint32_t p = 0; p < 4u; ++p) {
         const uint32_t py = py0 + p;
-        if (py >= rc.height) continue;
+        if (px >= rc.width || py >= rc.height) continue;
         const size_t i = (size_t) py * rc.width + px;
         const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
         TPart &Q = P[p];
-        bool generic = Q.vis > MAXK || ((fullmask >> p) & 1u);
+        bool generic = ((fullmask >> p) & 1u) != 0u;             // a home with every slot taken may have more records
         if (!generic && Q.N == 0u) { outf[i] = bgc; continue; }
-        if (!COUNTED) Q.cnt = Q.vis;
         if (!SINGLE) generic = generic || Q.chain == PART_GENERIC || rc.nchains > 65536u;
         uint32_t pxl = 0;
         if (!generic) {
@@ -1056,7 +1086,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             }
             pxl = c_make(cr, cg, cb, ca);
             generic = tie;
-            if (tie && stats) atomicAdd(&stats->ties, 1ull);
+            if (tie) atomicAdd(&cx->n_ties, 1u);
         }
         if (!generic) {
             const uint32_t chain = SINGLE ? 0u : Q.chain;
@@ -1067,9 +1097,14 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             outf[i] = ov.finish(bgc, true);
             continue;
         }
-        if (stats) atomicAdd(&stats->generic, 1ull);
-        outf[i] = resolve_generic_tile<SINGLE>(smem, &bn, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
+        atomicAdd(&cx->n_generic, 1u);
+        outf[i] = resolve_generic_tile<SINGLE>(smem, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
                                                y_frame, lx, band * 4u + p, bgc);
+    }
+    __syncthreads();
+    if (tid == 0u && stats) {
+        if (cx->n_generic) atomicAdd(&stats->generic, (unsigned long long) cx->n_generic);
+        if (cx->n_ties) atomicAdd(&stats->ties, (unsigned long long) cx->n_ties);
     }
 }
 
@@ -1599,14 +1634,14 @@ static bool ensure_bins(Engine *E) {
     const size_t cnt_bytes = (size_t) 2 * RBATCH * ntiles * 4 * sizeof(uint32_t);
     if (!dev_alloc(E, (void **) &E->tb_rec, nrec * 8, "bin records") || !dev_alloc(E, (void **) &E->tb_atom, nrec * 4, "bin atoms") ||
         (want_chain && !dev_alloc(E, (void **) &E->tb_chain, nrec * 4, "bin chains")) ||
-        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 4, "bin flag")) {
+        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4, "bin flag")) {
         E->err.clear();                                                   // not an error: the general path needs none of this
         dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
         E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr;
         return false;
     }
     cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
-    cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
+    cudaMemsetAsync(E->tb_flag, 0, 8 * 4, E->stream);
     E->tb_tiles_x = tx; E->tb_tiles_y = ty; E->tb_has_chain = want_chain;
     E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
     return true;
@@ -1819,10 +1854,12 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     if (E->check("render")) rcode = AMX_ERR_CUDA;
     if (rcode == AMX_OK && tiled_used) {
         // did every bin hold its records?  If not, the same frames go through the general path (identical results)
-        uint32_t flag = 0;
-        if (E->fail(cudaMemcpyAsync(&flag, E->tb_flag, 4, cudaMemcpyDeviceToHost, E->stream), "bin flag") ||
+        uint32_t flag8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (E->fail(cudaMemcpyAsync(flag8, E->tb_flag, sizeof flag8, cudaMemcpyDeviceToHost, E->stream), "bin flag") ||
             E->fail(cudaStreamSynchronize(E->stream), "render")) return AMX_ERR_CUDA;
-        if (flag) {
+        for (int k = 0; k < 6; ++k) E->tb_demand[k] = std::max(E->tb_demand[k], flag8[1 + k]);
+        if (flag8[0]) {
+            E->tiled_fallbacks++;
             const size_t cnt_bytes = (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t);
             cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
             cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
@@ -1976,6 +2013,12 @@ int amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]) {
 int amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]) {
     if (!ctx || !frames2) return AMX_ERR_ARG;
     frames2[0] = ctx->e.tiled_frames; frames2[1] = ctx->e.general_frames;
+    return AMX_OK;
+}
+int amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]) {
+    if (!ctx || !stats8) return AMX_ERR_ARG;
+    for (int k = 0; k < 6; ++k) stats8[k] = ctx->e.tb_demand[k];
+    stats8[6] = ctx->e.tiled_fallbacks; stats8[7] = ctx->e.tiled_blocked ? 1 : 0;
     return AMX_OK;
 }
 int amx_background(amx_ctx *ctx, double t, uint32_t *out, int out_is_device) {

@@ -298,6 +298,11 @@ class Engine:
         self._ck(self.L.amx_render_path_frames(self.h, _p(st)), "render_path_frames")
         return dict(tiled=int(st[0]), general=int(st[1]))
 
+    def render_tiled_stats(self):
+        st = np.zeros(8, dtype=np.uint64)
+        self._ck(self.L.amx_render_tiled_stats(self.h, _p(st)), "render_tiled_stats")
+        return dict(max_bin=[int(v) for v in st[:4]], max_tile=int(st[4]), max_overflow=int(st[5]), fallbacks=int(st[6]), blocked=bool(st[7]))
+
     def render_blob(self, b, t):
         cap = self.cw * self.ch + 16
         xy = np.zeros((cap, 2), dtype=np.uint16)

@@ -330,7 +330,7 @@ def run_b200(args):
                    "l2": "256 MB buffer written between timed steps", "step": "render %d frames; swap: %d rounds" % (F, SWAP_ROUNDS),
                    "parallelism": "frames: frame-range x%d; swap: atom-range x%d + 1 all-gather/step" % (world, world)},
         "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None,
-                     "peak_kind": peak_kind, "kernel": "k_scatter+k_gather_composite (per frame)",
+                     "peak_kind": peak_kind, "kernel": "k_bin+k_tile (per frame)",
                      "bytes_per_unit": render_bytes, "unit_name": "frame"},
         "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps, "rounds_per_step": SWAP_ROUNDS,
                  "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
@@ -340,7 +340,7 @@ def run_b200(args):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "render_stats": e.render_stats(),
+        "render_stats": dict(e.render_stats(), path_frames=e.render_path_frames(), tiled=e.render_tiled_stats()),
         "match": {"rounds": int(args.match_rounds), "proposals_per_atom": args.match_rounds / 2.0, "cost_initial": cost0, "cost_matched": cost1},
     }
 

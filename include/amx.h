@@ -144,6 +144,10 @@ int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
 /* frames rendered so far by [0] the tiled path (shared-memory tiles, feather == 0 without fluid) and [1] the general
  * A-buffer path (feather, per-blob fetch, or more than 3.5 atoms per pixel over a 32x32 tile); both are exact */
 int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
+/* tiled-path diagnostics: [0..3] largest record count seen in a bin of class interior / last column / last row / corner,
+ * [4] largest record total of a tile, [5] longest per-tile overflow list, [6] render calls repeated on the general path,
+ * [7] 1 while the tiled path is blocked for the current table */
+int  amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]);
 /* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
  * returns count via *n (pixels in reference emission order), -1 in *n when the blob index is out of range */
 int  amx_render_blob(amx_ctx *ctx, uint32_t blob, double t, uint64_t cap, uint16_t *xy_out, uint32_t *rgba_out, int64_t *n, uint64_t *group);
