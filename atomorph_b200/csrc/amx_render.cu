@@ -42,6 +42,7 @@
 #include <numeric>
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <cuda_pipeline.h>
 #include "amx_engine.h"
 
 namespace amx {
@@ -713,24 +714,23 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // k_gather_pixel; ties, several blobs at a pixel, homes with overflow records take the ordered double replay
 // (resolve_contributions).
 //
-// Capacity: a tile takes T_SREC records per frame (its nine bins together; an interior bin holds 3.5 atoms per pixel).
+// Capacity: a tile takes T_SREC records per frame (its nine bins together: 3 atoms per pixel; an interior bin holds 2.5 atoms per pixel).
 // A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
 // are identical, both being exact).
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
-#define T_SWW    1090u                  // 33 * 33 homes, padded to a whole number of 32-bit words
 #define T_NLEV   8u                     // direct record slots per home
-#define T_SREC   4096u                  // records a tile takes in one frame (own four bins + five neighbour bins)
+#define T_SREC   3072u                  // records a tile takes in one frame (own four bins + five neighbour bins)
 #define T_OVF    512u                   // records beyond the T_NLEV-th of their home
 #define T_EMPTY  0xffffu
-#define T_CAP0   3584u                  // bin capacities per class (interior / last column or row / corner)
-#define T_CAP1   256u
+#define T_CAP0   2560u                  // bin capacities per class (interior / last column or row / corner)
+#define T_CAP1   192u
 #define T_CAP3   64u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
 #define T_KEY_NONE 0xffffffffu
 
 struct Bins {
-    uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | lx << 16 | ly << 22}
+    uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | home << 16}, home = (ly + 1) * 33 + lx + 1
     uint32_t *atom;       // same layout: original atom index (the reference's summation order)
     uint32_t *chain;      // same layout: chain of the atom; nullptr for a single chain
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
@@ -763,7 +763,7 @@ __device__ __forceinline__ void bin_store(const BinPend &p, const Bins &bn, uint
 }
 
 template <int MOTION, bool PERLIN, bool H2>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
@@ -807,7 +807,7 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
                     const uint32_t lx = hx & 31u, ly = hy & 31u;
                     const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
                     cur.key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
-                    cur.meta[s] = fr | (lx << 16) | (ly << 22);
+                    cur.meta[s] = fr | (((ly + 1u) * T_SW + lx + 1u) << 16);    // home in the tile's shared-memory coordinates
                 }
             }
         }
@@ -841,12 +841,13 @@ struct TileCtx {
 #define T_SMEM_REC   0u
 #define T_SMEM_ATOM  (T_SREC * 8u)
 #define T_SMEM_SLOT  (T_SMEM_ATOM + T_SREC * 4u)
-#define T_SMEM_OVF   (T_SMEM_SLOT + T_NLEV * T_SWW * 2u)
+#define T_SMEM_OVF   (T_SMEM_SLOT + T_SW * T_SW * T_NLEV * 2u)      // slots: [home][level], 16 bytes per home
 #define T_SMEM_CTX   (T_SMEM_OVF + T_OVF * 2u)
 #define T_SMEM_CHAIN (T_SMEM_CTX + (uint32_t) sizeof(TileCtx))
 #define T_SMEM_BYTES(SINGLE) (T_SMEM_CHAIN + ((SINGLE) ? 0u : T_SREC * 2u))
 
-__device__ __forceinline__ uint32_t t_home(uint32_t meta) { return ((meta >> 22) & 63u) * T_SW + ((meta >> 16) & 63u); }
+__device__ __forceinline__ uint32_t t_home(uint32_t meta) { return meta >> 16; }
+static_assert(T_NLEV == 8u, "one 16-byte load fetches the eight slots of a home");
 
 // Fold the records of home h (shared-memory coordinates) into the pixel it reaches with dy = 0 (Pa) and the one with
 // dy = 1 (Pb); DX selects the x weight.  Returns true when every slot of the home is taken (there may be overflow
@@ -854,11 +855,13 @@ __device__ __forceinline__ uint32_t t_home(uint32_t meta) { return ((meta >> 22)
 template <bool SINGLE, bool COUNTED, int DX, bool HAS_A, bool HAS_B>
 __device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_slot, const uint16_t *__restrict__ s_chain,
                                           uint32_t h, TPart &Pa, TPart &Pb) {
+    const uint4 sl = *(const uint4 *) (s_slot + h * T_NLEV);              // the eight slots of the home
+    const uint32_t slw[4] = {sl.x, sl.y, sl.z, sl.w};
     bool has = true;
 #pragma unroll
     for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
-        const uint32_t idx = s_slot[lev * T_SWW + h];
-        has = has && idx != T_EMPTY;
+        const uint32_t idx = (lev & 1u) ? slw[lev >> 1] >> 16 : slw[lev >> 1] & 0xffffu;
+        has = idx != T_EMPTY;                                             // slots fill in order: empty from the first empty one on
         if (lev >= 2u && !__any_sync(0xffffffffu, has)) break;
         const uint32_t j = has ? idx : 0u;
         const uint2 r = s_rec[j];
@@ -908,7 +911,7 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
             };
             uint32_t lev = 0;
             for (; lev < T_NLEV; ++lev) {
-                const uint32_t idx = s_slot[lev * T_SWW + h];
+                const uint32_t idx = s_slot[h * T_NLEV + lev];
                 if (idx == T_EMPTY) break;
                 emit(idx);
             }
@@ -927,7 +930,7 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
 
 // pass 2: one CTA per (tile, frame of the batch); thread = pixel column lx of a band of four rows
 template <bool SINGLE, bool COUNTED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SINGLE ? 4 : 3)
 k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
        const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
        const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
@@ -962,7 +965,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     }
     // this tile's counters in the OTHER counter buffer (dirty from the previous batch) are cleared for the next batch
     if (tid >= 32u && tid < 36u) bn.cnt_other[((size_t) slot * ntiles + tile) * 4u + (tid - 32u)] = 0u;
-    for (uint32_t w = tid; w < T_SWW / 2u; w += 256u) ((uint32_t *) s_slot)[w] = 0xffffffffu;        // level 0
+    for (uint32_t w = tid; w < T_SW * T_SW; w += 256u) ((uint4 *) s_slot)[w] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     __syncthreads();
     if (tid == 0u) {
         uint32_t acc = 0;
@@ -997,16 +1000,26 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         return;
     }
 
-    // ---- stage the records in shared memory, home coordinates made tile-local (+1: halo column / row at 0)
+    // ---- stage the records in shared memory: asynchronous copies (LDGSTS), all nine segments in flight at once
     for (uint32_t s = 0; s < 9u; ++s) {
         const uint32_t j0 = cx->segstart[s], n = cx->segstart[s + 1u] - j0, first = cx->segfirst[s];
-        const bool west = s == 4u || s == 5u || s == 8u, north = s >= 6u;
         for (uint32_t i = tid; i < n; i += 256u) {
-            const uint2 r = bn.rec[(size_t) first + i];
-            const uint32_t sx = west ? 0u : ((r.y >> 16) & 31u) + 1u, sy = north ? 0u : ((r.y >> 22) & 31u) + 1u;
-            s_rec[j0 + i] = make_uint2(r.x, (r.y & 0xffffu) | (sx << 16) | (sy << 22));
-            s_atom[j0 + i] = bn.atom[(size_t) first + i];
+            __pipeline_memcpy_async(&s_rec[j0 + i], &bn.rec[(size_t) first + i], 8);
+            __pipeline_memcpy_async(&s_atom[j0 + i], &bn.atom[(size_t) first + i], 4);
             if (!SINGLE) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
+        }
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    // a neighbour's record sits in ITS last column / row: that is this tile's halo column / row 0
+    {
+        const uint32_t w0 = cx->segstart[4], w1 = cx->segstart[6], n1 = cx->segstart[8], e1 = cx->segstart[9];
+        for (uint32_t j = w0 + tid; j < e1; j += 256u) {
+            uint32_t back = 0u;
+            if (j < w1 || j >= n1) back += 32u;                   // western and north-western neighbour: x 32 -> 0
+            if (j >= w1) back += 32u * T_SW;                      // northern and north-western neighbour: y 32 -> 0
+            s_rec[j].y -= back << 16;
         }
     }
     __syncthreads();
@@ -1016,16 +1029,15 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     uint32_t act = nq >= 1u ? (1u << (nq - 1u)) - 1u : 0u;      // q < nq - 1: always a record
     if (nq >= 1u && tid + ((nq - 1u) << 8) < m) act |= 1u << (nq - 1u);
     for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
-        uint16_t *sl = s_slot + lev * T_SWW;
-        if (lev + 1u < T_NLEV) for (uint32_t w = tid; w < T_SWW / 2u; w += 256u) ((uint32_t *) (sl + T_SWW))[w] = 0xffffffffu;
+        uint16_t *sl = s_slot + lev;
         for (uint32_t a = act; a; a &= a - 1u) {
             const uint32_t j = tid + (((uint32_t) __ffs((int) a) - 1u) << 8);
-            sl[t_home(s_rec[j].y)] = (uint16_t) j;
+            sl[t_home(s_rec[j].y) * T_NLEV] = (uint16_t) j;
         }
         if (!__syncthreads_or(act != 0u)) break;                 // nobody stored anything in this round
         for (uint32_t a = act; a; a &= a - 1u) {
             const uint32_t q = (uint32_t) __ffs((int) a) - 1u, j = tid + (q << 8);
-            if (sl[t_home(s_rec[j].y)] == j) act &= ~(1u << q);
+            if (sl[t_home(s_rec[j].y) * T_NLEV] == j) act &= ~(1u << q);
         }
     }
     for (uint32_t a = act; a; a &= a - 1u) {
@@ -1086,7 +1098,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             }
             pxl = c_make(cr, cg, cb, ca);
             generic = tie;
-            if (tie) atomicAdd(&cx->n_ties, 1u);
+            if (tie && stats) atomicAdd(&stats->ties, 1ull);
         }
         if (!generic) {
             const uint32_t chain = SINGLE ? 0u : Q.chain;
@@ -1097,14 +1109,9 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             outf[i] = ov.finish(bgc, true);
             continue;
         }
-        atomicAdd(&cx->n_generic, 1u);
+        if (stats) atomicAdd(&stats->generic, 1ull);
         outf[i] = resolve_generic_tile<SINGLE>(smem, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
                                                y_frame, lx, band * 4u + p, bgc);
-    }
-    __syncthreads();
-    if (tid == 0u && stats) {
-        if (cx->n_generic) atomicAdd(&stats->generic, (unsigned long long) cx->n_generic);
-        if (cx->n_ties) atomicAdd(&stats->ties, (unsigned long long) cx->n_ties);
     }
 }
 
