@@ -714,16 +714,28 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // k_gather_pixel; ties, several blobs at a pixel, homes with overflow records take the ordered double replay
 // (resolve_contributions).
 //
-// Capacity: a tile takes T_SREC records per frame (its nine bins together: 3 atoms per pixel; an interior bin holds 2.5 atoms per pixel).
+// Capacity: a tile takes T_SREC records per frame (its nine bins together: 3 atoms per pixel; an interior bin holds 2.5).
 // A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
 // are identical, both being exact).
+#ifndef T_CTAS
+#define T_CTAS 4                        // resident k_tile CTAs per SM the single-chain instance is compiled for (64 registers)
+#endif
+#ifndef T_ROWPF
+#define T_ROWPF 0                       // 1: load the slot words of the next home row before folding the current one
+#endif
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
 #define T_NLEV   8u                     // direct record slots per home
-#define T_SREC   3072u                  // records a tile takes in one frame (own four bins + five neighbour bins)
+#if T_CTAS >= 4
+#define T_SREC   3072u                  // (4 CTAs of 55 KB per SM)
+#define T_CAP0   2560u
+#else
+#define T_SREC   4096u                  // (3 CTAs of 72 KB per SM)
+#define T_CAP0   3584u
+#endif
 #define T_OVF    512u                   // records beyond the T_NLEV-th of their home
 #define T_EMPTY  0xffffu
-#define T_CAP0   2560u                  // bin capacities per class (interior / last column or row / corner)
+// T_SREC: records a tile takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities per class (interior / last column or row / corner)
 #define T_CAP1   192u
 #define T_CAP3   64u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
@@ -853,10 +865,9 @@ static_assert(T_NLEV == 8u, "one 16-byte load fetches the eight slots of a home"
 // dy = 1 (Pb); DX selects the x weight.  Returns true when every slot of the home is taken (there may be overflow
 // records).  Slots 0 and 1 are folded branch-free by the whole warp, the others behind a vote.
 template <bool SINGLE, bool COUNTED, int DX, bool HAS_A, bool HAS_B>
-__device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_slot, const uint16_t *__restrict__ s_chain,
-                                          uint32_t h, TPart &Pa, TPart &Pb) {
-    const uint4 sl = *(const uint4 *) (s_slot + h * T_NLEV);              // the eight slots of the home
-    const uint32_t slw[4] = {sl.x, sl.y, sl.z, sl.w};
+__device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain,
+                                          const uint4 sl, TPart &Pa, TPart &Pb) {
+    const uint32_t slw[4] = {sl.x, sl.y, sl.z, sl.w};                     // the eight slots of the home
     bool has = true;
 #pragma unroll
     for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
@@ -930,7 +941,7 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
 
 // pass 2: one CTA per (tile, frame of the batch); thread = pixel column lx of a band of four rows
 template <bool SINGLE, bool COUNTED>
-__global__ void __launch_bounds__(256, SINGLE ? 4 : 3)
+__global__ void __launch_bounds__(256, SINGLE ? T_CTAS : 3)
 k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
        const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
        const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
@@ -1056,19 +1067,34 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     for (uint32_t p = 0; p < 4u; ++p) { P[p].R = P[p].G = P[p].B = P[p].A = P[p].N = P[p].cnt = 0u; P[p].chain = PART_NONE; }
     uint32_t fullmask = 0;
     {
-        const uint32_t hb = band * 4u * T_SW + lx;
+        const uint4 *sl4 = (const uint4 *) s_slot + (band * 4u * T_SW + lx);     // [home]: the eight slots of a home in 16 bytes
         TPart dummy;
         dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = 0u; dummy.chain = PART_NONE;
-        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
-        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_slot, s_chain, hb + 1u, dummy, P[0])) fullmask |= 1u;
-        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_slot, s_chain, hb, dummy, P[0])) fullmask |= 1u;
+        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0
+        // only.  The slot words of the next row are loaded before the current row is folded.
+        uint4 s0 = sl4[1], s1 = sl4[0];
+        uint4 n0, n1;
+#if T_ROWPF
+        n0 = sl4[T_SW + 1u]; n1 = sl4[T_SW];
+#endif
+        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_chain, s0, dummy, P[0])) fullmask |= 1u;
+        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_chain, s1, dummy, P[0])) fullmask |= 1u;
 #pragma unroll
         for (uint32_t hr = 1; hr < 4u; ++hr) {
-            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_slot, s_chain, hb + hr * T_SW + 1u, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
-            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_slot, s_chain, hb + hr * T_SW, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+#if T_ROWPF
+            s0 = n0; s1 = n1;
+            n0 = sl4[(hr + 1u) * T_SW + 1u]; n1 = sl4[(hr + 1u) * T_SW];
+#else
+            s0 = sl4[hr * T_SW + 1u]; s1 = sl4[hr * T_SW];
+#endif
+            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_chain, s0, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_chain, s1, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
         }
-        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_slot, s_chain, hb + 4u * T_SW + 1u, P[3], dummy)) fullmask |= 8u;
-        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_slot, s_chain, hb + 4u * T_SW, P[3], dummy)) fullmask |= 8u;
+#if !T_ROWPF
+        n0 = sl4[4u * T_SW + 1u]; n1 = sl4[4u * T_SW];
+#endif
+        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_chain, n0, P[3], dummy)) fullmask |= 8u;
+        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_chain, n1, P[3], dummy)) fullmask |= 8u;
     }
 
     // ---- resolve (the tail of k_gather_pixel)
@@ -1579,17 +1605,43 @@ static void launch_background(Engine *E, const RConst &rc, const RFrame &rf, uin
 
 static dim3 grid2d(uint32_t w, uint32_t h) { return dim3(div_up(w, 32), div_up(h, 8)); }
 
-// AMX_KTIME=1: per-kernel device times (cudaEvents, one sync per launch) accumulated and printed -- diagnostics only
+// Per-kernel device times (amx_kernel_times / AMX_KTIME=1): CUDA event pairs recorded around the two render kernels of
+// every batch on the engine's stream, WITHOUT synchronising; the pairs are resolved when the times are read.
 struct KTime {
-    bool on; cudaEvent_t a, b; double tot[4]; uint64_t n[4];
-    KTime() : on(getenv("AMX_KTIME") != nullptr), a(nullptr), b(nullptr) { for (int i = 0; i < 4; ++i) { tot[i] = 0; n[i] = 0; } }
-    void begin(cudaStream_t st) { if (!on) return; if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, st); }
-    void end(cudaStream_t st, int k, uint32_t frames) {
+    bool on, report;
+    std::vector<cudaEvent_t> pool;            // pairs: [2k] before, [2k + 1] after
+    std::vector<uint32_t> what;               // per pair: kernel class (0 scatter / bin, 1 gather / tile) | frames << 8
+    size_t used;
+    double tot[2]; uint64_t frames[2], launches[2];
+    KTime() : on(getenv("AMX_KTIME") != nullptr), report(on), used(0) { reset(); }
+    void reset() { for (int i = 0; i < 2; ++i) { tot[i] = 0; frames[i] = 0; launches[i] = 0; } }
+    void begin(cudaStream_t st) {
         if (!on) return;
-        cudaEventRecord(b, st); cudaEventSynchronize(b);
-        float ms = 0; cudaEventElapsedTime(&ms, a, b); tot[k] += ms; n[k] += frames;
+        if (used == 4096) collect();            // bounded pool: resolve (one synchronisation) and reuse
+        if (pool.size() < 2 * (used + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); pool.push_back(a); pool.push_back(b); what.push_back(0); }
+        cudaEventRecord(pool[2 * used], st);
     }
-    ~KTime() { if (on) for (int k = 0; k < 2; ++k) if (n[k]) fprintf(stderr, "[AMX_KTIME] %s: %.2f us/frame over %llu frames\n", k ? "gather" : "scatter", 1000.0 * tot[k] / n[k], (unsigned long long) n[k]); }
+    void end(cudaStream_t st, int k, uint32_t nframes) {
+        if (!on) return;
+        cudaEventRecord(pool[2 * used + 1], st);
+        what[used] = (uint32_t) k | (nframes << 8);
+        ++used;
+    }
+    void collect() {
+        for (size_t i = 0; i < used; ++i) {
+            float ms = 0;
+            cudaEventSynchronize(pool[2 * i + 1]);
+            if (cudaEventElapsedTime(&ms, pool[2 * i], pool[2 * i + 1]) != cudaSuccess) continue;
+            const int k = (int) (what[i] & 255u);
+            tot[k] += ms; frames[k] += what[i] >> 8; launches[k] += 1;
+        }
+        used = 0;
+    }
+    ~KTime() {
+        if (!report) return;
+        collect();
+        for (int k = 0; k < 2; ++k) if (frames[k]) fprintf(stderr, "[AMX_KTIME] %s: %.2f us/frame over %llu frames, %.2f us/launch\n", k ? "gather/tile" : "scatter/bin", 1000.0 * tot[k] / frames[k], (unsigned long long) frames[k], 1000.0 * tot[k] / launches[k]);
+    }
 };
 static KTime g_ktime;
 
@@ -2015,6 +2067,19 @@ int amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]) {
     if (E->fail(cudaMemcpyAsync(h, E->d_render_stats, sizeof h, cudaMemcpyDeviceToHost, E->stream), "render stats") ||
         E->fail(cudaStreamSynchronize(E->stream), "render stats")) return AMX_ERR_CUDA;
     for (int i = 0; i < 3; ++i) stats3[i] = h[i];
+    return AMX_OK;
+}
+int amx_kernel_times(amx_ctx *ctx, int enable, double ms2[2], uint64_t launches2[2], uint64_t frames2[2]) {
+    if (!ctx) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    g_ktime.collect();
+    for (int k = 0; k < 2; ++k) {
+        if (ms2) ms2[k] = g_ktime.tot[k];
+        if (launches2) launches2[k] = g_ktime.launches[k];
+        if (frames2) frames2[k] = g_ktime.frames[k];
+    }
+    g_ktime.reset();
+    g_ktime.on = enable != 0;
     return AMX_OK;
 }
 int amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]) {

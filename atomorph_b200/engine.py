@@ -298,6 +298,15 @@ class Engine:
         self._ck(self.L.amx_render_path_frames(self.h, _p(st)), "render_path_frames")
         return dict(tiled=int(st[0]), general=int(st[1]))
 
+    def kernel_times(self, enable):
+        """Per-kernel device times of the render batches since the last call (ms, launches, frames per kernel class:
+        0 = k_bin / k_scatter, 1 = k_tile / k_gather_pixel); then switches the event recording on or off."""
+        ms = np.zeros(2, dtype=np.float64)
+        ln = np.zeros(2, dtype=np.uint64)
+        fr = np.zeros(2, dtype=np.uint64)
+        self._ck(self.L.amx_kernel_times(self.h, 1 if enable else 0, _p(ms), _p(ln), _p(fr)), "kernel_times")
+        return [dict(ms=float(ms[k]), launches=int(ln[k]), frames=int(fr[k])) for k in range(2)]
+
     def render_tiled_stats(self):
         st = np.zeros(8, dtype=np.uint64)
         self._ck(self.L.amx_render_tiled_stats(self.h, _p(st)), "render_tiled_stats")

@@ -276,6 +276,12 @@ def run_b200(args):
     launches0 = e.launch_count()
     sampler.start()
     ms_render = timed(render_step, args.steps, args.warmup)
+    # per-kernel launch durations for the roofline: a second pass over the same steps with a CUDA event pair around every
+    # render kernel launch (the pairs keep consecutive launches from overlapping their launch latencies, which costs ~8 %,
+    # so `value` above is timed without them)
+    e.kernel_times(True)
+    timed(render_step, max(1, min(args.steps, 3)), 1)
+    ktimes = e.kernel_times(False)                  # [k_bin, k_tile]
     st0 = e.swap_stats()
     ms_swap = timed(swap_step, args.steps, args.warmup)
     st1 = e.swap_stats()
@@ -318,7 +324,25 @@ def run_b200(args):
 
     render_bytes = A * 24 + P * 4                  # linear or h <= 3 -> 24 B/atom + 4 B/pixel
     swap_bytes = 32                                # h = 2: 4 distinct key points per proposal
-    r_ach = render_bytes * (F * args.steps) / (ms_render / 1000.0) / 1e9
+    # roofline of the render batch = the kernel pair k_bin + k_tile (one launch each per batch of frames): algorithmic bytes
+    # of the frames of a batch / the pair's device time, measured with CUDA events around each launch on the engine's stream
+    kb, kt = ktimes
+    if kb["launches"] and kt["launches"] and kt["frames"]:
+        pair_ms = kb["ms"] / kb["launches"] + kt["ms"] / kt["launches"]
+        frames_per_launch = kt["frames"] / float(kt["launches"])
+        r_ach = render_bytes * frames_per_launch / (pair_ms / 1000.0) / 1e9
+        kernels = {"k_bin": {"us_per_launch": 1000.0 * kb["ms"] / kb["launches"], "launches": kb["launches"]},
+                   "k_tile": {"us_per_launch": 1000.0 * kt["ms"] / kt["launches"], "launches": kt["launches"]},
+                   "frames_per_launch": frames_per_launch}
+    else:
+        r_ach = render_bytes * (F * args.steps) / (ms_render / 1000.0) / 1e9
+        kernels = None
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+            traffic = json.load(fh).get("k_bin+k_tile_dram_bytes_per_launch_pair")
+    except Exception:
+        pass
     s_ach = swap_bytes * (proposals / world) / (ms_swap / 1000.0) / 1e9
 
     line = {
@@ -329,9 +353,9 @@ def run_b200(args):
         "config": {"workload": "C2 synthetic %dx%d RGBA, 2 key frames, %d atoms, spline+cosine, %d frames per GPU" % (size, size, A, F),
                    "l2": "256 MB buffer written between timed steps", "step": "render %d frames; swap: %d rounds" % (F, SWAP_ROUNDS),
                    "parallelism": "frames: frame-range x%d; swap: atom-range x%d + 1 all-gather/step" % (world, world)},
-        "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None,
-                     "peak_kind": peak_kind, "kernel": "k_bin+k_tile (per frame)",
-                     "bytes_per_unit": render_bytes, "unit_name": "frame"},
+        "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": traffic,
+                     "peak_kind": peak_kind, "kernel": "k_bin+k_tile (one launch each per batch of frames)",
+                     "bytes_per_unit": render_bytes, "unit_name": "frame", "kernels": kernels},
         "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps, "rounds_per_step": SWAP_ROUNDS,
                  "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
                               "traffic": None, "kernel": "k_swap_tiled", "bytes_per_unit": swap_bytes, "unit_name": "proposal",

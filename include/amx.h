@@ -141,6 +141,11 @@ int  amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out);
  * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
  * went to an overflow list */
 int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
+/* device time of the two render kernels of every batch ([0] k_bin or k_scatter, [1] k_tile or k_gather_pixel), measured
+ * with CUDA event pairs on the engine's stream without synchronising between launches.  Returns the milliseconds,
+ * launches and frames accumulated since the previous call, then switches the recording on (enable != 0) or off.
+ * Process-wide (one engine per process records). */
+int  amx_kernel_times(amx_ctx *ctx, int enable, double ms2[2], uint64_t launches2[2], uint64_t frames2[2]);
 /* frames rendered so far by [0] the tiled path (shared-memory tiles, feather == 0 without fluid) and [1] the general
  * A-buffer path (feather, per-blob fetch, or more than 3.5 atoms per pixel over a 32x32 tile); both are exact */
 int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
