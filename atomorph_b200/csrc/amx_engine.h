@@ -144,7 +144,7 @@ struct Engine {
     uint4    *ab_pair_base = nullptr;
     uint32_t *ab_ovf_head = nullptr;
     uint4    *ab_ovf_rec = nullptr;
-    uint32_t  render_batch = 2;            // frames per scatter/gather launch pair
+    uint32_t  render_batch = 8;            // frames per launch pair (clamped to RBATCH on the tiled path, GBATCH on the general one)
     // tiled path (amx_render.cu: Bins): record bins per (frame slot of a batch, 32x32-pixel tile)
     uint2    *tb_rec = nullptr;
     uint32_t *tb_atom = nullptr, *tb_chain = nullptr;

@@ -49,7 +49,8 @@ namespace amx {
 
 #define MAXK 32
 #define K_SLOTS 4          // direct A-buffer slots per pixel (two 32-byte pairs)
-#define RBATCH 2           // frames per launch (all of one key-frame interval)
+#define RBATCH 8           // frames per launch of the tiled path (all of one key-frame interval)
+#define GBATCH 2           // frames per launch of the general A-buffer path (its buffers are per canvas position and frame)
 
 struct RConst {
     uint32_t width, height, cw, ch;
@@ -85,8 +86,8 @@ struct RBatch {
 // Record: x = colour, y = x_fract | y_fract << 8 | (chain & 0xffff) << 16, z = atom (direct) / next (overflow).
 struct ABuf {
     uint32_t *cnt;
-    uint4    *pair;               // [RBATCH][canvas][2]
-    uint4    *pair2;              // [RBATCH][canvas][2], sparsely used
+    uint4    *pair;               // [GBATCH][canvas][2]
+    uint4    *pair2;              // [GBATCH][canvas][2], sparsely used
     uint32_t *ovf_head;
     uint4    *ovf_rec;
     size_t    canvas;             // stride between batch slots (cnt, pair/2, pair2/2, ovf_head)
@@ -270,11 +271,11 @@ __device__ __forceinline__ RawIn load_raw(const RIn &ri, size_t A, uint32_t y, s
 }
 
 // records of one atom whose slots have been claimed but not yet stored
-struct Pending { uint32_t home[RBATCH], col[RBATCH], meta[RBATCH], k[RBATCH], who, okmask; };
+struct Pending { uint32_t home[GBATCH], col[GBATCH], meta[GBATCH], k[GBATCH], who, okmask; };
 
 __device__ __forceinline__ void store_pending(const Pending &p, const ABuf &ab, RenderStats *__restrict__ stats) {
 #pragma unroll
-    for (uint32_t s = 0; s < RBATCH; ++s) {
+    for (uint32_t s = 0; s < GBATCH; ++s) {
         if (!(p.okmask & (1u << s))) continue;
         const size_t hp = (size_t) s * ab.canvas + p.home[s];
         const uint4 rec = make_uint4(p.col[s], p.meta[s], p.who, 0u);
@@ -326,7 +327,7 @@ k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, R
             in.lag = raw.lag; in.slope = raw.slope;
             const uint32_t meta_chain = (raw.chain & 0xffffu) << 16;
 #pragma unroll
-            for (uint32_t s = 0; s < RBATCH; ++s) {
+            for (uint32_t s = 0; s < GBATCH; ++s) {
                 if (s >= nb) continue;
                 uint32_t fr, hx, hy;
                 if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &cur.col[s], &fr)) {
@@ -338,7 +339,7 @@ k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, R
         }
         store_pending(pend, ab, stats);
 #pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s)
+        for (uint32_t s = 0; s < GBATCH; ++s)
             if (cur.okmask & (1u << s)) cur.k[s] = atomicAdd(&ab.cnt[(size_t) s * ab.canvas + cur.home[s]], 1u);
         pend = cur;
     }
@@ -751,29 +752,12 @@ struct Bins {
                           // [1..4] largest bin count seen per class, [5] largest tile total, [6] longest overflow list (diagnostics)
     uint32_t  tiles_x, tiles_y;
 };
-__device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls == 0u ? 0u : cls == 1u ? T_CAP0 : cls == 2u ? T_CAP0 + T_CAP1 : T_CAP0 + 2u * T_CAP1; }
+__device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls ? T_CAP0 + (cls - 1u) * T_CAP1 : 0u; }
 __device__ __forceinline__ uint32_t bin_cap(uint32_t cls) { return cls == 0u ? T_CAP0 : cls == 3u ? T_CAP3 : T_CAP1; }
 
-// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile.
-// Software-pipelined like k_scatter: the records of an atom are stored one iteration after their slots were claimed, so
-// the claiming atomics have a whole iteration of arithmetic to come back.
-struct BinPend { uint32_t key[RBATCH], col[RBATCH], meta[RBATCH], who[RBATCH], base[RBATCH], atom, chain; };
-
-__device__ __forceinline__ void bin_store(const BinPend &p, const Bins &bn, uint32_t nb, uint32_t ntiles) {
-#pragma unroll
-    for (uint32_t s = 0; s < RBATCH; ++s) {
-        if (s >= nb) continue;
-        const uint32_t b = __shfl_sync(0xffffffffu, p.base[s], (int) (p.who[s] & 255u));      // the leader's claim
-        if (p.key[s] == T_KEY_NONE) continue;
-        const uint32_t cls = p.key[s] & 3u, pos = b + (p.who[s] >> 8);
-        if (pos >= bin_cap(cls)) continue;                        // dropped: k_tile sees the counter beyond the capacity and raises the flag
-        const size_t o = ((size_t) s * ntiles + (p.key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
-        bn.rec[o] = make_uint2(p.col[s], p.meta[s]);
-        bn.atom[o] = p.atom;
-        if (bn.chain) bn.chain[o] = p.chain;
-    }
-}
-
+// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile.  An atom's
+// key points and end colours are loaded and converted once for all frames of the batch; the claiming atomics of all
+// frames are issued back to back before the first record is stored.
 template <int MOTION, bool PERLIN, bool H2>
 __global__ void __launch_bounds__(256, 2)
 k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
@@ -787,20 +771,15 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     RawIn next = RawIn();
     if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
-    BinPend pend;
-#pragma unroll
-    for (uint32_t s = 0; s < RBATCH; ++s) { pend.key[s] = T_KEY_NONE; pend.col[s] = pend.meta[s] = pend.who[s] = pend.base[s] = 0u; }
-    pend.atom = pend.chain = 0u;
     // warp-uniform trip count: claiming bin slots is a warp collective
     for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
         const bool valid = i < n_live;
         const RawIn raw = next;
         if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
 
-        BinPend cur;
-        cur.atom = raw.atom; cur.chain = raw.chain;
+        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
 #pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) { cur.key[s] = T_KEY_NONE; cur.col[s] = cur.meta[s] = 0u; }
+        for (uint32_t s = 0; s < RBATCH; ++s) { key[s] = T_KEY_NONE; col[s] = meta[s] = 0u; }
         const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
         if (use) {
             AtomIn in;
@@ -815,28 +794,38 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
                 if (s >= nb) continue;
                 uint32_t fr, hx, hy;
                 // a home at x >= width or y >= height reaches no pixel of the image
-                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &cur.col[s], &fr) && hx < rc.width && hy < rc.height) {
+                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr) && hx < rc.width && hy < rc.height) {
                     const uint32_t lx = hx & 31u, ly = hy & 31u;
                     const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
-                    cur.key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
-                    cur.meta[s] = fr | (((ly + 1u) * T_SW + lx + 1u) << 16);    // home in the tile's shared-memory coordinates
+                    key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
+                    meta[s] = fr | (((ly + 1u) * T_SW + lx + 1u) << 16);    // home in the tile's shared-memory coordinates
                 }
             }
         }
-        bin_store(pend, bn, nb, ntiles);
         // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots
+        uint32_t who[RBATCH], base[RBATCH];
 #pragma unroll
         for (uint32_t s = 0; s < RBATCH; ++s) {
-            cur.base[s] = 0u; cur.who[s] = 0u;
+            base[s] = 0u; who[s] = 0u;
             if (s >= nb) continue;
-            const uint32_t peers = __match_any_sync(0xffffffffu, cur.key[s]);
+            const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
             const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
-            cur.who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-            if (lane == leader && cur.key[s] != T_KEY_NONE) cur.base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + cur.key[s]], (uint32_t) __popc(peers));
+            who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
+            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
         }
-        pend = cur;
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            if (s >= nb) continue;
+            const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));      // the leader's claim
+            if (key[s] == T_KEY_NONE) continue;
+            const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
+            if (pos >= bin_cap(cls)) continue;                    // dropped: k_tile sees the counter beyond the capacity and raises the flag
+            const size_t o = ((size_t) s * ntiles + (key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
+            bn.rec[o] = make_uint2(col[s], meta[s]);
+            bn.atom[o] = raw.atom;
+            if (bn.chain) bn.chain[o] = raw.chain;
+        }
     }
-    bin_store(pend, bn, nb, ntiles);
 }
 
 struct TPart { uint32_t R, G, B, A, N, cnt, chain; };
@@ -1444,20 +1433,20 @@ int engine_render_prepare(Engine *E) {
     if (rcode != AMX_OK) return rcode;
     size_t cv = E->canvas();
     if (!E->ab_cnt) {
-        // A-buffer for RBATCH frames: counters + K_SLOTS direct records per canvas position, overflow list per atom
+        // A-buffer for GBATCH frames: counters + K_SLOTS direct records per canvas position, overflow list per atom
         // (cnt and pair get a guard of cw + 1 positions in front: the gather reads its left / upper neighbours unconditionally)
         const size_t guard = (size_t) E->cw + 1;
-        if (!dev_alloc(E, (void **) &E->ab_cnt_base, (2 * RBATCH * cv + guard) * 4, "abuf counters") ||
+        if (!dev_alloc(E, (void **) &E->ab_cnt_base, (2 * GBATCH * cv + guard) * 4, "abuf counters") ||
             !dev_alloc(E, (void **) &E->d_render_stats, sizeof(RenderStats), "render stats") ||
-            !dev_alloc(E, (void **) &E->ab_pair_base, ((size_t) 2 * RBATCH * cv + 2 * guard) * 16, "abuf record pairs") ||
-            !dev_alloc(E, (void **) &E->ab_pair2, (size_t) 2 * RBATCH * cv * 16, "abuf second record pairs") ||
-            !dev_alloc(E, (void **) &E->ab_ovf_head, RBATCH * cv * 4, "abuf overflow heads") ||
-            !dev_alloc(E, (void **) &E->ab_ovf_rec, RBATCH * E->A * 16, "abuf overflow records"))
+            !dev_alloc(E, (void **) &E->ab_pair_base, ((size_t) 2 * GBATCH * cv + 2 * guard) * 16, "abuf record pairs") ||
+            !dev_alloc(E, (void **) &E->ab_pair2, (size_t) 2 * GBATCH * cv * 16, "abuf second record pairs") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_head, GBATCH * cv * 4, "abuf overflow heads") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_rec, GBATCH * E->A * 16, "abuf overflow records"))
             return AMX_ERR_NOMEM;
         // two counter buffers: the gather of a batch clears the one the previous batch used, so no memset per batch
         E->ab_cnt = E->ab_cnt_base + guard;
         E->ab_pair = E->ab_pair_base + 2 * guard;
-        cudaMemsetAsync(E->ab_cnt_base, 0, (2 * RBATCH * cv + guard) * 4, E->stream);
+        cudaMemsetAsync(E->ab_cnt_base, 0, (2 * GBATCH * cv + guard) * 4, E->stream);
         cudaMemsetAsync(E->d_render_stats, 0, sizeof(RenderStats), E->stream);
         E->ab_parity = 0; E->ab_dirty[0] = E->ab_dirty[1] = 0;
     }
@@ -1648,12 +1637,12 @@ static KTime g_ktime;
 static ABuf make_abuf(Engine *E) {
     ABuf ab;
     size_t cv = E->canvas();
-    ab.cnt = E->ab_cnt + (size_t) E->ab_parity * RBATCH * cv; ab.pair = E->ab_pair; ab.pair2 = E->ab_pair2; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
+    ab.cnt = E->ab_cnt + (size_t) E->ab_parity * GBATCH * cv; ab.pair = E->ab_pair; ab.pair2 = E->ab_pair2; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
     ab.canvas = cv; ab.A = E->A;
     return ab;
 }
 
-// scatter `nb` frames (<= RBATCH) into the slots of the A-buffer
+// scatter `nb` frames (<= GBATCH) into the slots of the A-buffer
 // (into the counter buffer E->ab_parity, which is clean by invariant)
 static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb) {
     RIn ri;
@@ -1808,7 +1797,10 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         if (rcode != AMX_OK) return rcode;
         d_dst = E->d_out;
     }
-    const uint32_t NB = std::max(1u, std::min<uint32_t>(E->render_batch, RBATCH));
+    // frames per launch pair: AMX_RENDER_BATCH (default RBATCH) on the tiled path, at most GBATCH on the general one
+    // feather == 0 without fluid: the tiled path, unless it is switched off / has overflowed with this table
+    const bool tiled = have_chains && E->tiled_enabled && !E->tiled_blocked && E->p.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
+    const uint32_t NB = std::max(1u, std::min<uint32_t>(E->render_batch, tiled ? RBATCH : GBATCH));
     if (E->p.keep_background && E->d_bg_cap < (size_t) NB * np) {
         dev_free(E->d_bg); E->d_bg = nullptr; E->d_bg_cap = 0;
         if (!dev_alloc(E, (void **) &E->d_bg, (size_t) NB * np * 4, "bg")) return AMX_ERR_NOMEM;
@@ -1820,8 +1812,6 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     Acc ac = make_acc(E);
     size_t cv = E->canvas();
     const bool single = E->nchains == 1;
-    // feather == 0 without fluid: the tiled path, unless it is switched off / has overflowed with this table
-    const bool tiled = have_chains && E->tiled_enabled && !E->tiled_blocked && rc.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
     bool tiled_used = false;
     RBatch rb;
     rb.chain_only = -1;
@@ -1849,7 +1839,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         E->general_frames += nb;
         launch_scatter(E, rc, rb, nb);
         const uint32_t p = E->ab_parity, q = p ^ 1u;
-        uint32_t *cnt_other = E->ab_cnt + (size_t) q * RBATCH * cv;
+        uint32_t *cnt_other = E->ab_cnt + (size_t) q * GBATCH * cv;
         // the gather clears slots [0, nb) of the other counter buffer; a longer dirty tail (previous batch was larger) is memset
         if (E->ab_dirty[q] > nb) cudaMemsetAsync(cnt_other + (size_t) nb * cv, 0, (size_t) (E->ab_dirty[q] - nb) * cv * 4, E->stream);
         dim3 grid(div_up(rc.cw, 32), div_up(rc.ch, 8), nb);
