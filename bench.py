@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[1]): synthetic 1024x1024 RGBA, 2 key frames (ful
 1 048 576 atoms, spline motion + cosine fading, 64 output frames.
 
 One STEP = one pass of the hot path over one batch:
-    render phase : the 64 output frames of the morph (k_scatter / k_gather_composite per batch of frames)
+    render phase : the 64 output frames of the morph (k_bin + k_tile per batch of 8 frames)
     swap phase   : SWAP_ROUNDS rounds of disjoint pair-swap proposals on the 1M-atom chain
 Both phases are timed separately with CUDA events on the engine's stream, inputs resident in HBM.
 `value` is the render throughput (frames/s); the swap throughput and its roofline are reported in
