@@ -721,9 +721,6 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #ifndef T_CTAS
 #define T_CTAS 4                        // resident k_tile CTAs per SM the single-chain instance is compiled for (64 registers)
 #endif
-#ifndef T_ROWPF
-#define T_ROWPF 0                       // 1: load the slot words of the next home row before folding the current one
-#endif
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
 #define T_NLEV   8u                     // direct record slots per home
@@ -1056,34 +1053,36 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     for (uint32_t p = 0; p < 4u; ++p) { P[p].R = P[p].G = P[p].B = P[p].A = P[p].N = P[p].cnt = 0u; P[p].chain = PART_NONE; }
     uint32_t fullmask = 0;
     {
-        const uint4 *sl4 = (const uint4 *) s_slot + (band * 4u * T_SW + lx);     // [home]: the eight slots of a home in 16 bytes
+        const uint32_t hb = band * 4u * T_SW + lx;
+        const uint4 *sl4 = (const uint4 *) s_slot + hb;                           // [home]: the eight slots of a home in 16 bytes
+        // nothing at any of the homes that reach the warp's 32 x 4 pixels (sparse scenes): background only
+        bool any0 = false;
+#pragma unroll
+        for (uint32_t hr = 0; hr < 5u; ++hr) any0 = any0 || s_slot[(hb + hr * T_SW) * T_NLEV] != T_EMPTY || s_slot[(hb + hr * T_SW + 1u) * T_NLEV] != T_EMPTY;
+        if (!__any_sync(0xffffffffu, any0)) {
+            if (px < rc.width) {
+#pragma unroll
+                for (uint32_t p = 0; p < 4u; ++p) {
+                    const uint32_t py = py0 + p;
+                    if (py >= rc.height) continue;
+                    const size_t i = (size_t) py * rc.width + px;
+                    outf[i] = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+                }
+            }
+            return;
+        }
         TPart dummy;
         dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = 0u; dummy.chain = PART_NONE;
-        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0
-        // only.  The slot words of the next row are loaded before the current row is folded.
-        uint4 s0 = sl4[1], s1 = sl4[0];
-        uint4 n0, n1;
-#if T_ROWPF
-        n0 = sl4[T_SW + 1u]; n1 = sl4[T_SW];
-#endif
-        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_chain, s0, dummy, P[0])) fullmask |= 1u;
-        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_chain, s1, dummy, P[0])) fullmask |= 1u;
+        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
+        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_chain, sl4[1], dummy, P[0])) fullmask |= 1u;
+        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_chain, sl4[0], dummy, P[0])) fullmask |= 1u;
 #pragma unroll
         for (uint32_t hr = 1; hr < 4u; ++hr) {
-#if T_ROWPF
-            s0 = n0; s1 = n1;
-            n0 = sl4[(hr + 1u) * T_SW + 1u]; n1 = sl4[(hr + 1u) * T_SW];
-#else
-            s0 = sl4[hr * T_SW + 1u]; s1 = sl4[hr * T_SW];
-#endif
-            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_chain, s0, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
-            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_chain, s1, P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_chain, sl4[hr * T_SW + 1u], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_chain, sl4[hr * T_SW], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
         }
-#if !T_ROWPF
-        n0 = sl4[4u * T_SW + 1u]; n1 = sl4[4u * T_SW];
-#endif
-        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_chain, n0, P[3], dummy)) fullmask |= 8u;
-        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_chain, n1, P[3], dummy)) fullmask |= 8u;
+        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_chain, sl4[4u * T_SW + 1u], P[3], dummy)) fullmask |= 8u;
+        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_chain, sl4[4u * T_SW], P[3], dummy)) fullmask |= 8u;
     }
 
     // ---- resolve (the tail of k_gather_pixel)

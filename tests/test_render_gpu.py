@@ -111,3 +111,22 @@ def test_tiled_path_overflow_falls_back(reflib):
         assert mx <= 1 and n <= 0.01 * 96 * 96
     paths = e.render_path_frames()
     assert paths["general"] >= 3 and paths["tiled"] <= 1, paths
+
+
+def test_tiled_diagnostics_and_kernel_times():
+    """amx_render_tiled_stats / amx_kernel_times: bin occupancy of a rendered batch and per-kernel device times."""
+    images = scenes.square_to_disc(128) if hasattr(scenes, "square_to_disc") else scenes.ellipses(128, 2, seed=5)
+    e = eng.Engine(0, seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=1000)
+    e.load_images(images)
+    e.step(8)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    e.kernel_times(True)
+    frames = e.render([f / 16.0 for f in range(16)])
+    kt = e.kernel_times(False)
+    assert frames.shape[0] == 16
+    assert kt[0]["frames"] == 16 and kt[1]["frames"] == 16 and kt[0]["launches"] == kt[1]["launches"] >= 2
+    assert kt[0]["ms"] > 0 and kt[1]["ms"] > 0
+    st = e.render_tiled_stats()
+    assert st["fallbacks"] == 0 and not st["blocked"]
+    assert 0 < st["max_bin"][0] <= 2560 and st["max_tile"] >= st["max_bin"][0]
+    assert e.render_path_frames() == dict(tiled=16, general=0)
