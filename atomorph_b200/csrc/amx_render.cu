@@ -833,8 +833,7 @@ struct TileCtx {
     uint32_t segstart[10];    // prefix sums of the nine segment lengths: tile-local record index -> segment
     uint32_t segfirst[9];     // global index of a segment's first record
     uint32_t novf;
-    uint32_t n_generic, n_ties;   // per-tile diagnostics, flushed with one atomic each
-    uint32_t pad[2];
+    uint32_t pad[4];
 };
 #define T_SMEM_REC   0u
 #define T_SMEM_ATOM  (T_SREC * 8u)
@@ -847,41 +846,51 @@ struct TileCtx {
 __device__ __forceinline__ uint32_t t_home(uint32_t meta) { return meta >> 16; }
 static_assert(T_NLEV == 8u, "one 16-byte load fetches the eight slots of a home");
 
-// Fold the records of home h (shared-memory coordinates) into the pixel it reaches with dy = 0 (Pa) and the one with
-// dy = 1 (Pb); DX selects the x weight.  Returns true when every slot of the home is taken (there may be overflow
-// records).  Slots 0 and 1 are folded branch-free by the whole warp, the others behind a vote.
+// Fold one record into the pixel it reaches with dy = 0 (Pa) and the one with dy = 1 (Pb); DX selects the x weight.
 template <bool SINGLE, bool COUNTED, int DX, bool HAS_A, bool HAS_B>
-__device__ __forceinline__ bool fold_home(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain,
-                                          const uint4 sl, TPart &Pa, TPart &Pb) {
-    const uint32_t slw[4] = {sl.x, sl.y, sl.z, sl.w};                     // the eight slots of the home
-    bool has = true;
+__device__ __forceinline__ void fold_rec(const uint2 r, bool has, uint32_t tag, TPart &Pa, TPart &Pb) {
+    const uint32_t fx = DX ? r.y : r.y ^ 0xffu;                               // DX ? x_fract : 255 - x_fract
+    const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
+    const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
+    const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
+    if (HAS_A) {
+        const uint32_t n = wx * (255u - yf);
+        Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n;
+        if (COUNTED) Pa.cnt += (n != 0u);
+        if (!SINGLE) { if (n) Pa.chain = merge_chain(Pa.chain, tag); }
+    }
+    if (HAS_B) {
+        const uint32_t n = wx * yf;
+        Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n;
+        if (COUNTED) Pb.cnt += (n != 0u);
+        if (!SINGLE) { if (n) Pb.chain = merge_chain(Pb.chain, tag); }
+    }
+}
+
+// Fold the records of the two homes of one home row that reach a thread's pixel column -- s0: home column lx + 1 (dx = 0),
+// s1: home column lx (dx = 1); each is the 16-byte word holding the home's eight slots -- into the pixel they reach with
+// dy = 0 (Pa) and the one with dy = 1 (Pb).  The two homes advance level by level TOGETHER (two independent load chains);
+// slots 0 and 1 are folded branch-free by the whole warp, the others behind one vote per level.  Returns true when every
+// slot of one of the homes is taken (there may be overflow records).
+template <bool SINGLE, bool COUNTED, bool HAS_A, bool HAS_B>
+__device__ __forceinline__ bool fold_row(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain,
+                                         const uint4 s0, const uint4 s1, TPart &Pa, TPart &Pb) {
+    const uint32_t w0[4] = {s0.x, s0.y, s0.z, s0.w}, w1[4] = {s1.x, s1.y, s1.z, s1.w};
+    bool has0 = true, has1 = true;
 #pragma unroll
     for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
-        const uint32_t idx = (lev & 1u) ? slw[lev >> 1] >> 16 : slw[lev >> 1] & 0xffffu;
-        has = idx != T_EMPTY;                                             // slots fill in order: empty from the first empty one on
-        if (lev >= 2u && !__any_sync(0xffffffffu, has)) break;
-        const uint32_t j = has ? idx : 0u;
-        const uint2 r = s_rec[j];
-        const uint32_t fx = DX ? r.y : r.y ^ 0xffu;                           // DX ? x_fract : 255 - x_fract
-        const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
-        const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
-        const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
-        uint32_t tag = 0u;
-        if (!SINGLE) tag = s_chain[j];
-        if (HAS_A) {
-            const uint32_t n = wx * (255u - yf);
-            Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n;
-            if (COUNTED) Pa.cnt += (n != 0u);
-            if (!SINGLE) { if (n) Pa.chain = merge_chain(Pa.chain, tag); }
-        }
-        if (HAS_B) {
-            const uint32_t n = wx * yf;
-            Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n;
-            if (COUNTED) Pb.cnt += (n != 0u);
-            if (!SINGLE) { if (n) Pb.chain = merge_chain(Pb.chain, tag); }
-        }
+        const uint32_t i0 = (lev & 1u) ? w0[lev >> 1] >> 16 : w0[lev >> 1] & 0xffffu;
+        const uint32_t i1 = (lev & 1u) ? w1[lev >> 1] >> 16 : w1[lev >> 1] & 0xffffu;
+        has0 = i0 != T_EMPTY; has1 = i1 != T_EMPTY;                          // slots fill in order: empty from the first empty one on
+        if (lev >= 2u && !__any_sync(0xffffffffu, has0 || has1)) break;
+        const uint32_t j0 = has0 ? i0 : 0u, j1 = has1 ? i1 : 0u;
+        const uint2 r0 = s_rec[j0], r1 = s_rec[j1];
+        uint32_t t0 = 0u, t1 = 0u;
+        if (!SINGLE) { t0 = s_chain[j0]; t1 = s_chain[j1]; }
+        fold_rec<SINGLE, COUNTED, 0, HAS_A, HAS_B>(r0, has0, t0, Pa, Pb);
+        fold_rec<SINGLE, COUNTED, 1, HAS_A, HAS_B>(r1, has1, t1, Pa, Pb);
     }
-    return has;
+    return has0 || has1;
 }
 
 // the ordered double replay of one pixel of a tile (local pixel lx, ly): ties, several blobs, overflowing homes
@@ -943,6 +952,12 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     const uint32_t tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y, slot = blockIdx.z;
     const uint32_t ntiles = bn.tiles_x * bn.tiles_y, tile = ty * bn.tiles_x + tx;
     const uint32_t y_frame = rb.f[slot].y;
+#ifdef T_PROFILE
+    long long t_prev = clock64();
+#define T_PHASE(k) do { if (tid == 0u) { const long long t_now = clock64(); atomicAdd((unsigned long long *) (bn.flag + 8) + (k), (unsigned long long) (t_now - t_prev)); t_prev = t_now; } } while (0)
+#else
+#define T_PHASE(k) do { } while (0)
+#endif
 
     // the nine segments: 0..3 own bins; 4, 5 western neighbour (last column, corner); 6, 7 northern one (last row, corner);
     // 8 north-western one (corner)
@@ -974,10 +989,11 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             atomicOr(bn.flag, 1u);
             for (uint32_t s = 1; s <= 9u; ++s) cx->segstart[s] = min(cx->segstart[s], T_SREC);
         }
-        cx->novf = 0u; cx->n_generic = 0u; cx->n_ties = 0u;
+        cx->novf = 0u;
     }
     __syncthreads();
     const uint32_t m = cx->segstart[9];
+    T_PHASE(0);
 
     const uint32_t lx = tid & 31u, band = tid >> 5;
     const uint32_t px = tx * T_TILE + lx, py0 = ty * T_TILE + band * 4u;
@@ -1003,8 +1019,8 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         for (uint32_t i = tid; i < n; i += 256u) {
             __pipeline_memcpy_async(&s_rec[j0 + i], &bn.rec[(size_t) first + i], 8);
             __pipeline_memcpy_async(&s_atom[j0 + i], &bn.atom[(size_t) first + i], 4);
-            if (!SINGLE) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
         }
+        if (!SINGLE) for (uint32_t i = tid; i < n; i += 256u) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -1021,6 +1037,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     }
     __syncthreads();
 
+    T_PHASE(1);
     // ---- order by home: store-and-check rounds (a thread walks only the records it still has to place)
     const uint32_t nq = (m + 255u) >> 8;                         // records per thread, <= 16
     uint32_t act = nq >= 1u ? (1u << (nq - 1u)) - 1u : 0u;      // q < nq - 1: always a record
@@ -1042,6 +1059,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         if (k < T_OVF) s_ovf[k] = (uint16_t) (tid + (((uint32_t) __ffs((int) a) - 1u) << 8));
     }
     __syncthreads();
+    T_PHASE(2);
     if (tid == 0u && cx->novf > 0u) {
         if (cx->novf > bn.flag[6]) atomicMax(&bn.flag[6], cx->novf);
         if (cx->novf > T_OVF) atomicOr(bn.flag, 1u);
@@ -1074,17 +1092,14 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         TPart dummy;
         dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = 0u; dummy.chain = PART_NONE;
         // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
-        if (fold_home<SINGLE, COUNTED, 0, false, true>(s_rec, s_chain, sl4[1], dummy, P[0])) fullmask |= 1u;
-        if (fold_home<SINGLE, COUNTED, 1, false, true>(s_rec, s_chain, sl4[0], dummy, P[0])) fullmask |= 1u;
+        if (fold_row<SINGLE, COUNTED, false, true>(s_rec, s_chain, sl4[1], sl4[0], dummy, P[0])) fullmask |= 1u;
 #pragma unroll
-        for (uint32_t hr = 1; hr < 4u; ++hr) {
-            if (fold_home<SINGLE, COUNTED, 0, true, true>(s_rec, s_chain, sl4[hr * T_SW + 1u], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
-            if (fold_home<SINGLE, COUNTED, 1, true, true>(s_rec, s_chain, sl4[hr * T_SW], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
-        }
-        if (fold_home<SINGLE, COUNTED, 0, true, false>(s_rec, s_chain, sl4[4u * T_SW + 1u], P[3], dummy)) fullmask |= 8u;
-        if (fold_home<SINGLE, COUNTED, 1, true, false>(s_rec, s_chain, sl4[4u * T_SW], P[3], dummy)) fullmask |= 8u;
+        for (uint32_t hr = 1; hr < 4u; ++hr)
+            if (fold_row<SINGLE, COUNTED, true, true>(s_rec, s_chain, sl4[hr * T_SW + 1u], sl4[hr * T_SW], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
+        if (fold_row<SINGLE, COUNTED, true, false>(s_rec, s_chain, sl4[4u * T_SW + 1u], sl4[4u * T_SW], P[3], dummy)) fullmask |= 8u;
     }
 
+    T_PHASE(3);
     // ---- resolve (the tail of k_gather_pixel)
 #pragma unroll
     for (uint32_t p = 0; p < 4u; ++p) {
@@ -1127,6 +1142,11 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         outf[i] = resolve_generic_tile<SINGLE>(smem, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
                                                y_frame, lx, band * 4u + p, bgc);
     }
+    T_PHASE(4);
+#ifdef T_PROFILE
+    if (tid == 0u) atomicAdd((unsigned long long *) (bn.flag + 8) + 5, 1ull);
+#endif
+#undef T_PHASE
 }
 
 // gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
@@ -1681,14 +1701,14 @@ static bool ensure_bins(Engine *E) {
     const size_t cnt_bytes = (size_t) 2 * RBATCH * ntiles * 4 * sizeof(uint32_t);
     if (!dev_alloc(E, (void **) &E->tb_rec, nrec * 8, "bin records") || !dev_alloc(E, (void **) &E->tb_atom, nrec * 4, "bin atoms") ||
         (want_chain && !dev_alloc(E, (void **) &E->tb_chain, nrec * 4, "bin chains")) ||
-        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4, "bin flag")) {
+        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4 + 8 * 8, "bin flag")) {
         E->err.clear();                                                   // not an error: the general path needs none of this
         dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
         E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr;
         return false;
     }
     cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
-    cudaMemsetAsync(E->tb_flag, 0, 8 * 4, E->stream);
+    cudaMemsetAsync(E->tb_flag, 0, 8 * 4 + 8 * 8, E->stream);
     E->tb_tiles_x = tx; E->tb_tiles_y = ty; E->tb_has_chain = want_chain;
     E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
     return true;
@@ -2078,6 +2098,14 @@ int amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]) {
 }
 int amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]) {
     if (!ctx || !stats8) return AMX_ERR_ARG;
+#ifdef T_PROFILE
+    if (ctx->e.tb_flag) {       // debug build: cycles per k_tile phase summed over the CTAs (thread 0's view)
+        unsigned long long ph[8];
+        cudaMemcpy(ph, ctx->e.tb_flag + 8, sizeof ph, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[T_PROFILE] CTAs %llu; cycles per CTA: setup %.0f, staging %.0f, rounds %.0f, fold %.0f, resolve %.0f\n", ph[5],
+                (double) ph[0] / ph[5], (double) ph[1] / ph[5], (double) ph[2] / ph[5], (double) ph[3] / ph[5], (double) ph[4] / ph[5]);
+    }
+#endif
     for (int k = 0; k < 6; ++k) stats8[k] = ctx->e.tb_demand[k];
     stats8[6] = ctx->e.tiled_fallbacks; stats8[7] = ctx->e.tiled_blocked ? 1 : 0;
     return AMX_OK;
