@@ -824,7 +824,6 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
         }
     }
 }
-
 struct TPart { uint32_t R, G, B, A, N, cnt, chain; };
 static_assert(4u * T_NLEV <= MAXK, "the fast path folds at most MAXK records into a pixel (32-bit sums)");
 

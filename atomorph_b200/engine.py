@@ -224,9 +224,12 @@ class Engine:
         widths = np.array([c["words"].shape[1] for c in chains], dtype=np.uint64)
         ms = np.array([c.get("max_surface", c["words"].shape[1]) for c in chains], dtype=np.uint64)
         h = chains[0]["words"].shape[0] if n else 0
-        words = (np.concatenate([np.ascontiguousarray(c["words"], dtype=np.uint64).reshape(-1) for c in chains])
-                 if n else np.zeros(0, dtype=np.uint64))
-        words = np.ascontiguousarray(words)
+        if n == 1 and chains[0]["words"].dtype == np.uint64 and chains[0]["words"].flags["C_CONTIGUOUS"]:
+            words = chains[0]["words"].reshape(-1)               # no host copy (the caller's buffer may be pinned)
+        else:
+            words = (np.concatenate([np.ascontiguousarray(c["words"], dtype=np.uint64).reshape(-1) for c in chains])
+                     if n else np.zeros(0, dtype=np.uint64))
+            words = np.ascontiguousarray(words)
         self._ck(self.L.amx_import_chains(self.h, n, _p(keys), _p(widths), _p(ms), h, _p(words)), "import_chains")
 
     def table_device_ptr(self, column):

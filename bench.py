@@ -291,6 +291,11 @@ def run_b200(args):
 
     # e2e through the C-ABI with host buffers: upload the table (H2D), render, copy frames back (D2H)
     chain_words = e.chains()
+    pinned_in = []
+    for c in chain_words:                          # the step's inputs live in pinned host memory
+        t = torch.from_numpy(np.ascontiguousarray(c["words"]).view(np.int64)).pin_memory()
+        pinned_in.append(t)
+        c["words"] = t.numpy().view(np.uint64)
     host_out = torch.empty((F, size, size), dtype=torch.int32).pin_memory()
     h2d = sum(c["words"].nbytes for c in chain_words)
     d2h = F * P * 4
