@@ -77,6 +77,8 @@ def build_oracle():
         _run(["make", "-C", odir, "port"])
     if os.path.isdir("/root/reference"):
         _run(["make", "-C", odir, "ref"])
+        if os.path.exists(OUT):
+            _run(["make", "-C", odir, "demo"])       # the reference's CLI against both libraries (tests/test_demo_gpu.py)
 
 
 def build_all(verbose=False, force=False):
