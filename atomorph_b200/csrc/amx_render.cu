@@ -708,31 +708,24 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // reads nine bins: its own four, classes 1 and 3 of its western neighbour, 2 and 3 of the northern one and 3 of the
 // north-western one.  Every record is written once.
 //
-// Ordering by home inside the tile without atomics (ATOMS is 2 cycles per lane): every home has T_NLEV slots; in round
-// r all still unplaced records STORE their index into slot r of their home, after a barrier the one whose index
-// survived owns the slot and the others go on to round r + 1.  Records left after T_NLEV rounds go to a short overflow
-// list.  Pixels then fold the slots of the homes that reach them into exact integer sums exactly like
-// k_gather_pixel; ties, several blobs at a pixel, homes with overflow records take the ordered double replay
-// (resolve_contributions).
+// Ordering by home inside the tile: a counting sort in shared memory -- one shared-memory atomicAdd per record on its home's
+// counter hands out the record's rank, an in-place exclusive scan of the 33 x 33 counters gives the homes' offsets, and the
+// record indices are scattered to offset + rank.  (A first version avoided shared-memory atomics with store-and-check rounds
+// over eight slots per home; it needed 2.4 x the cycles for the ordering and made the fold slower, see DESIGN.md.)  The two
+// homes of a home row that reach a pixel column are neighbours, so their records are ONE contiguous range of the sorted
+// array.  Pixels fold the records of the homes that reach them into exact integer sums exactly like k_gather_pixel; ties,
+// several blobs at a pixel and pixels with more than MAXK records take the ordered double replay (resolve_contributions).
 //
 // Capacity: a tile takes T_SREC records per frame (its nine bins together: 3 atoms per pixel; an interior bin holds 2.5).
-// A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general path above (the results of the two paths
-// are identical, both being exact).
+// A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general
+// path above (the results of the two paths are identical, both being exact).
 #ifndef T_CTAS
 #define T_CTAS 4                        // resident k_tile CTAs per SM the single-chain instance is compiled for (64 registers)
 #endif
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
-#define T_NLEV   8u                     // direct record slots per home
-#if T_CTAS >= 4
-#define T_SREC   3072u                  // (4 CTAs of 55 KB per SM)
+#define T_SREC   3072u                  // (54 KB of shared memory per CTA: 4 CTAs per SM)
 #define T_CAP0   2560u
-#else
-#define T_SREC   4096u                  // (3 CTAs of 72 KB per SM)
-#define T_CAP0   3584u
-#endif
-#define T_OVF    512u                   // records beyond the T_NLEV-th of their home
-#define T_EMPTY  0xffffu
 // T_SREC: records a tile takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities per class (interior / last column or row / corner)
 #define T_CAP1   192u
 #define T_CAP3   64u
@@ -746,7 +739,7 @@ struct Bins {
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
     uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
     uint32_t *flag;       // [0] != 0: something overflowed, the frames must be rendered again by the general path;
-                          // [1..4] largest bin count seen per class, [5] largest tile total, [6] longest overflow list (diagnostics)
+                          // [1..4] largest bin count seen per class, [5] largest tile total (diagnostics)
     uint32_t  tiles_x, tiles_y;
 };
 __device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls ? T_CAP0 + (cls - 1u) * T_CAP1 : 0u; }
@@ -825,71 +818,60 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
     }
 }
 struct TPart { uint32_t R, G, B, A, N, cnt, chain; };
-static_assert(4u * T_NLEV <= MAXK, "the fast path folds at most MAXK records into a pixel (32-bit sums)");
 
 // what the out-of-line replay needs to find the records of a pixel again (lives in shared memory)
 struct TileCtx {
     uint32_t segstart[10];    // prefix sums of the nine segment lengths: tile-local record index -> segment
     uint32_t segfirst[9];     // global index of a segment's first record
-    uint32_t novf;
+    uint32_t wsum[8];         // per-warp totals of the offset scan
     uint32_t pad[4];
 };
 #define T_SMEM_REC   0u
 #define T_SMEM_ATOM  (T_SREC * 8u)
 #define T_SMEM_SLOT  (T_SMEM_ATOM + T_SREC * 4u)
-#define T_SMEM_OVF   (T_SMEM_SLOT + T_SW * T_SW * T_NLEV * 2u)      // slots: [home][level], 16 bytes per home
-#define T_SMEM_CTX   (T_SMEM_OVF + T_OVF * 2u)
+#define T_SORT_OFF_BYTES 4368u          // u32 offsets [33 * 33 + 3]
+#define T_SMEM_CTX   (T_SMEM_SLOT + T_SORT_OFF_BYTES + 2u * T_SREC * 2u)   // then u16 ranks [T_SREC] and u16 sorted indices [T_SREC]
 #define T_SMEM_CHAIN (T_SMEM_CTX + (uint32_t) sizeof(TileCtx))
 #define T_SMEM_BYTES(SINGLE) (T_SMEM_CHAIN + ((SINGLE) ? 0u : T_SREC * 2u))
 
 __device__ __forceinline__ uint32_t t_home(uint32_t meta) { return meta >> 16; }
-static_assert(T_NLEV == 8u, "one 16-byte load fetches the eight slots of a home");
 
-// Fold one record into the pixel it reaches with dy = 0 (Pa) and the one with dy = 1 (Pb); DX selects the x weight.
-template <bool SINGLE, bool COUNTED, int DX, bool HAS_A, bool HAS_B>
-__device__ __forceinline__ void fold_rec(const uint2 r, bool has, uint32_t tag, TPart &Pa, TPart &Pb) {
-    const uint32_t fx = DX ? r.y : r.y ^ 0xffu;                               // DX ? x_fract : 255 - x_fract
-    const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
-    const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
-    const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
-    if (HAS_A) {
-        const uint32_t n = wx * (255u - yf);
-        Pa.R += cr * n; Pa.G += cg * n; Pa.B += cb * n; Pa.A += ca * n; Pa.N += n;
-        if (COUNTED) Pa.cnt += (n != 0u);
-        if (!SINGLE) { if (n) Pa.chain = merge_chain(Pa.chain, tag); }
-    }
-    if (HAS_B) {
-        const uint32_t n = wx * yf;
-        Pb.R += cr * n; Pb.G += cg * n; Pb.B += cb * n; Pb.A += ca * n; Pb.N += n;
-        if (COUNTED) Pb.cnt += (n != 0u);
-        if (!SINGLE) { if (n) Pb.chain = merge_chain(Pb.chain, tag); }
-    }
-}
-
-// Fold the records of the two homes of one home row that reach a thread's pixel column -- s0: home column lx + 1 (dx = 0),
-// s1: home column lx (dx = 1); each is the 16-byte word holding the home's eight slots -- into the pixel they reach with
-// dy = 0 (Pa) and the one with dy = 1 (Pb).  The two homes advance level by level TOGETHER (two independent load chains);
-// slots 0 and 1 are folded branch-free by the whole warp, the others behind one vote per level.  Returns true when every
-// slot of one of the homes is taken (there may be overflow records).
+// Sorted layout: s_sorted holds the record indices ordered by home, s_off[h] the position of home h's first record.
+// The two homes of a home row that reach a thread's pixel column are neighbours (h0: column lx, dx = 1; h0 + 1: column
+// lx + 1, dx = 0), so their records form ONE contiguous range, walked by one loop (the first two iterations by the whole
+// warp, the rest behind a vote).  Returns the number of records of the two homes.
 template <bool SINGLE, bool COUNTED, bool HAS_A, bool HAS_B>
-__device__ __forceinline__ bool fold_row(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain,
-                                         const uint4 s0, const uint4 s1, TPart &Pa, TPart &Pb) {
-    const uint32_t w0[4] = {s0.x, s0.y, s0.z, s0.w}, w1[4] = {s1.x, s1.y, s1.z, s1.w};
-    bool has0 = true, has1 = true;
-#pragma unroll
-    for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
-        const uint32_t i0 = (lev & 1u) ? w0[lev >> 1] >> 16 : w0[lev >> 1] & 0xffffu;
-        const uint32_t i1 = (lev & 1u) ? w1[lev >> 1] >> 16 : w1[lev >> 1] & 0xffffu;
-        has0 = i0 != T_EMPTY; has1 = i1 != T_EMPTY;                          // slots fill in order: empty from the first empty one on
-        if (lev >= 2u && !__any_sync(0xffffffffu, has0 || has1)) break;
-        const uint32_t j0 = has0 ? i0 : 0u, j1 = has1 ? i1 : 0u;
-        const uint2 r0 = s_rec[j0], r1 = s_rec[j1];
-        uint32_t t0 = 0u, t1 = 0u;
-        if (!SINGLE) { t0 = s_chain[j0]; t1 = s_chain[j1]; }
-        fold_rec<SINGLE, COUNTED, 0, HAS_A, HAS_B>(r0, has0, t0, Pa, Pb);
-        fold_rec<SINGLE, COUNTED, 1, HAS_A, HAS_B>(r1, has1, t1, Pa, Pb);
+__device__ __forceinline__ uint32_t fold_row_sorted(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain, const uint16_t *__restrict__ s_sorted,
+                                                    const uint32_t *__restrict__ s_off, uint32_t h0, TPart &Pa, TPart &Pb) {
+    const uint32_t a = s_off[h0], mid = s_off[h0 + 1u], b = s_off[h0 + 2u];
+    const uint32_t n = b - a, nn = min(n, (uint32_t) MAXK + 1u);           // beyond MAXK the pixel takes the replay anyway
+    for (uint32_t it = 0; ; ++it) {
+        const bool has = it < nn;
+        if (it >= 2u && !__any_sync(0xffffffffu, has)) break;
+        const uint32_t p = a + it;
+        uint32_t j = 0u;
+        if (has) j = s_sorted[p];
+        const uint2 r = s_rec[j];
+        const uint32_t fx = p < mid ? r.y : r.y ^ 0xffu;                     // dx = 1 ? x_fract : 255 - x_fract
+        const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
+        const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
+        const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
+        uint32_t tag = 0u;
+        if (!SINGLE) tag = s_chain[j];
+        if (HAS_A) {
+            const uint32_t w = wx * (255u - yf);
+            Pa.R += cr * w; Pa.G += cg * w; Pa.B += cb * w; Pa.A += ca * w; Pa.N += w;
+            if (COUNTED) Pa.cnt += (w != 0u);
+            if (!SINGLE) { if (w) Pa.chain = merge_chain(Pa.chain, tag); }
+        }
+        if (HAS_B) {
+            const uint32_t w = wx * yf;
+            Pb.R += cr * w; Pb.G += cg * w; Pb.B += cb * w; Pb.A += ca * w; Pb.N += w;
+            if (COUNTED) Pb.cnt += (w != 0u);
+            if (!SINGLE) { if (w) Pb.chain = merge_chain(Pb.chain, tag); }
+        }
     }
-    return has0 || has1;
+    return n;
 }
 
 // the ordered double replay of one pixel of a tile (local pixel lx, ly): ties, several blobs, overflowing homes
@@ -898,9 +880,6 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
                                                       const int32_t *__restrict__ boc, const uint32_t *__restrict__ blob_avg,
                                                       const uint32_t *__restrict__ blob_distinct, uint32_t y_frame, uint32_t lx, uint32_t ly, uint32_t bgc) {
     const uint2 *s_rec = (const uint2 *) (smem + T_SMEM_REC);
-    const uint16_t *s_slot = (const uint16_t *) (smem + T_SMEM_SLOT);
-    const uint16_t *s_ovf = (const uint16_t *) (smem + T_SMEM_OVF);
-    const TileCtx *cx = (const TileCtx *) (smem + T_SMEM_CTX);
     const uint32_t *s_atom = (const uint32_t *) (smem + T_SMEM_ATOM);
     const RConst rc = *rcp;
     auto visit = [&](auto f) {
@@ -914,16 +893,9 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
                 const uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
                 if (n) f(s_atom[j], r.x, n, 0u);
             };
-            uint32_t lev = 0;
-            for (; lev < T_NLEV; ++lev) {
-                const uint32_t idx = s_slot[h * T_NLEV + lev];
-                if (idx == T_EMPTY) break;
-                emit(idx);
-            }
-            if (lev == T_NLEV) {
-                const uint32_t nov = min(cx->novf, T_OVF);
-                for (uint32_t q = 0; q < nov; ++q) { const uint32_t j = s_ovf[q]; if (t_home(s_rec[j].y) == h) emit(j); }
-            }
+            const uint32_t *s_off = (const uint32_t *) (smem + T_SMEM_SLOT);
+            const uint16_t *s_sorted = (const uint16_t *) (smem + T_SMEM_SLOT + T_SORT_OFF_BYTES) + T_SREC;
+            for (uint32_t p = s_off[h], e = s_off[h + 1u]; p < e; ++p) emit(s_sorted[p]);
         }
     };
     Over ov;
@@ -943,8 +915,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     extern __shared__ __align__(16) unsigned char smem[];
     uint2 *s_rec = (uint2 *) (smem + T_SMEM_REC);
     uint32_t *s_atom = (uint32_t *) (smem + T_SMEM_ATOM);
-    uint16_t *s_slot = (uint16_t *) (smem + T_SMEM_SLOT);
-    uint16_t *s_ovf = (uint16_t *) (smem + T_SMEM_OVF);
     TileCtx *cx = (TileCtx *) (smem + T_SMEM_CTX);
     uint16_t *s_chain = (uint16_t *) (smem + T_SMEM_CHAIN);
 
@@ -976,7 +946,10 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     }
     // this tile's counters in the OTHER counter buffer (dirty from the previous batch) are cleared for the next batch
     if (tid >= 32u && tid < 36u) bn.cnt_other[((size_t) slot * ntiles + tile) * 4u + (tid - 32u)] = 0u;
-    for (uint32_t w = tid; w < T_SW * T_SW; w += 256u) ((uint4 *) s_slot)[w] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    uint32_t *s_off = (uint32_t *) (smem + T_SMEM_SLOT);
+    uint16_t *s_rank = (uint16_t *) (smem + T_SMEM_SLOT + T_SORT_OFF_BYTES);
+    uint16_t *s_sorted = s_rank + T_SREC;
+    for (uint32_t w = tid; w < T_SW * T_SW + 3u; w += 256u) s_off[w] = 0u;
     __syncthreads();
     if (tid == 0u) {
         uint32_t acc = 0;
@@ -988,7 +961,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             atomicOr(bn.flag, 1u);
             for (uint32_t s = 1; s <= 9u; ++s) cx->segstart[s] = min(cx->segstart[s], T_SREC);
         }
-        cx->novf = 0u;
     }
     __syncthreads();
     const uint32_t m = cx->segstart[9];
@@ -1037,33 +1009,29 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     __syncthreads();
 
     T_PHASE(1);
-    // ---- order by home: store-and-check rounds (a thread walks only the records it still has to place)
-    const uint32_t nq = (m + 255u) >> 8;                         // records per thread, <= 16
-    uint32_t act = nq >= 1u ? (1u << (nq - 1u)) - 1u : 0u;      // q < nq - 1: always a record
-    if (nq >= 1u && tid + ((nq - 1u) << 8) < m) act |= 1u << (nq - 1u);
-    for (uint32_t lev = 0; lev < T_NLEV; ++lev) {
-        uint16_t *sl = s_slot + lev;
-        for (uint32_t a = act; a; a &= a - 1u) {
-            const uint32_t j = tid + (((uint32_t) __ffs((int) a) - 1u) << 8);
-            sl[t_home(s_rec[j].y) * T_NLEV] = (uint16_t) j;
-        }
-        if (!__syncthreads_or(act != 0u)) break;                 // nobody stored anything in this round
-        for (uint32_t a = act; a; a &= a - 1u) {
-            const uint32_t q = (uint32_t) __ffs((int) a) - 1u, j = tid + (q << 8);
-            if (sl[t_home(s_rec[j].y) * T_NLEV] == j) act &= ~(1u << q);
-        }
-    }
-    for (uint32_t a = act; a; a &= a - 1u) {
-        const uint32_t k = atomicAdd(&cx->novf, 1u);
-        if (k < T_OVF) s_ovf[k] = (uint16_t) (tid + (((uint32_t) __ffs((int) a) - 1u) << 8));
+    // ---- order by home: counting sort in shared memory (count with one atomic per record, offset scan, scatter of the indices)
+    for (uint32_t j = tid; j < m; j += 256u) s_rank[j] = (uint16_t) atomicAdd(&s_off[t_home(s_rec[j].y)], 1u);
+    __syncthreads();
+    {
+        // exclusive scan of the 1089 counts in place: thread t owns homes [5t, 5t + 5)
+        const uint32_t base = tid * 5u, lane = tid & 31u, warp = tid >> 5;
+        uint32_t c[5], sum = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 5u; ++k) { c[k] = base + k < T_SW * T_SW ? s_off[base + k] : 0u; sum += c[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31u) cx->wsum[warp] = incl;
+        __syncthreads();
+        uint32_t excl = incl - sum;
+        for (uint32_t w = 0; w < warp; ++w) excl += cx->wsum[w];
+#pragma unroll
+        for (uint32_t k = 0; k < 5u; ++k) if (base + k < T_SW * T_SW + 3u) { s_off[base + k] = excl; excl += c[k]; }   // [1089 .. 1091] = m: sentinels
     }
     __syncthreads();
+    for (uint32_t j = tid; j < m; j += 256u) s_sorted[s_off[t_home(s_rec[j].y)] + s_rank[j]] = (uint16_t) j;
+    __syncthreads();
     T_PHASE(2);
-    if (tid == 0u && cx->novf > 0u) {
-        if (cx->novf > bn.flag[6]) atomicMax(&bn.flag[6], cx->novf);
-        if (cx->novf > T_OVF) atomicOr(bn.flag, 1u);
-    }
-
     // ---- fold: home rows band*4 .. band*4 + 4 (shared-memory coordinates), home columns lx + 1 (dx = 0) and lx (dx = 1)
     TPart P[4];
 #pragma unroll
@@ -1071,11 +1039,10 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     uint32_t fullmask = 0;
     {
         const uint32_t hb = band * 4u * T_SW + lx;
-        const uint4 *sl4 = (const uint4 *) s_slot + hb;                           // [home]: the eight slots of a home in 16 bytes
         // nothing at any of the homes that reach the warp's 32 x 4 pixels (sparse scenes): background only
         bool any0 = false;
 #pragma unroll
-        for (uint32_t hr = 0; hr < 5u; ++hr) any0 = any0 || s_slot[(hb + hr * T_SW) * T_NLEV] != T_EMPTY || s_slot[(hb + hr * T_SW + 1u) * T_NLEV] != T_EMPTY;
+        for (uint32_t hr = 0; hr < 5u; ++hr) any0 = any0 || s_off[hb + hr * T_SW + 2u] != s_off[hb + hr * T_SW];
         if (!__any_sync(0xffffffffu, any0)) {
             if (px < rc.width) {
 #pragma unroll
@@ -1090,12 +1057,15 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         }
         TPart dummy;
         dummy.R = dummy.G = dummy.B = dummy.A = dummy.N = dummy.cnt = 0u; dummy.chain = PART_NONE;
-        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only
-        if (fold_row<SINGLE, COUNTED, false, true>(s_rec, s_chain, sl4[1], sl4[0], dummy, P[0])) fullmask |= 1u;
+        // home row 0 reaches pixel row 0 with dy = 1 only; rows 1..3 reach two pixel rows; row 4 reaches pixel row 3 with dy = 0 only.
+        // A pixel that more than MAXK records reach (32-bit sums) takes the replay.
+        uint32_t vis[5];
+        vis[0] = fold_row_sorted<SINGLE, COUNTED, false, true>(s_rec, s_chain, s_sorted, s_off, hb, dummy, P[0]);
 #pragma unroll
-        for (uint32_t hr = 1; hr < 4u; ++hr)
-            if (fold_row<SINGLE, COUNTED, true, true>(s_rec, s_chain, sl4[hr * T_SW + 1u], sl4[hr * T_SW], P[hr - 1u], P[hr])) fullmask |= 3u << (hr - 1u);
-        if (fold_row<SINGLE, COUNTED, true, false>(s_rec, s_chain, sl4[4u * T_SW + 1u], sl4[4u * T_SW], P[3], dummy)) fullmask |= 8u;
+        for (uint32_t hr = 1; hr < 4u; ++hr) vis[hr] = fold_row_sorted<SINGLE, COUNTED, true, true>(s_rec, s_chain, s_sorted, s_off, hb + hr * T_SW, P[hr - 1u], P[hr]);
+        vis[4] = fold_row_sorted<SINGLE, COUNTED, true, false>(s_rec, s_chain, s_sorted, s_off, hb + 4u * T_SW, P[3], dummy);
+#pragma unroll
+        for (uint32_t p = 0; p < 4u; ++p) if (vis[p] + vis[p + 1u] > MAXK) fullmask |= 1u << p;
     }
 
     T_PHASE(3);

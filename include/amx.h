@@ -150,7 +150,7 @@ int  amx_kernel_times(amx_ctx *ctx, int enable, double ms2[2], uint64_t launches
  * A-buffer path (feather, per-blob fetch, or more than 3.5 atoms per pixel over a 32x32 tile); both are exact */
 int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
 /* tiled-path diagnostics: [0..3] largest record count seen in a bin of class interior / last column / last row / corner,
- * [4] largest record total of a tile, [5] longest per-tile overflow list, [6] render calls repeated on the general path,
+ * [4] largest record total of a tile, [5] unused (0), [6] render calls repeated on the general path,
  * [7] 1 while the tiled path is blocked for the current table */
 int  amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]);
 /* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
