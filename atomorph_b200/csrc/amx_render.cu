@@ -801,7 +801,7 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
             const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
             const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
             who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[(size_t) s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
+            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
         }
 #pragma unroll
         for (uint32_t s = 0; s < RBATCH; ++s) {
@@ -809,8 +809,11 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
             const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));      // the leader's claim
             if (key[s] == T_KEY_NONE) continue;
             const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
-            if (pos >= bin_cap(cls)) continue;                    // dropped: k_tile sees the counter beyond the capacity and raises the flag
-            const size_t o = ((size_t) s * ntiles + (key[s] >> 2)) * T_STRIDE + bin_off(cls) + pos;
+            // capacity and offset of the four bins of a tile, 16 bits each, looked up with one shift
+            const uint32_t cap = (uint32_t) ((((unsigned long long) T_CAP3 << 48) | ((unsigned long long) T_CAP1 << 32) | ((unsigned long long) T_CAP1 << 16) | T_CAP0) >> (cls * 16u)) & 0xffffu;
+            const uint32_t off = (uint32_t) ((((unsigned long long) (T_CAP0 + 2u * T_CAP1) << 48) | ((unsigned long long) (T_CAP0 + T_CAP1) << 32) | ((unsigned long long) T_CAP0 << 16)) >> (cls * 16u)) & 0xffffu;
+            if (pos >= cap) continue;                             // dropped: k_tile sees the counter beyond the capacity and raises the flag
+            const uint32_t o = (s * ntiles + (key[s] >> 2)) * T_STRIDE + off + pos;      // < 2^32 records (ensure_bins)
             bn.rec[o] = make_uint2(col[s], meta[s]);
             bn.atom[o] = raw.atom;
             if (bn.chain) bn.chain[o] = raw.chain;
