@@ -10,8 +10,9 @@
  * colours are within the threshold (color_distance, color.h:17-24) -- a deterministic stand-in
  * for the reference's RNG-dependent merge order, compared statistically only.
  *
- * Algorithm: lock-free union-find on the pixel grid (label = smaller root wins through
- * atomicMin), then path compression; the root of a component is its smallest canvas index
+ * Algorithm: lock-free union-find (label = smaller root wins through atomicMin), first per
+ * 32x32-pixel tile in shared memory on tile-local indices, then across the tile borders in
+ * global memory, then path compression; the root of a component is its smallest canvas index
  * (= smallest xy2pos, the canonical label of SURVEY.md M2).  Statistics are exact integer
  * sums (count, x, y, r, g, b, a) reduced per warp with __match_any_sync before one atomic per
  * distinct root, then divided in double -- the reference reaches the same means through a
@@ -60,6 +61,84 @@ k_ccl_merge(const uint8_t *__restrict__ present, const uint32_t *__restrict__ st
     if (y > 0 && present[i - cw] && (!use_threshold || color_distance(stored[i], stored[i - cw]) <= threshold)) uf_union(lab, (uint32_t) i, (uint32_t) (i - cw));
 }
 
+// Tiled labelling: one CTA per 32x32-pixel tile runs the same union-find on TILE-LOCAL indices in shared memory (the
+// contention of a large component stays on chip), flattens it and writes, for every pixel, the canvas index of the
+// smallest pixel of its tile-local component -- the tile-local row-major order equals the canvas order inside a tile, so
+// that is the component's canonical label.  Only the pixels in the first column / row of a tile then need a global union
+// with their left / upper neighbour (k_ccl_border): 1/16 of the global atomics of the one-pass version.
+#define CCL_T 32u
+__device__ __forceinline__ uint32_t suf_find(const uint32_t *lab, uint32_t i) {
+    uint32_t p = lab[i];
+    while (p != i) { i = p; p = lab[i]; }
+    return i;
+}
+__device__ __forceinline__ void suf_union(uint32_t *lab, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = suf_find(lab, a);
+        b = suf_find(lab, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_tile(const uint8_t *__restrict__ present, const uint32_t *__restrict__ stored, uint32_t *__restrict__ lab, uint32_t cw, uint32_t ch,
+           int use_threshold, double threshold, int merge) {
+    __shared__ uint32_t s_lab[CCL_T * CCL_T];
+    __shared__ uint32_t s_col[CCL_T * CCL_T];
+    __shared__ uint8_t s_pre[CCL_T * CCL_T];
+    const uint32_t x0 = blockIdx.x * CCL_T, y0 = blockIdx.y * CCL_T;
+    for (uint32_t l = threadIdx.x; l < CCL_T * CCL_T; l += 256u) {
+        const uint32_t x = x0 + (l & 31u), y = y0 + (l >> 5);
+        const bool in = x < cw && y < ch;
+        const size_t g = (size_t) y * cw + x;
+        const bool pr = in && present[g];
+        s_pre[l] = pr ? 1 : 0;
+        s_col[l] = pr ? stored[g] : 0u;
+        s_lab[l] = l;
+    }
+    __syncthreads();
+    if (merge) {
+        for (uint32_t l = threadIdx.x; l < CCL_T * CCL_T; l += 256u) {
+            if (!s_pre[l]) continue;
+            if ((l & 31u) && s_pre[l - 1u] && (!use_threshold || color_distance(s_col[l], s_col[l - 1u]) <= threshold)) suf_union(s_lab, l, l - 1u);
+            if ((l >> 5) && s_pre[l - CCL_T] && (!use_threshold || color_distance(s_col[l], s_col[l - CCL_T]) <= threshold)) suf_union(s_lab, l, l - CCL_T);
+        }
+        __syncthreads();
+    }
+    for (uint32_t l = threadIdx.x; l < CCL_T * CCL_T; l += 256u) {
+        const uint32_t x = x0 + (l & 31u), y = y0 + (l >> 5);
+        if (x >= cw || y >= ch) continue;
+        const size_t g = (size_t) y * cw + x;
+        if (!s_pre[l]) { lab[g] = 0xffffffffu; continue; }
+        const uint32_t r = suf_find(s_lab, l);
+        lab[g] = (uint32_t) ((size_t) (y0 + (r >> 5)) * cw + x0 + (r & 31u));
+    }
+}
+
+// global unions across tile borders: pixels in the first column / row of a tile with their left / upper neighbour
+__global__ void __launch_bounds__(256)
+k_ccl_border(const uint8_t *__restrict__ present, const uint32_t *__restrict__ stored, uint32_t *__restrict__ lab, uint32_t cw, uint32_t ch,
+             int use_threshold, double threshold) {
+    // thread -> (tile row or column line, position along it): first the vertical border lines (x % 32 == 0, x > 0), then the horizontal ones
+    const uint32_t nvx = (cw - 1u) / CCL_T, nhy = (ch - 1u) / CCL_T;               // number of interior border lines
+    const size_t nv = (size_t) nvx * ch, nh = (size_t) nhy * cw;
+    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nv) {
+        const uint32_t x = (uint32_t) (t / ch + 1u) * CCL_T, y = (uint32_t) (t % ch);
+        const size_t g = (size_t) y * cw + x;
+        if (present[g] && present[g - 1] && (!use_threshold || color_distance(stored[g], stored[g - 1]) <= threshold)) uf_union(lab, (uint32_t) g, (uint32_t) g - 1u);
+    } else if (t < nv + nh) {
+        const size_t u = t - nv;
+        const uint32_t y = (uint32_t) (u / cw + 1u) * CCL_T, x = (uint32_t) (u % cw);
+        const size_t g = (size_t) y * cw + x;
+        if (present[g] && present[g - cw] && (!use_threshold || color_distance(stored[g], stored[g - cw]) <= threshold)) uf_union(lab, (uint32_t) g, (uint32_t) (g - cw));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_ccl_compress(uint32_t *__restrict__ lab, size_t n, uint32_t *__restrict__ root_flag) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,25 +160,47 @@ k_ccl_stats(const uint32_t *__restrict__ lab, const uint32_t *__restrict__ root_
     int32_t b = -1;
     if (r != 0xffffffffu) b = (int32_t) root_rank[r];
     if (i < n) label[i] = b;
+    // a block whose pixels all belong to ONE blob (large blobs: most blocks) adds its seven sums through shared memory:
+    // seven global atomics per block instead of seven per warp on the same addresses
+    __shared__ int s_first;
+    __shared__ unsigned long long s_sum[7];
+    if (threadIdx.x == 0) s_first = -2;
+    if (threadIdx.x < 7) s_sum[threadIdx.x] = 0ull;
+    __syncthreads();
+    if (b >= 0) s_first = b;                                     // any writer wins: only used when all agree
+    __syncthreads();
+    const int first = s_first;
+    const bool uniform = __syncthreads_and(b < 0 || b == first) != 0;
     unsigned active = __ballot_sync(0xffffffffu, b >= 0);
-    if (b < 0) return;
-    unsigned peers = __match_any_sync(active, b);
     unsigned lane = threadIdx.x & 31;
-    unsigned leader = __ffs(peers) - 1;
-    uint32_t c = stored[i];
-    unsigned long long v[7] = {1ull, (unsigned long long) (i % cw), (unsigned long long) (i / cw), c_r(c), c_g(c), c_b(c), c_a(c)};
-    // reduce within the peer group (small loops over set bits; groups are usually the whole warp)
+    if (b >= 0) {
+        unsigned peers = __match_any_sync(active, b);
+        unsigned leader = __ffs(peers) - 1;
+        uint32_t c = stored[i];
+        unsigned long long v[7] = {1ull, (unsigned long long) (i % cw), (unsigned long long) (i / cw), c_r(c), c_g(c), c_b(c), c_a(c)};
+        // reduce within the peer group: one REDUX per sum when the whole warp is one blob (the usual case; every value is
+        // < 2^16, so 32 of them fit 32 bits), a loop over the set bits otherwise
+        const bool whole = peers == 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        unsigned long long s = 0;
-        unsigned m = peers;
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            s += __shfl_sync(peers, v[k], src);
+        for (int k = 0; k < 7; ++k) {
+            unsigned long long s = 0;
+            if (whole) s = __reduce_add_sync(0xffffffffu, (unsigned) v[k]);
+            else {
+                unsigned m = peers;
+                while (m) {
+                    int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    s += __shfl_sync(peers, v[k], src);
+                }
+            }
+            if (lane == leader) {
+                if (uniform) atomicAdd(&s_sum[k], s);
+                else atomicAdd(&sums[(size_t) b * 8 + k], s);
+            }
         }
-        if (lane == leader) atomicAdd(&sums[(size_t) b * 8 + k], s);
     }
+    __syncthreads();
+    if (uniform && first >= 0 && threadIdx.x < 7 && s_sum[threadIdx.x]) atomicAdd(&sums[(size_t) first * 8 + threadIdx.x], s_sum[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -155,9 +256,14 @@ static int blobify_frame(Engine *E, uint32_t index) {
     if (!dev_alloc(E, (void **) &lab, n * 4, "ccl lab") || !dev_alloc(E, (void **) &flag, n * 4, "ccl flag") || !dev_alloc(E, (void **) &rank, n * 4, "ccl rank")) rc = AMX_ERR_NOMEM;
     if (rc == AMX_OK) {
         bool use_thr = E->p.blob_threshold < 1.0;
-        k_ccl_init<<<div_up(n, 256), 256, 0, E->stream>>>(f.present, lab, n);
-        if (E->p.blob_max_size > 1)
-            k_ccl_merge<<<div_up(n, 256), 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold);
+        // tile-local labelling in shared memory, then unions across the tile borders only
+        const bool merge = E->p.blob_max_size > 1;
+        const dim3 tgrid(div_up(E->cw, CCL_T), div_up(E->ch, CCL_T));
+        k_ccl_tile<<<tgrid, 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold, merge ? 1 : 0);
+        if (merge) {
+            const size_t nborder = (size_t) ((E->cw - 1u) / CCL_T) * E->ch + (size_t) ((E->ch - 1u) / CCL_T) * E->cw;
+            if (nborder) k_ccl_border<<<div_up(nborder, 256), 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold);
+        }
         k_ccl_compress<<<div_up(n, 256), 256, 0, E->stream>>>(lab, n, flag);
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, rank, (int) n, E->stream);
         if (!dev_alloc(E, &tmp, tmp_bytes, "scan tmp")) rc = AMX_ERR_NOMEM;
