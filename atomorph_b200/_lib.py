@@ -73,6 +73,8 @@ def lib():
     sig("amx_pack_owned", i32, vp, u32, u32, u64, u64, vp, P(u64))
     sig("amx_unpack_owned", i32, vp, u32, u32, u64, u32, vp)
     sig("amx_swap_tiled_epoch", i32, vp, u32, u32, u64, u32, u32, u32)
+    sig("amx_swap_local_epoch", i32, vp, u32, u32, u64, u32)
+    sig("amx_set_swap_locality", i32, vp, u32)
     sig("amx_pack_tiled", i32, vp, u32, u32, u64, u32, u32, vp, P(u64))
     sig("amx_unpack_tiled", i32, vp, u32, u32, u64, vp)
     sig("amx_cost", i32, vp, P(f64))
@@ -105,7 +107,7 @@ AMX_SYMBOLS = [
     "amx_get_state", "amx_get_energy", "amx_blobify", "amx_blob_count", "amx_export_blobs", "amx_import_blobs",
     "amx_match_init", "amx_match_rounds", "amx_match_energy", "amx_init_chains", "amx_chain_count",
     "amx_chain_info", "amx_export_chain", "amx_import_chains", "amx_table_device_ptr", "amx_swap_rounds",
-    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_background",
+    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_swap_local_epoch", "amx_set_swap_locality", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_background",
     "amx_fluid_create", "amx_fluid_set_particles", "amx_fluid_get_particles", "amx_fluid_step",
     "amx_fluid_get_nodes", "amx_launch_count", "amx_timer_start", "amx_timer_stop",
 ]

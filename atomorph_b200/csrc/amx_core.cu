@@ -89,6 +89,7 @@ int amx_create(amx_ctx **out, int device) {
     c->e.own_stream = true;
     if (const char *nb = getenv("AMX_RENDER_BATCH")) c->e.render_batch = (uint32_t) std::max(1, atoi(nb));   // tuning knob (frames per launch pair)
     c->e.swap_global_only = getenv("AMX_SWAP_GLOBAL") != nullptr;
+    if (const char *lo = getenv("AMX_SWAP_LOCALITY")) c->e.swap_locality = (uint32_t) std::max(0, atoi(lo));   // every n-th tiled epoch pairs spatial neighbours
     if (const char *tl = getenv("AMX_RENDER_TILED")) c->e.tiled_enabled = atoi(tl) != 0;                      // 0: general A-buffer render path only
     cudaEventCreate(&c->e.ev0);
     cudaEventCreate(&c->e.ev1);
@@ -104,6 +105,7 @@ void amx_destroy(amx_ctx *ctx) {
     cudaSetDevice(E->device);
     reset_all(E);
     dev_free(E->d_swapstats);
+    dev_free(E->loc_buf); dev_free(E->loc_tmp);
     dev_free(E->d_out);
     dev_free(E->d_perlin);
     if (E->copy_stream) cudaStreamDestroy(E->copy_stream);

@@ -115,6 +115,10 @@ struct Engine {
     uint64_t *d_swapstats = nullptr;  // proposals, accepted, gain
     uint64_t  swapstats[3] = {0, 0, 0};
     bool      swap_global_only = false;   // AMX_SWAP_GLOBAL=1: one-round-per-launch kernels only (for comparisons)
+    uint32_t  swap_locality = 0;          // every n-th tiled epoch pairs spatial neighbours (amx_set_swap_locality / AMX_SWAP_LOCALITY; 0 = never)
+    uint32_t *loc_buf = nullptr;          // locality epochs: Morton keys / atom order (4 x 2^k u32) and the sort workspace
+    void     *loc_tmp = nullptr;
+    size_t    loc_cap = 0, loc_tmp_bytes = 0;
     uint64_t *d_partials = nullptr;   // cost partial sums
     uint32_t  n_partials = 0;
 
@@ -197,6 +201,7 @@ int engine_alloc_chains(Engine *E, uint32_t nchains, const uint64_t *keys, const
                         const uint64_t *max_surface, uint32_t height);                      // amx_chain.cu
 int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds);          // amx_swap.cu
 int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks);
+int engine_swap_local_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoch, uint32_t rounds);
 int engine_cost(Engine *E, double *cost);                                                   // amx_swap.cu
 int engine_render_prepare(Engine *E);                                                       // amx_render.cu
 int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int out_is_device);  // amx_render.cu

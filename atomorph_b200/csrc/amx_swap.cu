@@ -30,6 +30,7 @@
  * +16 B written per accepted swap.
  */
 #include <algorithm>
+#include <cub/cub.cuh>
 #include "amx_engine.h"
 
 namespace amx {
@@ -137,8 +138,11 @@ k_swap_multi(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
 
 // Per-epoch bijection u -> atom on k-bit indices: two multiply / xorshift rounds (each step is invertible mod 2^k).
 // Tile t owns u in [t * TILE_ATOMS, (t + 1) * TILE_ATOMS): a pseudo-random subset of the chain.
-struct TileMap { uint32_t a1, a2, c, s1, s2, mask; };
+// Locality epochs (default off): `perm` lists the atoms in Morton order of their column-y position
+// (padding slots hold 0xffffffff) and slot u is atom perm[(u + shift) & mask], so a tile holds 1024 spatial neighbours.
+struct TileMap { uint32_t a1, a2, c, s1, s2, mask; const uint32_t *perm; uint32_t shift; };
 __host__ __device__ __forceinline__ uint32_t tile_atom(const TileMap &tm, uint32_t u) {
+    if (tm.perm) return tm.perm[(u + tm.shift) & tm.mask];
     uint32_t v = (u * tm.a1) & tm.mask;
     v ^= v >> tm.s1;
     v = (v * tm.a2 + tm.c) & tm.mask;
@@ -154,6 +158,7 @@ static TileMap make_tilemap(uint64_t seed, uint64_t stream, uint64_t epoch, unsi
     tm.c = (uint32_t) r2 & tm.mask;
     tm.s1 = std::max(1u, k / 2);
     tm.s2 = std::max(1u, (k + 1) / 2);
+    tm.perm = nullptr; tm.shift = 0u;
     return tm;
 }
 
@@ -374,6 +379,66 @@ int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
     return E->check("tiled swap epoch") ? AMX_ERR_CUDA : AMX_OK;
 }
 
+// ---- locality epochs ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t morton_spread(uint32_t v) {        // 16 bits -> every other bit
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__global__ void __launch_bounds__(256)
+k_local_keys(const pword *__restrict__ col, uint64_t off, uint32_t w, uint32_t n2k, uint32_t *__restrict__ key, uint32_t *__restrict__ val) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n2k) return;
+    if (u < w) { const pword p = col[off + u]; key[u] = morton_spread(pw_x(p)) | (morton_spread(pw_y(p)) << 1); val[u] = u; }
+    else { key[u] = 0xffffffffu; val[u] = 0xffffffffu; }          // padding slot: behind every atom, never proposed
+}
+
+// One locality epoch on column y of `chain`: the atoms are sorted by the Morton code of their CURRENT column-y position,
+// consecutive runs of 1024 (shifted by a per-epoch random offset) form the tiles, and `rounds` rounds of random pairings
+// run inside every tile exactly as in a uniform epoch.  Proposals between spatial neighbours are the ones that still pay
+// late in the refinement, when uniform partners are accepted with probability ~ 1/proposals-per-atom.
+int engine_swap_local_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoch, uint32_t rounds) {
+    if (chain >= E->nchains || y >= E->h || rounds == 0 || !tiled_ok(E, chain)) return AMX_ERR_ARG;
+    const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
+    const unsigned k = ceil_log2(w);
+    const uint32_t n2k = 1u << k, ntiles = 1u << (k - TILE_BITS);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (int) n2k, 0, 32, E->stream);
+    if (E->loc_cap < n2k || E->loc_tmp_bytes < tmp_bytes) {
+        dev_free(E->loc_buf); dev_free(E->loc_tmp); E->loc_buf = nullptr; E->loc_tmp = nullptr; E->loc_cap = 0; E->loc_tmp_bytes = 0;
+        if (!dev_alloc(E, (void **) &E->loc_buf, (size_t) n2k * 16, "locality keys") || !dev_alloc(E, &E->loc_tmp, tmp_bytes, "locality sort")) return AMX_ERR_NOMEM;
+        E->loc_cap = n2k; E->loc_tmp_bytes = tmp_bytes;
+    }
+    uint32_t *key = E->loc_buf, *key2 = key + n2k, *val = key2 + n2k, *perm = val + n2k;
+    pword *col = E->table + (size_t) y * E->A;
+    k_local_keys<<<div_up(n2k, 256), 256, 0, E->stream>>>(col, off, (uint32_t) w, n2k, key, val);
+    cub::DeviceRadixSort::SortPairs(E->loc_tmp, tmp_bytes, key, key2, val, perm, (int) n2k, 0, 32, E->stream);
+    E->launches += 2;
+    TileMap tm = make_tilemap(E->p.seed, chain, epoch, k);
+    tm.perm = perm;
+    tm.shift = (uint32_t) rng64(E->p.seed, 0x10ca1u + chain, epoch) & tm.mask;
+    const uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
+    const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
+    const bool h2 = E->h == 2;
+    const size_t smem = (size_t) (h2 ? 2 : 3) * TILE_ATOMS * sizeof(uint2);
+    cudaFuncSetAttribute(k_swap_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_ATOMS * (int) sizeof(uint2));
+    cudaFuncSetAttribute(k_swap_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_ATOMS * (int) sizeof(uint2));
+    unsigned long long *st = (unsigned long long *) E->d_swapstats;
+    // the positions move while the tiles are refined: the order is rebuilt per epoch, further launches reuse it
+    for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
+        const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
+        const uint64_t round_base = (epoch << 20) + done + (1ull << 19);
+        if (h2) k_swap_tiled<true><<<ntiles, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, 0u, r, E->p.seed, round_base, st);
+        else    k_swap_tiled<false><<<ntiles, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, 0u, r, E->p.seed, round_base, st);
+        E->launches++;
+    }
+    E->render_ready = false;
+    return E->check("locality swap epoch") ? AMX_ERR_CUDA : AMX_OK;
+}
+
 int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds) {
     if (E->nchains == 0 || E->h < 2) return AMX_OK;
     if (chain >= (int32_t) E->nchains || column >= (int32_t) E->h) return AMX_ERR_ARG;
@@ -385,7 +450,9 @@ int engine_swap_rounds(Engine *E, int32_t chain, int32_t column, uint64_t rounds
             const uint32_t r = (uint32_t) std::min<uint64_t>(rounds, TILE_MAX_ROUNDS);
             const uint64_t epoch = E->rng_round++;
             const uint32_t y = column >= 0 ? (uint32_t) column : (uint32_t) (rng64(E->p.seed, 0xc01u, epoch) % E->h);
-            int rcode = engine_swap_tiled_epoch(E, c, y, epoch, r, 0, 1);
+            // every `swap_locality`-th epoch pairs spatial neighbours instead of uniform partners (default: never)
+            const bool local = E->swap_locality > 0 && (epoch % E->swap_locality) == E->swap_locality - 1;
+            int rcode = local ? engine_swap_local_epoch(E, c, y, epoch, r) : engine_swap_tiled_epoch(E, c, y, epoch, r, 0, 1);
             if (rcode != AMX_OK) return rcode;
             rounds -= r;
         }
@@ -511,6 +578,17 @@ int amx_swap_tiled_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t
     if (!ctx) return AMX_ERR_ARG;
     cudaSetDevice(ctx->e.device);
     return engine_swap_tiled_epoch(&ctx->e, chain, column, epoch, rounds, rank, nranks);
+}
+
+int amx_swap_local_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds) {
+    if (!ctx) return AMX_ERR_ARG;
+    cudaSetDevice(ctx->e.device);
+    return engine_swap_local_epoch(&ctx->e, chain, column, epoch, rounds);
+}
+int amx_set_swap_locality(amx_ctx *ctx, uint32_t every) {
+    if (!ctx) return AMX_ERR_ARG;
+    ctx->e.swap_locality = every;
+    return AMX_OK;
 }
 
 // the slots u of the epoch's bijection that rank `rank` owns, as a contiguous buffer (count = its tiles * 2^TILE_BITS)

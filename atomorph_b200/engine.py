@@ -258,6 +258,14 @@ class Engine:
     def swap_tiled_epoch(self, epoch, rounds, column, rank=0, nranks=1, chain=0):
         self._ck(self.L.amx_swap_tiled_epoch(self.h, chain, column, int(epoch), int(rounds), int(rank), int(nranks)), "swap_tiled_epoch")
 
+    def swap_local_epoch(self, epoch, rounds, column, chain=0):
+        """One locality epoch: tiles of 1024 spatial neighbours (Morton order of the column's current positions)."""
+        self._ck(self.L.amx_swap_local_epoch(self.h, chain, column, int(epoch), int(rounds)), "swap_local_epoch")
+
+    def set_swap_locality(self, every):
+        """Every `every`-th epoch of swap_rounds / step pairs spatial neighbours (0 = never, the default)."""
+        self._ck(self.L.amx_set_swap_locality(self.h, int(every)), "set_swap_locality")
+
     def pack_tiled(self, epoch, column, rank, nranks, d_out_ptr, chain=0):
         n = C.c_uint64(0)
         self._ck(self.L.amx_pack_tiled(self.h, chain, column, int(epoch), int(rank), int(nranks), C.c_void_p(d_out_ptr), C.byref(n)), "pack_tiled")

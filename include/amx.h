@@ -123,6 +123,12 @@ int  amx_unpack_owned(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t se
  * slots the rank owns into a contiguous device buffer, the ranks all-gather those buffers (equal sizes when n divides
  * the tile count) and amx_unpack_tiled scatters the gathered slots (rank-major = slot order) back into the column. */
 int  amx_swap_tiled_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds, uint32_t rank, uint32_t nranks);
+/* Locality-biased proposals (extension, default off; the intent of the reference's experimental kd-tree variant,
+ * thread.cpp:893-986): a locality epoch sorts the atoms by the Morton code of their current column position and refines
+ * runs of 1024 spatial neighbours in shared memory.  amx_set_swap_locality(ctx, n) makes every n-th epoch of
+ * amx_swap_rounds / amx_step a locality epoch (0 = never: the counted metric uses uniform partners only). */
+int  amx_swap_local_epoch(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rounds);
+int  amx_set_swap_locality(amx_ctx *ctx, uint32_t every);
 int  amx_pack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rank, uint32_t nranks, void *d_out, uint64_t *count);
 int  amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, const void *d_in);
 int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_energy(chain*), thread.cpp:1109-1125, summed over chains */

@@ -185,3 +185,46 @@ def test_tiled_epochs_shard_across_ranks():
         assert np.array_equal(wa, wb)
     assert np.array_equal(np.sort(wa[1]), np.sort(start[0]["words"][1]))
     assert ea.cost() < 0.5 * c0
+
+
+def test_locality_epochs_converge_faster_and_keep_the_permutation():
+    """Locality-biased proposals (default off): every other epoch pairs spatial neighbours.  Same
+    number of proposals, same start: the cost must end lower than with uniform partners only, the gain bookkeeping stays
+    exact and every column stays a permutation of its key points."""
+    images = scenes.square_to_disc(256)
+    params = dict(seed=1, motion=eng.LINEAR, fading=eng.LINEAR, threads=0, cycle_length=1000)
+
+    def fresh():
+        e = eng.Engine(0, **params)
+        e.load_images(images)
+        e.step(8)
+        assert e.state() == eng.STATE_ATOM_MORPHING
+        return e
+
+    ROUNDS = 64 * 48
+    a = fresh()
+    before = a.chains()[0]["words"].copy()
+    c0 = a.cost()
+    sa0 = a.swap_stats()
+    a.swap_rounds(ROUNDS, column=1)
+    n_uniform = int(a.swap_stats()[0] - sa0[0])
+    c_uniform = a.cost()
+
+    b = fresh()
+    assert b.cost() == c0
+    b.set_swap_locality(2)
+    st0 = b.swap_stats()
+    b.swap_rounds(ROUNDS, column=1)
+    st = b.swap_stats()
+    c_mixed = b.cost()
+    after = b.chains()[0]["words"]
+    assert _rows_are_permutation(before, after)
+    assert c0 - c_mixed == float(int(st[2] - st0[2]))
+    assert int(st[0] - st0[0]) == n_uniform                          # the same number of proposals
+    assert c_mixed < c_uniform < c0, (c0, c_uniform, c_mixed)
+    print("cost: start %.4g, uniform %.4g, with locality epochs %.4g (%.1f %% lower)" % (c0, c_uniform, c_mixed, 100.0 * (1.0 - c_mixed / c_uniform)))
+
+    # the explicit entry point: one locality epoch on its own lowers the cost as well
+    c = fresh()
+    c.swap_local_epoch(0, 64, column=1)
+    assert c.cost() < c0
