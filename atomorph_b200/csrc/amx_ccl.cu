@@ -6,9 +6,9 @@
  * blob_max_size = SIZE_MAX, blob_min_size = 1, blob_number = 1) every pair of 4-adjacent
  * pixels ends in the same blob, i.e. the final partition is exactly the set of 4-connected
  * components of the presence mask (measured).  That deterministic regime is
- * what is bit-exact here; for blob_threshold < 1 adjacent pixels are joined when their STORED
- * colours are within the threshold (color_distance, color.h:17-24) -- a deterministic stand-in
- * for the reference's RNG-dependent merge order, compared statistically only.
+ * what is bit-exact here; the other regimes (blob_number > 1, blob_threshold < 1, size limits)
+ * apply the reference's merge rules in parallel rounds (agglomerate_frame below) and are
+ * compared statistically only -- the reference's own result depends on its RNG order.
  *
  * Algorithm: lock-free union-find (label = smaller root wins through atomicMin), first per
  * 32x32-pixel tile in shared memory on tile-local indices, then across the tile borders in
@@ -139,6 +139,103 @@ k_ccl_border(const uint8_t *__restrict__ present, const uint32_t *__restrict__ s
     }
 }
 
+// ---------------------------------------------------------------------------------------- agglomerative regime
+// blob_number > 1, blob_threshold < 1, blob_max_size or blob_min_size set: the reference grows blobs one merge at a time
+// in an RNG order (thread.cpp:288-404: the blob at the back of a shuffled vector merges with the neighbour whose MEAN
+// colour is nearest, if within the threshold; undersized blobs ignore the threshold; blobs at blob_max_size stop) until
+// blob_number blobs are left.  Its result depends on the RNG order, so it cannot be reproduced bit for bit;
+// what is kept here is the rule set, applied in parallel rounds: every blob proposes its nearest-colour neighbour, MUTUAL
+// proposals merge (disjoint pairs, so a round is conflict-free), means are size-weighted averages of the two means
+// exactly as thread.cpp:348-357, distances are taken between the means rounded to 8 bits (thread.cpp:324-326), and the
+// last round applies only as many merges (smallest distance first) as are needed to land on blob_number exactly.
+struct Agg {
+    uint32_t *lab;          // parent per canvas position (root = its own index)
+    double   *mean;         // [4][canvas] mean colour of the blob rooted at a position (0..255 scale)
+    uint32_t *size;         // [canvas]
+    uint32_t *col;          // [canvas] mean colour rounded to 8 bits per channel
+    unsigned long long *best;   // [canvas] (squared colour distance << 46 | tie-break hash << 32 | neighbour root), ~0 = none
+    size_t    n;
+};
+
+__global__ void __launch_bounds__(256)
+k_agg_init(const uint8_t *__restrict__ present, const uint32_t *__restrict__ stored, Agg g) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    g.best[i] = ~0ull;
+    if (!present[i]) { g.lab[i] = 0xffffffffu; g.size[i] = 0u; return; }
+    const uint32_t c = stored[i];
+    g.lab[i] = (uint32_t) i; g.size[i] = 1u; g.col[i] = c;
+    g.mean[i] = (double) c_r(c); g.mean[g.n + i] = (double) c_g(c); g.mean[2 * g.n + i] = (double) c_b(c); g.mean[3 * g.n + i] = (double) c_a(c);
+}
+
+// every pair of 4-adjacent pixels in different blobs: both blobs consider each other
+__global__ void __launch_bounds__(256)
+k_agg_best(Agg g, uint32_t cw, uint32_t ch, double threshold, uint32_t max_size, uint32_t min_size, uint32_t round) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const uint32_t a = g.lab[i];
+    if (a == 0xffffffffu) return;
+    const uint32_t x = (uint32_t) (i % cw), y = (uint32_t) (i / cw);
+    const uint32_t sa = g.size[a], ca = g.col[a];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (k == 0 ? x + 1 >= cw : y + 1 >= ch) continue;
+        const uint32_t b = g.lab[k == 0 ? i + 1 : i + cw];
+        if (b == 0xffffffffu || b == a) continue;
+        const uint32_t sb = g.size[b], cb = g.col[b];
+        if (sa >= max_size || sb >= max_size) continue;                              // thread.cpp:304: a blob at the cap stops growing
+        const int rd = (int) c_r(ca) - (int) c_r(cb), gd = (int) c_g(ca) - (int) c_g(cb), bd = (int) c_b(ca) - (int) c_b(cb), ad = (int) c_a(ca) - (int) c_a(cb);
+        const uint32_t sq = (uint32_t) (rd * rd + gd * gd + bd * bd + ad * ad);
+        const bool within = sqrt((double) sq) / 510.0 <= threshold;                  // color_distance, color.h:17-24
+        if (!within && sa >= min_size && sb >= min_size) continue;                   // thread.cpp:382-387: undersized blobs ignore the threshold
+        // key: squared distance (18 bits) | per-round hash of the neighbour (14 bits: equal distances -- flat regions -- are
+        // broken in a different random order every round, so about a third of the blobs find a mutual partner) | neighbour
+        const unsigned long long d = (unsigned long long) sq << 46;
+        atomicMin(&g.best[a], d | ((unsigned long long) (mix64(((unsigned long long) round << 32) | b) >> 50) << 32) | b);
+        atomicMin(&g.best[b], d | ((unsigned long long) (mix64(((unsigned long long) round << 32) | a) >> 50) << 32) | a);
+    }
+}
+
+// mutual proposals -> pair list (the smaller root of a pair reports it)
+__global__ void __launch_bounds__(256)
+k_agg_pairs(Agg g, unsigned long long *__restrict__ pairs, uint32_t *__restrict__ count) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n || g.lab[i] != (uint32_t) i) return;
+    const unsigned long long ba = g.best[i];
+    if (ba == ~0ull) return;
+    const uint32_t b = (uint32_t) ba;
+    if (b > (uint32_t) i && (uint32_t) g.best[b] == (uint32_t) i) {
+        const uint32_t k = atomicAdd(count, 1u);
+        pairs[k] = (ba & 0xffffffff00000000ull) | (uint32_t) i;                      // (distance, smaller root): the partner is best[i]
+    }
+}
+
+// merge the first `m` pairs of the (sorted) list: the larger root hangs under the smaller one
+__global__ void __launch_bounds__(256)
+k_agg_merge(Agg g, const unsigned long long *__restrict__ pairs, uint32_t m) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const uint32_t a = (uint32_t) pairs[k], b = (uint32_t) g.best[a];
+    const double s1 = (double) g.size[a], s2 = (double) g.size[b];
+    const double weight = s2 / (s1 + s2);                                            // thread.cpp:348-357
+    double ch4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { ch4[c] = (1.0 - weight) * g.mean[c * g.n + a] + weight * g.mean[c * g.n + b]; g.mean[c * g.n + a] = ch4[c]; }
+    g.size[a] = g.size[a] + g.size[b];
+    g.col[a] = c_make(to_u8(round(ch4[0])), to_u8(round(ch4[1])), to_u8(round(ch4[2])), to_u8(round(ch4[3])));
+    g.lab[b] = a;
+}
+
+// point every pixel at its root again and clear the proposals
+__global__ void __launch_bounds__(256)
+k_agg_flatten(Agg g) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    g.best[i] = ~0ull;
+    if (g.lab[i] == 0xffffffffu) return;
+    g.lab[i] = uf_find(g.lab, (uint32_t) i);
+}
+
 __global__ void __launch_bounds__(256)
 k_ccl_compress(uint32_t *__restrict__ lab, size_t n, uint32_t *__restrict__ root_flag) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +339,57 @@ int engine_build_blob_pixels(Engine *E, uint32_t index) {
     return rc;
 }
 
+// labels of the agglomerative regime into `lab` (roots = smallest canvas index of a blob); AMX_OK or an error
+static int agglomerate_frame(Engine *E, FrameDev &f, uint32_t *lab) {
+    const size_t n = E->canvas();
+    Agg g;
+    g.lab = lab; g.n = n; g.mean = nullptr; g.size = nullptr; g.col = nullptr; g.best = nullptr;
+    unsigned long long *pairs = nullptr, *pairs2 = nullptr;
+    uint32_t *d_count = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (unsigned long long *) nullptr, (unsigned long long *) nullptr, (int) (n / 2 + 1), 0, 64, E->stream);
+    int rc = AMX_OK;
+    if (!dev_alloc(E, (void **) &g.mean, n * 4 * sizeof(double), "agg means") || !dev_alloc(E, (void **) &g.size, n * 4, "agg sizes") ||
+        !dev_alloc(E, (void **) &g.col, n * 4, "agg colours") || !dev_alloc(E, (void **) &g.best, n * 8, "agg proposals") ||
+        !dev_alloc(E, (void **) &pairs, (n / 2 + 1) * 8, "agg pairs") || !dev_alloc(E, (void **) &pairs2, (n / 2 + 1) * 8, "agg pairs") ||
+        !dev_alloc(E, (void **) &d_count, 4, "agg count") || !dev_alloc(E, &tmp, tmp_bytes, "agg sort"))
+        rc = AMX_ERR_NOMEM;
+    if (rc == AMX_OK) {
+        const uint32_t max_size = (uint32_t) std::min<uint64_t>(E->p.blob_max_size, 0xffffffffull);
+        const uint32_t min_size = (uint32_t) std::min<uint64_t>(E->p.blob_min_size, 0xffffffffull);
+        const uint64_t target = std::max<uint64_t>(E->p.blob_number, 1);
+        k_agg_init<<<div_up(n, 256), 256, 0, E->stream>>>(f.present, f.stored, g);
+        E->launches++;
+        uint64_t blobs = f.pixel_count;
+        for (int round = 0; round < 4096 && blobs > target; ++round) {
+            cudaMemsetAsync(d_count, 0, 4, E->stream);
+            k_agg_best<<<div_up(n, 256), 256, 0, E->stream>>>(g, E->cw, E->ch, E->p.blob_threshold, max_size, min_size, (uint32_t) round + E->p.seed * 7919u);
+            k_agg_pairs<<<div_up(n, 256), 256, 0, E->stream>>>(g, pairs, d_count);
+            uint32_t npairs = 0;
+            cudaMemcpyAsync(&npairs, d_count, 4, cudaMemcpyDeviceToHost, E->stream);
+            if (E->fail(cudaStreamSynchronize(E->stream), "agglomerate")) { rc = AMX_ERR_CUDA; break; }
+            E->launches += 2;
+            if (npairs == 0) break;                                          // nothing can expand any more (thread.cpp:402)
+            uint32_t m = npairs;
+            const unsigned long long *list = pairs;
+            if (blobs - npairs < target) {
+                // the last round: only the blobs - target nearest pairs
+                m = (uint32_t) (blobs - target);
+                cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, pairs, pairs2, (int) npairs, 0, 64, E->stream);
+                list = pairs2;
+            }
+            k_agg_merge<<<div_up(m, 256), 256, 0, E->stream>>>(g, list, m);
+            k_agg_flatten<<<div_up(n, 256), 256, 0, E->stream>>>(g);
+            E->launches += 2;
+            blobs -= m;
+        }
+        if (rc == AMX_OK && E->check("agglomerate")) rc = AMX_ERR_CUDA;
+    }
+    dev_free(g.mean); dev_free(g.size); dev_free(g.col); dev_free(g.best); dev_free(pairs); dev_free(pairs2); dev_free(d_count); dev_free(tmp);
+    return rc;
+}
+
 static int blobify_frame(Engine *E, uint32_t index) {
     FrameDev &f = E->frames[index];
     size_t n = E->canvas();
@@ -256,13 +404,18 @@ static int blobify_frame(Engine *E, uint32_t index) {
     if (!dev_alloc(E, (void **) &lab, n * 4, "ccl lab") || !dev_alloc(E, (void **) &flag, n * 4, "ccl flag") || !dev_alloc(E, (void **) &rank, n * 4, "ccl rank")) rc = AMX_ERR_NOMEM;
     if (rc == AMX_OK) {
         bool use_thr = E->p.blob_threshold < 1.0;
+        // non-default regimes (several blobs wanted, a colour threshold, size limits): parallel agglomeration
+        const bool agglomerate = E->p.blob_number > 1 || use_thr || E->p.blob_max_size < 0xffffffffull || E->p.blob_min_size > 1;
+        if (agglomerate && E->p.blob_max_size > 1) rc = agglomerate_frame(E, f, lab);
         // tile-local labelling in shared memory, then unions across the tile borders only
-        const bool merge = E->p.blob_max_size > 1;
+        const bool merge = E->p.blob_max_size > 1 && !agglomerate;
+        if (!agglomerate || E->p.blob_max_size <= 1) {
         const dim3 tgrid(div_up(E->cw, CCL_T), div_up(E->ch, CCL_T));
         k_ccl_tile<<<tgrid, 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold, merge ? 1 : 0);
         if (merge) {
             const size_t nborder = (size_t) ((E->cw - 1u) / CCL_T) * E->ch + (size_t) ((E->ch - 1u) / CCL_T) * E->cw;
             if (nborder) k_ccl_border<<<div_up(nborder, 256), 256, 0, E->stream>>>(f.present, f.stored, lab, E->cw, E->ch, use_thr ? 1 : 0, E->p.blob_threshold);
+        }
         }
         k_ccl_compress<<<div_up(n, 256), 256, 0, E->stream>>>(lab, n, flag);
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, rank, (int) n, E->stream);

@@ -115,3 +115,93 @@ def test_chain_build_with_duplicates_and_volatile(reflib):
         cg = np.unique(gd & 0xffffffff, return_counts=True)
         assert np.array_equal(cr[0], cg[0])
         assert np.abs(cr[1].astype(int) - cg[1].astype(int)).max() <= 1
+
+
+def _blob_checks(labels, present):
+    """every blob 4-connected, the blobs partition exactly the present pixels."""
+    from scipy import ndimage
+    assert np.array_equal(labels >= 0, present)
+    for b in range(labels.max() + 1):
+        mask = labels == b
+        if mask.any():
+            _, ncomp = ndimage.label(mask)          # default structure: 4-connectivity
+            assert ncomp == 1, "blob %d is not connected" % b
+
+
+@pytest.mark.parametrize("number", [4, 37])
+def test_blob_number_regime_statistical(reflib, number):
+    """blob_number = N: the reference stops its RNG-ordered merging at N blobs per key frame, so only
+    statistics are comparable: exactly N blobs, each 4-connected, covering the present pixels, no dwarf next to a giant
+    (the reference's and our size spreads stay within the same order of magnitude)."""
+    images = scenes.ellipses(72, 2, seed=9)
+    m = build_ref(reflib, images, seed=1, target=reflib.STATE_BLOB_MATCHING, blob_number=number)
+    e = eng.Engine(0, seed=1, blob_number=number)
+    e.load_images(images)
+    e.blobify()
+    for i, key in enumerate(m.frame_keys()):
+        ref_sizes = np.array(sorted(len(b["surface"]) for b in m.blobs(key) if len(b["surface"])))
+        labels, stats, meta = e.export_blobs(i)
+        sizes = np.array(sorted(int(s) for s in meta[:, 1] if s > 0))
+        assert len(ref_sizes) == number and len(sizes) == number, (len(ref_sizes), len(sizes))
+        assert sizes.sum() == ref_sizes.sum() == int((images[i][..., 3] > 0).sum())
+        _blob_checks(labels, images[i][..., 3] > 0)
+        # colour-coherent regions on both sides: the pixel-weighted colour spread inside the blobs is of the same order
+        def spread(lab, nb):
+            img = e.stored_image(i).astype(np.int64)
+            tot = 0.0
+            for b in range(nb):
+                px = img[lab == b]
+                if len(px):
+                    ch = np.stack([(px >> s) & 255 for s in (0, 8, 16)], axis=1).astype(np.float64)
+                    tot += ch.var(axis=0).sum() * len(px)
+            return tot / max(1, (lab >= 0).sum())
+        ours, theirs = spread(labels, number), spread(m.blob_labels(key), int(m.blob_labels(key).max()) + 1)
+        assert ours <= 3.0 * theirs + 1.0, (ours, theirs)
+
+
+def test_blob_threshold_regime_is_a_fixpoint():
+    """blob_threshold < 1 with blob_number = 1: merging stops when no two adjacent blobs have mean colours within the
+    threshold (thread.cpp:402).  Checked on our own result: every blob connected, adjacent blobs farther apart than the
+    threshold (mean colours from the exact pixel sums, rounded to 8 bits as thread.cpp:324-326 does)."""
+    images = scenes.rect_blobs(96, 40, frames=2, seed=7, min_side=4, max_side=18)
+    # touching rectangles of different colours: paint a second layer over the gaps so that blobs of different colour touch
+    rng = np.random.default_rng(3)
+    for im in images:
+        gap = im[..., 3] == 0
+        im[gap] = np.array([rng.integers(0, 256), rng.integers(0, 256), rng.integers(0, 256), 255], dtype=np.uint8)
+    thr = 0.05
+    e = eng.Engine(0, seed=1, blob_threshold=thr, blob_delimiter=eng.RGB)
+    e.load_images(images)
+    e.blobify()
+    for i in range(2):
+        labels, stats, meta = e.export_blobs(i)
+        nb = int((meta[:, 1] > 0).sum())
+        assert 2 <= nb < 96 * 96 // 4
+        _blob_checks(labels, images[i][..., 3] > 0)
+        col = np.round(stats[:, 2:6] * 255.0)
+        a, b = labels[:, :-1], labels[:, 1:]
+        c, d = labels[:-1, :], labels[1:, :]
+        pairs = set()
+        for u, v in ((a, b), (c, d)):
+            diff = u != v
+            pairs.update(zip(u[diff].tolist(), v[diff].tolist()))
+        for u, v in pairs:
+            dist = np.sqrt(((col[u] - col[v]) ** 2).sum()) / 510.0
+            assert dist > thr - 0.01, (u, v, dist)
+
+
+def test_blob_number_pipeline_renders():
+    """several blobs per key frame through the whole device pipeline: blob matching, one chain per blob group, render."""
+    images = scenes.ellipses(64, 2, seed=12)
+    e = eng.Engine(0, seed=1, blob_number=6, motion=eng.LINEAR, fading=eng.LINEAR, threads=0, cycle_length=2000)
+    e.load_images(images)
+    e.step(400)
+    if e.state() == eng.STATE_BLOB_MATCHING:
+        e.next_state()
+        e.step(10)
+    assert e.state() == eng.STATE_ATOM_MORPHING, e.state()
+    assert e.chain_count() == 6
+    frames = e.render([0.0, 0.5])
+    n0, n1 = int((images[0][..., 3] > 0).sum()), int((images[1][..., 3] > 0).sum())
+    assert np.array_equal(frames[0] != 0, images[0][..., 3] > 0)          # t = 0: every pixel of the first key frame
+    assert (frames[1] != 0).sum() >= 0.8 * min(n0, n1)                    # t = 0.5: a morph of the two shapes
