@@ -37,7 +37,9 @@ def _run_cli(exe, indir, outdir, prefix, names, extra):
 
 
 @pytest.mark.skipif(not (os.path.exists(DEMO_B200) and os.path.exists(DEMO_REF)), reason="demo binaries not built (make -C oracle demo)")
-@pytest.mark.parametrize("flags", [["--motion-linear", "--fading-linear"], ["--motion-spline", "--fading-cosine"]], ids=["linear", "spline_cosine"])
+@pytest.mark.parametrize("flags", [["--motion-linear", "--fading-linear"], ["--motion-spline", "--fading-cosine"],
+                                   ["--motion-linear", "--fading-linear", "-b", "6", "-p", "3", "-c", "2", "-z", "1"]],
+                         ids=["linear", "spline_cosine", "six_blobs"])
 def test_reference_cli_runs_unchanged_on_the_device(tmp_path, flags):
     from PIL import Image
     images = scenes.ellipses(64, 2, seed=3)
@@ -51,12 +53,17 @@ def test_reference_cli_runs_unchanged_on_the_device(tmp_path, flags):
     ours = _run_cli(DEMO_B200, tmp_path, tmp_path, "b200", names, extra)
     ref = _run_cli(DEMO_REF, tmp_path, tmp_path, "ref", names, extra)
     assert ours[0].shape == ref[0].shape == (64, 64, 4)
-    # t = 0: independent of the matching -> bit-identical, and it is the first key frame after the 8-bit HSP round trip
-    assert np.array_equal(ours[0], ref[0])
-    assert np.array_equal(ours[0][..., 3] > 0, images[0][..., 3] > 0)
-    for f in range(1, FRAMES):
+    several_blobs = "-b" in flags
+    if not several_blobs:
+        # t = 0: independent of the matching -> bit-identical, and it is the first key frame after the 8-bit HSP round trip
+        assert np.array_equal(ours[0], ref[0])
+        assert np.array_equal(ours[0][..., 3] > 0, images[0][..., 3] > 0)
+    # (with several blobs per key frame the blob partition itself is RNG-dependent in the reference, and a blob that is
+    # smaller than its partner carries duplicate atoms at t = 0: all frames are compared statistically)
+    for f in range(0 if several_blobs else 1, FRAMES):
         a, b = ours[f].astype(np.float64), ref[f].astype(np.float64)
         ca, cb = (a[..., 3] > 0).sum(), (b[..., 3] > 0).sum()
-        assert cb > 0 and abs(ca - cb) <= 0.15 * cb, (f, ca, cb)
+        # (different blob partitions move the parts of the shape differently: looser bounds with several blobs)
+        assert cb > 0 and abs(ca - cb) <= (0.35 if several_blobs else 0.15) * cb, (f, ca, cb)
         ma, mb = a[a[..., 3] > 0][:, :3].mean(axis=0), b[b[..., 3] > 0][:, :3].mean(axis=0)
-        assert np.abs(ma - mb).max() <= 12.0, (f, ma, mb)
+        assert np.abs(ma - mb).max() <= (25.0 if several_blobs else 12.0), (f, ma, mb)
