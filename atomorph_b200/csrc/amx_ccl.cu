@@ -458,6 +458,87 @@ static int blobify_frame(Engine *E, uint32_t index) {
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------- unification (row a-B2)
+// thread::unify_frame (thread.cpp:426-585): blobs that never reached blob_min_size ("dust") are clustered among themselves:
+// a dust blob looks at blob_box_samples other dust blobs (the next ones in the reference's shuffled vector, i.e. random
+// ones), takes the nearest whose rounded centroid lies within blob_box_grip in both axes and absorbs it (size-weighted
+// means; the merged blob need not be connected -- "a pixel dust cloud"), until nothing merges any more or blob_number
+// blobs are left.  Only runs when there are more blobs than blob_number and blob_box_samples > 0.  The sampling order is
+// RNG-dependent in the reference; here the samples come from the counter RNG (statistical parity).
+__global__ void __launch_bounds__(256)
+k_relabel(int32_t *__restrict__ label, const int32_t *__restrict__ remap, size_t n) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t b = label[i];
+    if (b >= 0) label[i] = remap[b];
+}
+
+static int unify_frame(Engine *E, uint32_t index) {
+    FrameDev &f = E->frames[index];
+    const uint64_t min_size = E->p.blob_min_size, samples = E->p.blob_box_samples, target = std::max<uint64_t>(E->p.blob_number, 1);
+    const size_t nb = f.blobs.size();
+    if (min_size <= 1 || samples == 0 || nb <= target) return AMX_OK;
+    std::vector<uint32_t> dust;
+    for (size_t b = 0; b < nb; ++b) if (f.blobs[b].size > 0 && f.blobs[b].size < min_size) dust.push_back((uint32_t) b);
+    if (dust.size() < 2) return AMX_OK;
+    std::vector<int32_t> into(nb, -1);                  // absorbed blob -> absorbing blob
+    std::vector<BlobHost> bl = f.blobs;
+    uint64_t count = nb, draw = 0;
+    const uint64_t grip = E->p.blob_box_grip;
+    bool merged_any = false;
+    for (int pass = 0; pass < 64 && count > target; ++pass) {
+        bool merged = false;
+        for (size_t di = 0; di < dust.size() && count > target; ++di) {
+            const uint32_t u = dust[di];
+            if (into[u] >= 0) continue;
+            const long ux = std::lround(bl[u].stats[0]), uy = std::lround(bl[u].stats[1]);
+            int64_t best = -1;
+            uint64_t best_score = 0;
+            for (uint64_t k = 0; k < samples; ++k) {
+                const uint32_t v = dust[rng64(E->p.seed, 0xd057u + index, draw++) % dust.size()];
+                if (v == u || into[v] >= 0) continue;
+                const long vx = std::lround(bl[v].stats[0]), vy = std::lround(bl[v].stats[1]);
+                const uint64_t dx = (uint64_t) std::labs(ux - vx), dy = (uint64_t) std::labs(uy - vy);
+                if (dx > grip || dy > grip) continue;
+                const uint64_t score = dx * dx + dy * dy;
+                if (best < 0 || score < best_score) { best = v; best_score = score; }
+            }
+            if (best < 0) continue;
+            const double s1 = (double) bl[u].size, s2 = (double) bl[best].size, weight = s2 / (s1 + s2);     // thread.cpp:488-505
+            for (int k = 0; k < 6; ++k) bl[u].stats[k] = (1.0 - weight) * bl[u].stats[k] + weight * bl[best].stats[k];
+            bl[u].size += bl[best].size;
+            into[best] = (int32_t) u;
+            --count;
+            merged = merged_any = true;
+        }
+        if (!merged) break;
+    }
+    if (!merged_any) return AMX_OK;
+    // compact the survivors (blob vector order kept) and relabel the pixels
+    std::vector<int32_t> remap(nb, -1);
+    std::vector<BlobHost> out;
+    for (size_t b = 0; b < nb; ++b) if (into[b] < 0) { remap[b] = (int32_t) out.size(); BlobHost x = bl[b]; x.group = out.size(); out.push_back(x); }
+    for (size_t b = 0; b < nb; ++b) if (into[b] >= 0) { int32_t r = into[b]; while (into[r] >= 0) r = into[r]; remap[b] = remap[r]; }
+    int32_t *d_remap = nullptr;
+    if (!dev_alloc(E, (void **) &d_remap, nb * 4, "blob remap")) return AMX_ERR_NOMEM;
+    cudaMemcpyAsync(d_remap, remap.data(), nb * 4, cudaMemcpyHostToDevice, E->stream);
+    k_relabel<<<div_up(E->canvas(), 256), 256, 0, E->stream>>>(f.label, d_remap, E->canvas());
+    E->launches++;
+    bool bad = E->fail(cudaStreamSynchronize(E->stream), "unify") || E->check("unify");
+    dev_free(d_remap);
+    if (bad) return AMX_ERR_CUDA;
+    f.blobs = out;
+    return engine_build_blob_pixels(E, index);
+}
+
+int engine_unify(Engine *E) {
+    for (uint32_t i = 0; i < E->frames.size(); ++i) {
+        int rc = unify_frame(E, i);
+        if (rc != AMX_OK) return rc;
+    }
+    return AMX_OK;
+}
+
 int engine_blobify(Engine *E) {
     for (uint32_t i = 0; i < E->frames.size(); ++i) {
         int rc = blobify_frame(E, i);

@@ -192,6 +192,7 @@ inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned) ((a + b - 1) 
 // stage entry points (each in its own .cu)
 int engine_upload_convert(Engine *E, uint32_t index, const uint32_t *d_rgba_raw);           // amx_color.cu
 int engine_blobify(Engine *E);                                                              // amx_ccl.cu
+int engine_unify(Engine *E);                                                                // amx_ccl.cu
 int engine_build_blob_pixels(Engine *E, uint32_t index);                                    // amx_ccl.cu
 int engine_match_init(Engine *E);                                                           // amx_blobmatch.cu
 int engine_match_rounds(Engine *E, uint64_t rounds);                                        // amx_blobmatch.cu

@@ -5,7 +5,7 @@
  * Step accounting mirrors the reference so that callers that count work through iterate(n) keep
  * working (SURVEY.md section 9 note 14):
  *   - blob detection: the reference needs one step per merge; the GPU pass finishes in ONE step
- *   - unification:    one step (dust merging only matters for blob_min_size > 1)
+ *   - unification:    one step (engine_unify: dust clustering, only with blob_min_size > 1)
  *   - matching:       first step builds the blob map, each further step is one parallel round
  *   - atom morphing:  one step = max(1, threads) * cycle_length swap proposals on ONE chain,
  *                     chains served round-robin (thread.cpp:1043-1064).  n steps on a C-chain
@@ -83,9 +83,12 @@ static int pipeline_steps(Engine *E, uint64_t nsteps) {
                 E->state = ST_BLOB_UNIFICATION; E->counter = 0;
                 break;
             }
-            case ST_BLOB_UNIFICATION:
+            case ST_BLOB_UNIFICATION: {
+                int rc = engine_unify(E);                 // dust clustering: a no-op with the default blob_min_size = 1
+                if (rc != AMX_OK) return rc;
                 E->state = ST_BLOB_MATCHING; E->counter = 0;
                 break;
+            }
             case ST_BLOB_MATCHING: {
                 bool done = E->skip_state;
                 if (!done) {

@@ -205,3 +205,35 @@ def test_blob_number_pipeline_renders():
     n0, n1 = int((images[0][..., 3] > 0).sum()), int((images[1][..., 3] > 0).sum())
     assert np.array_equal(frames[0] != 0, images[0][..., 3] > 0)          # t = 0: every pixel of the first key frame
     assert (frames[1] != 0).sum() >= 0.8 * min(n0, n1)                    # t = 0.5: a morph of the two shapes
+
+
+def test_dust_unification_statistical(reflib):
+    """blob_min_size > 1 (row a-B2): isolated specks ("dust") are clustered among themselves within blob_box_grip
+    (thread.cpp:426-585).  The reference's sampling order is RNG-dependent: blob counts and the pixel budget are compared."""
+    rng = np.random.default_rng(11)
+    images = []
+    for k in range(2):
+        im = np.zeros((64, 64, 4), dtype=np.uint8)
+        ys, xs = np.nonzero(rng.random((64, 64)) < 0.06)            # isolated specks, a few 2-3 pixel clumps
+        im[ys, xs] = np.concatenate([rng.integers(0, 256, size=(len(ys), 3)), np.full((len(ys), 1), 255)], axis=1).astype(np.uint8)
+        im[20:30, 20:30] = [200, 40, 40, 255]                       # and one real blob
+        images.append(im)
+    params = dict(blob_min_size=6, blob_box_grip=12, blob_box_samples=20, blob_number=1)
+    m = build_ref(reflib, images, seed=1, target=reflib.STATE_BLOB_MATCHING, **params)
+    e = eng.Engine(0, seed=1, threads=0, cycle_length=10, **params)
+    e.load_images(images)
+    e.blobify()
+    before = [int((e.export_blobs(i)[2][:, 1] > 0).sum()) for i in range(2)]
+    e.step(1)                                                       # the unification step
+    assert e.state() == eng.STATE_BLOB_MATCHING
+    for i, key in enumerate(m.frame_keys()):
+        labels, stats, meta = e.export_blobs(i)
+        sizes = meta[:, 1][meta[:, 1] > 0]
+        n_ref = len([b for b in m.blobs(key) if len(b["surface"])])
+        present = images[i][..., 3] > 0
+        assert np.array_equal(labels >= 0, present)
+        assert int(sizes.sum()) == int(present.sum())
+        assert len(sizes) < 0.7 * before[i], (len(sizes), before[i])          # the dust has been clustered
+        assert 0.4 * n_ref <= len(sizes) <= 2.5 * n_ref, (len(sizes), n_ref)
+        # the real blob survives as one blob of its own
+        assert len(np.unique(labels[20:30, 20:30])) == 1
