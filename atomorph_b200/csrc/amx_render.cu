@@ -842,37 +842,43 @@ __device__ __forceinline__ uint32_t t_home(uint32_t meta) { return meta >> 16; }
 // Sorted layout: s_sorted holds the record indices ordered by home, s_off[h] the position of home h's first record.
 // The two homes of a home row that reach a thread's pixel column are neighbours (h0: column lx, dx = 1; h0 + 1: column
 // lx + 1, dx = 0), so their records form ONE contiguous range, walked by one loop (the first two iterations by the whole
-// warp, the rest behind a vote).  Returns the number of records of the two homes.
+// warp, the rest behind a vote), two records per iteration.  Returns the number of records of the two homes.
 template <bool SINGLE, bool COUNTED, bool HAS_A, bool HAS_B>
 __device__ __forceinline__ uint32_t fold_row_sorted(const uint2 *__restrict__ s_rec, const uint16_t *__restrict__ s_chain, const uint16_t *__restrict__ s_sorted,
                                                     const uint32_t *__restrict__ s_off, uint32_t h0, TPart &Pa, TPart &Pb) {
     const uint32_t a = s_off[h0], mid = s_off[h0 + 1u], b = s_off[h0 + 2u];
     const uint32_t n = b - a, nn = min(n, (uint32_t) MAXK + 1u);           // beyond MAXK the pixel takes the replay anyway
     // (a warp-wide max of the range lengths -- REDUX -- as the trip count measured 15 % slower than this vote per iteration)
-    for (uint32_t it = 0; ; ++it) {
-        const bool has = it < nn;
-        if (it >= 2u && !__any_sync(0xffffffffu, has)) break;
+    // Two records per iteration.  A bilinear weight is < 2^16 and a colour byte < 2^8, so IDP.2A (__dp2a_lo: c + a.lo * b.0 +
+    // a.hi * b.1) adds the contributions of BOTH records to one 32-bit sum: weights packed w0 | w1 << 16, colours c0 | c1 << 8.
+    for (uint32_t it = 0; ; it += 2u) {
+        const bool has0 = it < nn, has1 = it + 1u < nn;
+        if (it >= 2u && !__any_sync(0xffffffffu, has0)) break;
         const uint32_t p = a + it;
-        uint32_t j = 0u;
-        if (has) j = s_sorted[p];
-        const uint2 r = s_rec[j];
-        const uint32_t fx = p < mid ? r.y : r.y ^ 0xffu;                     // dx = 1 ? x_fract : 255 - x_fract
-        const uint32_t wx = has ? __byte_perm(fx, 0, 0x4440) : 0u;
-        const uint32_t yf = __byte_perm(r.y, 0, 0x4441);
-        const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
-        uint32_t tag = 0u;
-        if (!SINGLE) tag = s_chain[j];
+        uint32_t j0 = 0u, j1 = 0u;
+        if (has0) j0 = s_sorted[p];
+        if (has1) j1 = s_sorted[p + 1u];
+        const uint2 r0 = s_rec[j0], r1 = s_rec[j1];
+        const uint32_t fx0 = p < mid ? r0.y : r0.y ^ 0xffu, fx1 = p + 1u < mid ? r1.y : r1.y ^ 0xffu;     // dx = 1 ? x_fract : 255 - x_fract
+        const uint32_t wx0 = has0 ? __byte_perm(fx0, 0, 0x4440) : 0u, wx1 = has1 ? __byte_perm(fx1, 0, 0x4440) : 0u;
+        const uint32_t yf0 = __byte_perm(r0.y, 0, 0x4441), yf1 = __byte_perm(r1.y, 0, 0x4441);
+        // colour bytes of the two records side by side: channel k -> (c0.k | c1.k << 8)
+        const uint32_t cr = __byte_perm(r0.x, r1.x, 0x4440), cg = __byte_perm(r0.x, r1.x, 0x4451), cb = __byte_perm(r0.x, r1.x, 0x4462), ca = __byte_perm(r0.x, r1.x, 0x4473);
+        uint32_t t0 = 0u, t1 = 0u;
+        if (!SINGLE) { t0 = s_chain[j0]; t1 = s_chain[j1]; }
         if (HAS_A) {
-            const uint32_t w = wx * (255u - yf);
-            Pa.R += cr * w; Pa.G += cg * w; Pa.B += cb * w; Pa.A += ca * w; Pa.N += w;
-            if (COUNTED) Pa.cnt += (w != 0u);
-            if (!SINGLE) { if (w) Pa.chain = merge_chain(Pa.chain, tag); }
+            const uint32_t w0 = wx0 * (255u - yf0), w1 = wx1 * (255u - yf1), ww = w0 | (w1 << 16);
+            Pa.R = __dp2a_lo(ww, cr, Pa.R); Pa.G = __dp2a_lo(ww, cg, Pa.G); Pa.B = __dp2a_lo(ww, cb, Pa.B); Pa.A = __dp2a_lo(ww, ca, Pa.A);
+            Pa.N += w0 + w1;
+            if (COUNTED) Pa.cnt += (w0 != 0u) + (w1 != 0u);
+            if (!SINGLE) { if (w0) Pa.chain = merge_chain(Pa.chain, t0); if (w1) Pa.chain = merge_chain(Pa.chain, t1); }
         }
         if (HAS_B) {
-            const uint32_t w = wx * yf;
-            Pb.R += cr * w; Pb.G += cg * w; Pb.B += cb * w; Pb.A += ca * w; Pb.N += w;
-            if (COUNTED) Pb.cnt += (w != 0u);
-            if (!SINGLE) { if (w) Pb.chain = merge_chain(Pb.chain, tag); }
+            const uint32_t w0 = wx0 * yf0, w1 = wx1 * yf1, ww = w0 | (w1 << 16);
+            Pb.R = __dp2a_lo(ww, cr, Pb.R); Pb.G = __dp2a_lo(ww, cg, Pb.G); Pb.B = __dp2a_lo(ww, cb, Pb.B); Pb.A = __dp2a_lo(ww, ca, Pb.A);
+            Pb.N += w0 + w1;
+            if (COUNTED) Pb.cnt += (w0 != 0u) + (w1 != 0u);
+            if (!SINGLE) { if (w0) Pb.chain = merge_chain(Pb.chain, t0); if (w1) Pb.chain = merge_chain(Pb.chain, t1); }
         }
     }
     return n;
