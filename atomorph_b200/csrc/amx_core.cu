@@ -90,7 +90,7 @@ int amx_create(amx_ctx **out, int device) {
     if (const char *nb = getenv("AMX_RENDER_BATCH")) c->e.render_batch = (uint32_t) std::max(1, atoi(nb));   // tuning knob (frames per launch pair)
     c->e.swap_global_only = getenv("AMX_SWAP_GLOBAL") != nullptr;
     if (const char *lo = getenv("AMX_SWAP_LOCALITY")) c->e.swap_locality = (uint32_t) std::max(0, atoi(lo));   // every n-th tiled epoch pairs spatial neighbours
-    if (const char *tl = getenv("AMX_RENDER_TILED")) c->e.tiled_enabled = atoi(tl) != 0;                      // 0: general A-buffer render path only
+    if (const char *tl = getenv("AMX_RENDER_TILED")) { c->e.tiled_enabled = atoi(tl) != 0; c->e.tiled_multi = atoi(tl) >= 2; }   // 0: general A-buffer path only; 2: tiled path for multi-chain morphs too
     cudaEventCreate(&c->e.ev0);
     cudaEventCreate(&c->e.ev1);
     if (!dev_alloc(&c->e, (void **) &c->e.d_swapstats, 3 * sizeof(uint64_t), "swapstats")) { delete c; return AMX_ERR_NOMEM; }

@@ -157,6 +157,7 @@ struct Engine {
     uint32_t  tb_tiles_x = 0, tb_tiles_y = 0, tb_parity = 0, tb_dirty[2] = {0, 0};
     bool      tb_has_chain = false;
     bool      tiled_enabled = true;        // AMX_RENDER_TILED=0: general A-buffer path only (for comparisons)
+    bool      tiled_multi = false;         // AMX_RENDER_TILED=2: tiled path for morphs with several chains as well
     bool      tiled_blocked = false;       // a bin overflowed with the current table: general path until the next refresh
     uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_path_frames)
     uint32_t  tb_demand[6] = {0, 0, 0, 0, 0, 0};       // largest bin counts per class, tile total, overflow list seen (amx_render_tiled_stats)

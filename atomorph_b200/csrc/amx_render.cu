@@ -716,7 +716,7 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // array.  Pixels fold the records of the homes that reach them into exact integer sums exactly like k_gather_pixel; ties,
 // several blobs at a pixel and pixels with more than MAXK records take the ordered double replay (resolve_contributions).
 //
-// Capacity: a tile takes T_SREC records per frame (its nine bins together: 3 atoms per pixel; an interior bin holds 2.5).
+// Capacity: a tile takes T_SREC records per frame (its nine bins together: 4 atoms per pixel; an interior bin holds 3.5).
 // A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general
 // path above (the results of the two paths are identical, both being exact).
 #ifndef T_CTAS
@@ -724,11 +724,11 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #endif
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
-#define T_SREC   3072u                  // (54 KB of shared memory per CTA: 4 CTAs per SM)
-#define T_CAP0   2560u
+#define T_SREC   4096u                  // (12 B of shared memory per record, 54 KB per CTA: 4 CTAs per SM)
+#define T_CAP0   3584u
 // T_SREC: records a tile takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities per class (interior / last column or row / corner)
-#define T_CAP1   192u
-#define T_CAP3   64u
+#define T_CAP1   512u
+#define T_CAP3   128u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
 #define T_KEY_NONE 0xffffffffu
 
@@ -826,12 +826,12 @@ struct TPart { uint32_t R, G, B, A, N, cnt, chain; };
 struct TileCtx {
     uint32_t segstart[10];    // [1..9]: lengths of the nine segments
     uint32_t segfirst[9];     // global index of a segment's first record
+    uint32_t segprefix[10];   // prefix sums of the (clamped) segment lengths: tile-local record index -> segment
     uint32_t wsum[8];         // per-warp totals of the offset scan
     uint32_t pad[4];
 };
 #define T_SMEM_REC   0u
-#define T_SMEM_ATOM  (T_SREC * 8u)
-#define T_SMEM_SLOT  (T_SMEM_ATOM + T_SREC * 4u)
+#define T_SMEM_SLOT  (T_SREC * 8u)
 #define T_SORT_OFF_BYTES 4368u          // u32 offsets [33 * 33 + 3]
 #define T_SMEM_CTX   (T_SMEM_SLOT + T_SORT_OFF_BYTES + 2u * T_SREC * 2u)   // then u16 ranks [T_SREC] and u16 sorted indices [T_SREC]
 #define T_SMEM_CHAIN (T_SMEM_CTX + (uint32_t) sizeof(TileCtx))
@@ -886,11 +886,11 @@ __device__ __forceinline__ uint32_t fold_row_sorted(const uint2 *__restrict__ s_
 
 // the ordered double replay of one pixel of a tile (local pixel lx, ly): ties, several blobs, overflowing homes
 template <bool SINGLE>
-__device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem, const RConst *rcp, const uint32_t *__restrict__ chain_of,
+__device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem, const uint32_t *__restrict__ g_atom, const RConst *rcp, const uint32_t *__restrict__ chain_of,
                                                       const int32_t *__restrict__ boc, const uint32_t *__restrict__ blob_avg,
                                                       const uint32_t *__restrict__ blob_distinct, uint32_t y_frame, uint32_t lx, uint32_t ly, uint32_t bgc) {
     const uint2 *s_rec = (const uint2 *) (smem + T_SMEM_REC);
-    const uint32_t *s_atom = (const uint32_t *) (smem + T_SMEM_ATOM);
+    const TileCtx *cx = (const TileCtx *) (smem + T_SMEM_CTX);
     const RConst rc = *rcp;
     auto visit = [&](auto f) {
 #pragma unroll
@@ -901,7 +901,11 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
                 const uint2 r = s_rec[j];
                 const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
                 const uint32_t n = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
-                if (n) f(s_atom[j], r.x, n, 0u);
+                if (!n) return;
+                // the atom index stays in the bin (global memory): tile-local record index -> segment -> bin position
+                uint32_t sgm = 0;
+                while (sgm < 8u && j >= cx->segprefix[sgm + 1u]) ++sgm;
+                f(g_atom[(size_t) cx->segfirst[sgm] + (j - cx->segprefix[sgm])], r.x, n, 0u);
             };
             const uint32_t *s_off = (const uint32_t *) (smem + T_SMEM_SLOT);
             const uint16_t *s_sorted = (const uint16_t *) (smem + T_SMEM_SLOT + T_SORT_OFF_BYTES) + T_SREC;
@@ -924,7 +928,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
        const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint2 *s_rec = (uint2 *) (smem + T_SMEM_REC);
-    uint32_t *s_atom = (uint32_t *) (smem + T_SMEM_ATOM);
     TileCtx *cx = (TileCtx *) (smem + T_SMEM_CTX);
     uint16_t *s_chain = (uint16_t *) (smem + T_SMEM_CHAIN);
 
@@ -973,6 +976,10 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
 #pragma unroll
     for (uint32_t s = 1; s <= 9u; ++s) seg[s] = min(seg[s], T_SREC);   // (truncated for memory safety)
     const uint32_t m = seg[9];
+    if (tid == 0u) {                                             // for the replay path (read after the barriers below)
+#pragma unroll
+        for (uint32_t s = 0; s < 10u; ++s) cx->segprefix[s] = seg[s];
+    }
     T_PHASE(0);
 
     const uint32_t lx = tid & 31u, band = tid >> 5;
@@ -999,7 +1006,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
         const uint32_t j0 = seg[s], n = seg[s + 1u] - j0, first = cx->segfirst[s];
         for (uint32_t i = tid; i < n; i += 256u) {
             __pipeline_memcpy_async(&s_rec[j0 + i], &bn.rec[(size_t) first + i], 8);
-            __pipeline_memcpy_async(&s_atom[j0 + i], &bn.atom[(size_t) first + i], 4);
         }
         if (!SINGLE) for (uint32_t i = tid; i < n; i += 256u) s_chain[j0 + i] = (uint16_t) bn.chain[(size_t) first + i];
     }
@@ -1118,7 +1124,7 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
             continue;
         }
         if (stats) atomicAdd(&stats->generic, 1ull);
-        outf[i] = resolve_generic_tile<SINGLE>(smem, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
+        outf[i] = resolve_generic_tile<SINGLE>(smem, bn.atom, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct,
                                                y_frame, lx, band * 4u + p, bgc);
     }
     T_PHASE(4);
@@ -1797,7 +1803,9 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     }
     // frames per launch pair: AMX_RENDER_BATCH (default RBATCH) on the tiled path, at most GBATCH on the general one
     // feather == 0 without fluid: the tiled path, unless it is switched off / has overflowed with this table
-    const bool tiled = have_chains && E->tiled_enabled && !E->tiled_blocked && E->p.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
+    // (several chains: pixels shared by several blobs take the ordered replay, which runs better in the general path's small
+    // CTAs at full occupancy -- C4: 4.3 k against 1.8 k frames/s -- so the tiled path is for single-chain morphs unless forced)
+    const bool tiled = have_chains && E->tiled_enabled && (E->nchains == 1 || E->tiled_multi) && !E->tiled_blocked && E->p.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
     const uint32_t NB = std::max(1u, std::min<uint32_t>(E->render_batch, tiled ? RBATCH : GBATCH));
     if (E->p.keep_background && E->d_bg_cap < (size_t) NB * np) {
         dev_free(E->d_bg); E->d_bg = nullptr; E->d_bg_cap = 0;

@@ -44,9 +44,9 @@ def test_render_matches_reference(reflib, name, scene, params):
         ndiff += n
         total += ref.size
     assert ndiff <= 0.01 * total, "%s: %d of %d pixels differ" % (name, ndiff, total)
-    # feather == 0 goes through the tiled path (shared-memory tiles), feather > 0 through the general A-buffer path
+    # a single chain without feather goes through the tiled path (shared-memory tiles), everything else through the general A-buffer path
     paths = e.render_path_frames()
-    if params.get("feather", 0) == 0:
+    if params.get("feather", 0) == 0 and e.chain_count() == 1:
         assert paths["tiled"] == len(TIMES) and paths["general"] == 0, paths
     else:
         assert paths["tiled"] == 0, paths
@@ -130,3 +130,24 @@ def test_tiled_diagnostics_and_kernel_times():
     assert st["fallbacks"] == 0 and not st["blocked"]
     assert 0 < st["max_bin"][0] <= 2560 and st["max_tile"] >= st["max_bin"][0]
     assert e.render_path_frames() == dict(tiled=16, general=0)
+
+
+def test_tiled_path_with_several_chains_equals_general_path(reflib, monkeypatch):
+    """AMX_RENDER_TILED=2 forces the tiled path for multi-chain morphs (off by default: slower there): identical frames,
+    including pixels shared by several blobs, show_blobs and the background."""
+    images = scenes.rect_blobs(96, 30, frames=2, seed=8, min_side=4, max_side=16)
+    for params in (dict(motion=eng.LINEAR, fading=eng.LINEAR, density=2), dict(motion=eng.SPLINE, fading=eng.COSINE, show_blobs=eng.AVERAGE, keep_background=1)):
+        m = build_ref(reflib, images, seed=2, match_steps=200, **params)
+        ts = [m.get_time(f, 10) for f in range(10)]
+        monkeypatch.setenv("AMX_RENDER_TILED", "2")
+        e2 = engine_from_ref(m, images, seed=2, **params)
+        assert e2.chain_count() > 1
+        a = e2.render(ts)
+        assert e2.render_path_frames() == dict(tiled=10, general=0)
+        monkeypatch.setenv("AMX_RENDER_TILED", "1")
+        e1 = engine_from_ref(m, images, seed=2, **params)
+        b = e1.render(ts)
+        assert e1.render_path_frames() == dict(tiled=0, general=10)
+        assert np.array_equal(a, b)
+        n, mx = diff_stats(m.render(ts[4]), a[4])
+        assert mx <= 1 and n <= 0.01 * a[4].size
