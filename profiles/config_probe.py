@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Render throughput of BASELINE.json configs 4 and 5 (device-resident frames/s), tiled path against the general A-buffer path.
+"""Render throughput of BASELINE.json configs 3, 4 and 5 (device-resident frames/s), tiled path against the general A-buffer path.
 
     python profiles/config_probe.py > profiles/r01b_configs.txt      (needs a GPU)
 
 C4: 512x512, 2500 flat rectangles per key frame (one chain per blob group), density 2, linear motion + cosine fading,
-128 frames.  C5: 4096x4096, 8 cyclic key frames, 16.7 M atoms, spline motion, 64 of the 512 frames."""
+128 frames.  C3: 1024x1024, 2 key frames, fluid (10 MPM steps per frame) + perlin fading + feather 2, 16 frames (stateful
+particle path, one frame at a time; the tiled / general switch does not apply).  C5: 4096x4096, 8 cyclic key frames, 16.7 M atoms, spline motion, 64 of the 512 frames."""
 import os
 import sys
 import time
@@ -56,3 +57,24 @@ run("C4 512^2 2500 blobs d2 ", scenes.rect_blobs(512, 2500, frames=2, seed=11, m
     np.array([f / 128.0 for f in range(128)]), prep_c4)
 run("C5 4096^2 8 key frames ", scenes.rotating_shapes(4096, 8), dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=1000),
     np.array([f / 512.0 for f in range(64)]), prep_c5)
+
+
+def prep_c3(e):
+    e.step(8)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    e.swap_rounds(512)
+
+
+os.environ["AMX_RENDER_TILED"] = "1"
+e = eng.Engine(0, seed=1, motion=eng.SPLINE, fading=eng.PERLIN, feather=2, fluid=10, threads=0, cycle_length=1000)
+e.load_images(scenes.square_to_disc(1024))
+prep_c3(e)
+out = torch.empty((16, 1024, 1024), dtype=torch.int32, device="cuda:0")
+times = np.array([f / 64.0 for f in range(16)])
+e.render_into(times[:2], out.data_ptr(), True)
+e.sync()
+t0 = time.perf_counter()
+e.render_into(times, out.data_ptr(), True)
+e.sync()
+dt = time.perf_counter() - t0
+print("C3 1024^2 fluid 10 + perlin + feather 2: %8.1f frames/s (%.1f us/frame)" % (16 / dt, 1e6 * dt / 16), flush=True)
