@@ -21,6 +21,7 @@ struct Fluid {
     uint8_t *active = nullptr, *mature = nullptr, *owner = nullptr;
     double *aux = nullptr;       // [3][n] frame_key, source_pos, destination_pos (as handed in / out by the C-ABI)
     double *nf = nullptr;        // [NF_COUNT][gx*gy]
+    double *cell = nullptr;      // [5][gx*gy] colour sums per base cell of a step (k_fluid_p2g -> k_fluid_colour_box)
     uint64_t step_counter = 0;
     FluidDraw *draw = nullptr;   // driver state, allocated on the first fluid frame
 };
