@@ -119,6 +119,36 @@ k_fluid_colour_box(const double *__restrict__ cell, double *__restrict__ nf, uin
     }
 }
 
+// The colour part of the gather (fluidmodel.cpp:462-475) sums the colour fields of the nine nodes of a particle's stencil
+// UNWEIGHTED: a 3x3 box sum again, computed once per base cell (same operand order as the per-particle loop: x offset
+// outer, y offset inner, so the sums are bit-identical) into `cell`, which k_fluid_colour_box has consumed by then.  A
+// particle reads 5 values instead of 45.
+__global__ void __launch_bounds__(256)
+k_fluid_colour_gather(const double *__restrict__ nf, double *__restrict__ cell, uint32_t gsx, uint32_t gsy) {
+    __shared__ double s[10][34];
+    const size_t ng = (size_t) gsx * gsy;
+    const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+    const uint32_t X = blockIdx.x * 32u + tx, Y = blockIdx.y * 8u + ty;
+    for (int f = 0; f < 5; ++f) {
+        for (uint32_t l = threadIdx.x; l < 340u; l += 256u) {
+            const uint32_t nx = blockIdx.x * 32u + l % 34u, ny = blockIdx.y * 8u + l / 34u;
+            s[l / 34u][l % 34u] = (nx < gsx && ny < gsy) ? NODE(NF_R + f, (size_t) ny * gsx + nx) : 0.0;
+        }
+        __syncthreads();
+        if (X < gsx && Y < gsy) {
+            double sum = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    sum += s[ty + jj][tx + ii];
+                }
+            cell[(size_t) f * ng + (size_t) Y * gsx + X] = sum;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_fluid_forces(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,7 +260,7 @@ k_fluid_velocity(double *__restrict__ pf, const uint8_t *__restrict__ active, co
 
 __global__ void __launch_bounds__(128)
 k_fluid_g2p(double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
-            const double *__restrict__ nf, uint32_t gsx, uint32_t gsy, double steps_left, double freedom_radius, uint64_t seed, uint64_t stepno) {
+            const double *__restrict__ nf, const double *__restrict__ cell, uint32_t gsx, uint32_t gsy, double steps_left, double freedom_radius, uint64_t seed, uint64_t stepno) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !active[i]) return;
     size_t ng = (size_t) gsx * gsy;
@@ -238,6 +268,14 @@ k_fluid_g2p(double *__restrict__ pf, const uint8_t *__restrict__ active, const u
     PW w;
     particle_weights(x, y, w);
     double gu = 0.0, gv = 0.0, nR = 0.0, nG = 0.0, nB = 0.0, nA = 0.0, weight = 0.0;
+    // the whole stencil inside the grid (always, away from the walls): the colour sums of the nine nodes come precomputed
+    // per base cell (k_fluid_colour_gather); a node without colour weight holds zeros, so the reference's `if (weight > 0)`
+    // per node changes nothing
+    const bool boxed = w.cx >= 0 && w.cy >= 0 && (uint32_t) w.cx + 2u < gsx && (uint32_t) w.cy + 2u < gsy;
+    if (boxed) {
+        const size_t cidx = (size_t) w.cy * gsx + (size_t) w.cx;
+        nR = cell[0 * ng + cidx]; nG = cell[1 * ng + cidx]; nB = cell[2 * ng + cidx]; nA = cell[3 * ng + cidx]; weight = cell[4 * ng + cidx];
+    }
     for (int ii = 0; ii < 3; ++ii)
         for (int jj = 0; jj < 3; ++jj) {
             uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
@@ -246,8 +284,10 @@ k_fluid_g2p(double *__restrict__ pf, const uint8_t *__restrict__ active, const u
             double phi = w.px[ii] * w.py[jj];
             gu += phi * NODE(NF_U, idx);
             gv += phi * NODE(NF_V, idx);
-            double nw = NODE(NF_W, idx);
-            if (nw > 0.0) { weight += nw; nR += NODE(NF_R, idx); nG += NODE(NF_G, idx); nB += NODE(NF_B, idx); nA += NODE(NF_A, idx); }
+            if (!boxed) {
+                double nw = NODE(NF_W, idx);
+                if (nw > 0.0) { weight += nw; nR += NODE(NF_R, idx); nG += NODE(NF_G, idx); nB += NODE(NF_B, idx); nA += NODE(NF_A, idx); }
+            }
         }
     if (weight > 0.0) {          // fluidmodel.cpp:476-498
         nR /= weight; nG /= weight; nB /= weight; nA /= weight;
@@ -307,7 +347,9 @@ int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
         k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_AX, NF_AY);
         k_fluid_velocity<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy);
         k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_U, NF_V);
-        k_fluid_g2p<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy, (double) steps_left, freedom_radius,
+        k_fluid_colour_gather<<<dim3(div_up(F->gx, 32), div_up(F->gy, 8)), 256, 0, E->stream>>>(F->nf, F->cell, F->gx, F->gy);
+        E->launches++;
+        k_fluid_g2p<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->cell, F->gx, F->gy, (double) steps_left, freedom_radius,
                                                           E->p.seed, F->step_counter++);
         E->launches += 6;
     }
