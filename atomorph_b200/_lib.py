@@ -40,6 +40,7 @@ def lib():
     sig("amx_last_error", C.c_char_p, vp)
     sig("amx_version", C.c_char_p)
     sig("amx_set_stream", i32, vp, vp)
+    sig("amx_get_stream", vp, vp)
     sig("amx_device_sync", i32, vp)
     sig("amx_set_param", i32, vp, i32, f64)
     sig("amx_get_param", f64, vp, i32)
@@ -78,6 +79,18 @@ def lib():
     sig("amx_pack_tiled", i32, vp, u32, u32, u64, u32, u32, vp, P(u64))
     sig("amx_unpack_tiled", i32, vp, u32, u32, u64, vp)
     sig("amx_cost", i32, vp, P(f64))
+    sig("amx_comm_unique_id", i32, vp)
+    sig("amx_comm_init", i32, vp, vp, u32, u32)
+    sig("amx_comm_destroy", i32, vp)
+    sig("amx_comm_enable_p2p", i32, vp)
+    sig("amx_comm_disable_p2p", i32, vp)
+    sig("amx_comm_info", i32, vp, vp)
+    sig("amx_comm_check", i32, vp)
+    sig("amx_table_broadcast", i32, vp, u32)
+    sig("amx_swap_part_step", i32, vp, u32, u32, u64, u32, u32)
+    sig("amx_swap_columns_step", i32, vp, i32, u32, u64, u32, u32)
+    sig("amx_swap_phase_count", u32, vp)
+    sig("amx_column_hash", i32, vp, u32, vp)
     sig("amx_render_prepare", i32, vp)
     sig("amx_render", i32, vp, vp, u32, vp, i32)
     sig("amx_render_blob", i32, vp, u32, f64, u64, vp, vp, P(C.c_int64), P(u64))
@@ -101,13 +114,13 @@ def lib():
 
 # every symbol include/amx.h declares (checked by tests/test_abi.py without a GPU)
 AMX_SYMBOLS = [
-    "amx_create", "amx_destroy", "amx_last_error", "amx_version", "amx_set_stream", "amx_device_sync",
+    "amx_create", "amx_destroy", "amx_last_error", "amx_version", "amx_set_stream", "amx_get_stream", "amx_device_sync",
     "amx_set_param", "amx_get_param", "amx_reset", "amx_set_canvas", "amx_set_frame_count", "amx_upload_frame",
     "amx_upload_frame_device", "amx_download_fetch", "amx_download_stored", "amx_step", "amx_next_state",
     "amx_get_state", "amx_get_energy", "amx_blobify", "amx_blob_count", "amx_export_blobs", "amx_import_blobs",
     "amx_match_init", "amx_match_rounds", "amx_match_energy", "amx_init_chains", "amx_chain_count",
     "amx_chain_info", "amx_export_chain", "amx_import_chains", "amx_table_device_ptr", "amx_swap_rounds",
-    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_swap_local_epoch", "amx_set_swap_locality", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_background",
+    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_swap_local_epoch", "amx_set_swap_locality", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_comm_unique_id", "amx_comm_init", "amx_comm_destroy", "amx_comm_enable_p2p", "amx_comm_disable_p2p", "amx_comm_info", "amx_comm_check", "amx_table_broadcast", "amx_swap_part_step", "amx_swap_columns_step", "amx_swap_phase_count", "amx_column_hash", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_background",
     "amx_fluid_create", "amx_fluid_set_particles", "amx_fluid_get_particles", "amx_fluid_step",
     "amx_fluid_get_nodes", "amx_launch_count", "amx_timer_start", "amx_timer_stop",
 ]

@@ -25,6 +25,7 @@ int engine_alloc_chains(Engine *E, uint32_t nchains, const uint64_t *keys, const
     // same geometry as before (a table re-import): every device buffer, the render buffers included, is kept
     const bool same = E->table && E->chain_of && E->d_chain_off && E->nchains == nchains && E->h == height && E->chain_off == offs;
     if (!same) {
+        engine_dist_table_gone(E);
         dev_free(E->table); dev_free(E->chain_of); dev_free(E->d_chain_off);
         E->table = nullptr; E->chain_of = nullptr; E->d_chain_off = nullptr;
         engine_render_free(E);

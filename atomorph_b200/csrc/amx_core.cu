@@ -35,6 +35,7 @@ static void free_frames(Engine *E) {
     E->frames.clear();
 }
 static void free_chains(Engine *E) {
+    engine_dist_table_gone(E);
     dev_free(E->table); E->table = nullptr;
     dev_free(E->chain_of); E->chain_of = nullptr;
     dev_free(E->d_chain_off); E->d_chain_off = nullptr;
@@ -104,6 +105,7 @@ void amx_destroy(amx_ctx *ctx) {
     Engine *E = &ctx->e;
     cudaSetDevice(E->device);
     reset_all(E);
+    engine_dist_free(E);
     dev_free(E->d_swapstats);
     dev_free(E->loc_buf); dev_free(E->loc_tmp);
     dev_free(E->d_out);
@@ -121,19 +123,25 @@ const char *amx_last_error(amx_ctx *ctx) { return ctx ? ctx->e.err.c_str() : "nu
 int amx_set_stream(amx_ctx *ctx, void *cuda_stream) {
     if (!ctx) return AMX_ERR_ARG;
     Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
-    if (cuda_stream == nullptr) {
+    if (cuda_stream == AMX_STREAM_PRIVATE) {
+        // back to a private non-blocking stream
         if (!E->own_stream) {
             if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) return AMX_ERR_CUDA;
             E->own_stream = true;
         }
         return AMX_OK;
     }
+    // NULL is a stream like any other: the legacy default stream (what torch.cuda.current_stream().cuda_stream is unless
+    // the caller entered a torch.cuda.stream context).  The engine's work is then ordered with everything else on it.
     if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);
     E->stream = (cudaStream_t) cuda_stream;
     E->own_stream = false;
     return AMX_OK;
 }
+
+void *amx_get_stream(amx_ctx *ctx) { return ctx ? (void *) ctx->e.stream : nullptr; }
 
 int amx_device_sync(amx_ctx *ctx) {
     if (!ctx) return AMX_ERR_ARG;

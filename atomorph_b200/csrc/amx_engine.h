@@ -71,6 +71,7 @@ struct Params {
 };
 
 struct Fluid;   // amx_fluid.cu
+struct Dist;    // amx_dist.cu
 
 struct Engine {
     int          device = 0;
@@ -179,6 +180,7 @@ struct Engine {
     unsigned  perlin_seed_loaded = 0xffffffffu;
 
     Fluid *fluid = nullptr;
+    Dist  *dist = nullptr;                 // communicator, exchange buffers and peer mappings of the multi-GPU matcher
 
     bool fail(cudaError_t e, const char *what);
     bool check(const char *what);
@@ -212,6 +214,8 @@ int engine_background(Engine *E, double t, uint32_t *out, int out_is_device);   
 void engine_render_free(Engine *E);
 int engine_render_fluid(Engine *E, double time, uint32_t f, double tl, const uint32_t *d_bg, uint32_t *d_dst);   // amx_fluiddraw.cu
 void engine_fluid_free(Engine *E);
+void engine_dist_table_gone(Engine *E);                                                     // amx_dist.cu
+void engine_dist_free(Engine *E);
 
 } // namespace amx
 

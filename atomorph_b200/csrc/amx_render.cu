@@ -121,6 +121,7 @@ __device__ __forceinline__ uint32_t ovf_slot(const Acc &ac, uint32_t mask, uint3
         }
         s = (s + 1) & mask;
     }
+    if (insert) atomicOr(ac.ovf_used, 0x80000000u);       // table exhausted: the entry is dropped, the host reports it
     return 0xffffffffu;
 }
 
@@ -1658,7 +1659,8 @@ static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32
     const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
     // persistent grid: as many blocks as stay resident (queried once per kernel instance)
 #define AMX_SCATTER(M, P, H) do { \
-        static int per_sm = 0; \
+        static int per_sm_dev[64] = {0}; \
+        int &per_sm = per_sm_dev[E->device & 63];                 /* occupancy is a property of the device: cached per device */ \
         if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
         const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
         k_scatter<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, make_abuf(E), st); } while (0)
@@ -1721,7 +1723,8 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     g_ktime.begin(E->stream);
     if (n_live > 0) {
 #define AMX_BIN(M, P, H) do { \
-        static int per_sm = 0; \
+        static int per_sm_dev[64] = {0}; \
+        int &per_sm = per_sm_dev[E->device & 63]; \
         if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
         const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
         k_bin<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
@@ -1742,8 +1745,8 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     RenderStats *st = (RenderStats *) E->d_render_stats;
     const dim3 grid(E->tb_tiles_x, E->tb_tiles_y, nb);
 #define AMX_TILE(S, C) do { \
-        static bool attr = false; \
-        if (!attr) { cudaFuncSetAttribute(k_tile<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T_SMEM_BYTES(S)); attr = true; } \
+        /* the opt-in is per device (several engines on several GPUs may live in one process): set it on every launch */ \
+        cudaFuncSetAttribute(k_tile<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T_SMEM_BYTES(S)); \
         k_tile<S, C><<<grid, 256, T_SMEM_BYTES(S), E->stream>>>(bn, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
     const bool single = E->nchains == 1, counted = rc.density > 1;
     g_ktime.begin(E->stream);
@@ -1923,11 +1926,13 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             return engine_render(E, times, n, out, out_is_device);
         }
     }
-    if (rcode == AMX_OK && E->nchains > 1 && !out_is_device && E->d_ovf_used) {
+    if (rcode == AMX_OK && E->nchains > 1 && E->d_ovf_used && rc.feather > 0) {
+        // the open-addressing table of (pixel, blob) entries ran full somewhere in this call: entries were dropped
         uint32_t used = 0;
-        cudaMemcpy(&used, E->d_ovf_used, 4, cudaMemcpyDeviceToHost);
+        if (E->fail(cudaMemcpyAsync(&used, E->d_ovf_used, 4, cudaMemcpyDeviceToHost, E->stream), "overflow counter") ||
+            E->fail(cudaStreamSynchronize(E->stream), "overflow counter")) return AMX_ERR_CUDA;
         cudaMemsetAsync(E->d_ovf_used, 0, 4, E->stream);
-        if ((uint64_t) used > (uint64_t) E->ovf_cap * n) { E->err = "overflow table exhausted"; rcode = AMX_ERR_NOMEM; }
+        if (used & 0x80000000u) { E->err = "per-(pixel, blob) overflow table exhausted: frame incomplete"; rcode = AMX_ERR_NOMEM; }
     }
     return rcode;
 }

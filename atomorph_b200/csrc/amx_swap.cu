@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "amx_engine.h"
+#include "amx_swap.h"
 
 namespace amx {
 
@@ -131,25 +132,22 @@ k_swap_multi(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
 }
 
 // ---- shared-memory tiled rounds -----------------------------------------------------------------------------
-#define TILE_BITS 10                       // 1024 atoms per tile: 16 KB (h = 2) / 24 KB (h >= 3) of shared memory
-#define TILE_ATOMS (1u << TILE_BITS)
-#define TILE_THREADS 256
-#define TILE_MAX_ROUNDS 64                 // rounds per epoch (one load / store of the tile)
-
-// Per-epoch bijection u -> atom on k-bit indices: two multiply / xorshift rounds (each step is invertible mod 2^k).
-// Tile t owns u in [t * TILE_ATOMS, (t + 1) * TILE_ATOMS): a pseudo-random subset of the chain.
-// Locality epochs (default off): `perm` lists the atoms in Morton order of their column-y position
-// (padding slots hold 0xffffffff) and slot u is atom perm[(u + shift) & mask], so a tile holds 1024 spatial neighbours.
-struct TileMap { uint32_t a1, a2, c, s1, s2, mask; const uint32_t *perm; uint32_t shift; };
 __host__ __device__ __forceinline__ uint32_t tile_atom(const TileMap &tm, uint32_t u) {
     if (tm.perm) return tm.perm[(u + tm.shift) & tm.mask];
+    if (tm.imask) {
+        uint32_t lo = ((u & tm.imask) * tm.ia1) & tm.imask;
+        lo ^= lo >> tm.is1;
+        lo = (lo * tm.ia2 + tm.ic) & tm.imask;
+        lo ^= lo >> tm.is2;
+        u = (u & ~tm.imask) | lo;
+    }
     uint32_t v = (u * tm.a1) & tm.mask;
     v ^= v >> tm.s1;
     v = (v * tm.a2 + tm.c) & tm.mask;
     v ^= v >> tm.s2;
     return v;
 }
-static TileMap make_tilemap(uint64_t seed, uint64_t stream, uint64_t epoch, unsigned k) {
+TileMap make_tilemap(uint64_t seed, uint64_t stream, uint64_t epoch, unsigned k) {
     TileMap tm;
     uint64_t r1 = rng64(seed, 0x7111u + stream, epoch), r2 = rng64(seed, 0x7222u + stream, epoch);
     tm.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
@@ -158,8 +156,19 @@ static TileMap make_tilemap(uint64_t seed, uint64_t stream, uint64_t epoch, unsi
     tm.c = (uint32_t) r2 & tm.mask;
     tm.s1 = std::max(1u, k / 2);
     tm.s2 = std::max(1u, (k + 1) / 2);
+    tm.ia1 = tm.ia2 = 1u; tm.ic = 0u; tm.is1 = tm.is2 = 1u; tm.imask = 0u;
     tm.perm = nullptr; tm.shift = 0u;
     return tm;
+}
+// inner bijection of the low `ik` bits for sub-epoch `sub` of a step
+void tilemap_set_inner(TileMap &tm, uint64_t seed, uint64_t stream, uint64_t sub, unsigned ik) {
+    uint64_t r1 = rng64(seed, 0x7333u + stream, sub), r2 = rng64(seed, 0x7444u + stream, sub);
+    tm.imask = ik >= 32 ? 0xffffffffu : ((1u << ik) - 1u);
+    tm.ia1 = ((uint32_t) r1 | 1u) & tm.imask;
+    tm.ia2 = ((uint32_t) (r1 >> 32) | 1u) & tm.imask;
+    tm.ic = (uint32_t) r2 & tm.imask;
+    tm.is1 = std::max(1u, ik / 2);
+    tm.is2 = std::max(1u, (ik + 1) / 2);
 }
 
 // key point in shared memory: x in 1/256 px (24 bits) | flags << 24 in the low word, y in 1/256 px in the high word
@@ -177,18 +186,20 @@ __device__ __forceinline__ unsigned long long kp_dist(uint2 a, uint2 b) {
     return (unsigned long long) ((long long) dx * (long long) dx) + (unsigned long long) ((long long) dy * (long long) dy);
 }
 
-// One CTA = one tile.  `rounds` rounds of TILE_ATOMS / 2 disjoint proposals each, all inside shared memory.
-// Slots whose atom index falls behind the chain (w not a power of two) are marked invalid and never proposed.
-template <bool H2>
-__global__ void __launch_bounds__(TILE_THREADS)
+// One CTA = one tile of 2^TB atoms, NT threads.  `rounds` rounds of 2^(TB-1) disjoint proposals each, all inside shared
+// memory.  Slots whose atom index falls behind the chain (w not a power of two) are marked invalid and never proposed.
+template <bool H2, int TB, int NT>
+__global__ void __launch_bounds__(NT)
 k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pword *__restrict__ next, uint64_t off, uint32_t w,
-             TileMap tm, uint32_t tile0, uint32_t rounds, uint64_t seed, uint64_t round_base, unsigned long long *__restrict__ stats) {
+             TileMap tm, uint32_t tile0, uint32_t rounds, uint64_t seed, uint64_t round_base, unsigned long long *__restrict__ stats,
+             PeerCols peers) {
+    constexpr uint32_t TA = 1u << TB;
     extern __shared__ uint2 sm[];
-    uint2 *s_col = sm, *s_next = sm + TILE_ATOMS, *s_prev = sm + 2 * TILE_ATOMS;     // s_prev only when !H2
+    uint2 *s_col = sm, *s_next = sm + TA, *s_prev = sm + 2 * TA;     // s_prev only when !H2
     const uint32_t tile = tile0 + blockIdx.x;
-    const uint32_t ubase = tile << TILE_BITS;
+    const uint32_t ubase = tile << TB;
     // load: atom index from the bijection (recomputed at write-back), invalid slots get flag byte 0xff
-    for (uint32_t j = threadIdx.x; j < TILE_ATOMS; j += TILE_THREADS) {
+    for (uint32_t j = threadIdx.x; j < TA; j += NT) {
         uint32_t a = tile_atom(tm, ubase + j);
         if (a < w) {
             s_col[j] = kp_unpack(col[off + a]);
@@ -198,10 +209,10 @@ k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
             s_col[j] = make_uint2(0xff000000u, 0u);
         }
     }
-    // pairing masks of the epoch's rounds inside this tile: uniform over the non-zero TILE_BITS-bit values
+    // pairing masks of the epoch's rounds inside this tile: uniform over the non-zero TB-bit values
     __shared__ uint32_t s_mask[TILE_MAX_ROUNDS];
-    for (uint32_t r = threadIdx.x; r < rounds; r += TILE_THREADS)
-        s_mask[r] = 1u + (uint32_t) (rng64(seed, 0x5157u + tile, round_base + r) % (TILE_ATOMS - 1u));
+    for (uint32_t r = threadIdx.x; r < rounds; r += NT)
+        s_mask[r] = 1u + (uint32_t) (rng64(seed, 0x5157u + tile, round_base + r) % (TA - 1u));
     __syncthreads();
     unsigned prop = 0, acc = 0;
     unsigned long long gain = 0;
@@ -210,8 +221,8 @@ k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
         const unsigned topbit = 31u - __clz(m);
         const uint32_t lowmask = (1u << topbit) - 1u;
 #pragma unroll
-        for (uint32_t q = 0; q < TILE_ATOMS / 2 / TILE_THREADS; ++q) {
-            const uint32_t t = q * TILE_THREADS + threadIdx.x;
+        for (uint32_t q = 0; q < TA / 2 / NT; ++q) {
+            const uint32_t t = q * NT + threadIdx.x;
             const uint32_t i = ((t & ~lowmask) << 1) | (t & lowmask);        // t with a zero inserted at m's top bit
             const uint32_t j = i ^ m;
             const uint2 a = s_col[i], b = s_col[j];
@@ -235,11 +246,30 @@ k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
         }
         __syncthreads();
     }
-    for (uint32_t j = threadIdx.x; j < TILE_ATOMS; j += TILE_THREADS) {
+    for (uint32_t j = threadIdx.x; j < TA; j += NT) {
         uint32_t a = tile_atom(tm, ubase + j);
-        if (a < w) col[off + a] = kp_pack(s_col[j]);
+        if (a < w) {
+            const pword word = kp_pack(s_col[j]);
+            col[off + a] = word;
+            for (uint32_t p = 0; p < peers.n; ++p) peers.col[p][off + a] = word;      // NVLink stores, fire and forget
+        }
     }
     warp_add_stats(stats, prop, acc, gain);
+}
+
+// launch one epoch's kernel for tiles [t0, t0 + ntl) of 2^tb atoms
+void launch_swap_tiled(Engine *E, bool h2, int tb, pword *col, const pword *prev, const pword *next, uint64_t off, uint32_t w, const TileMap &tm,
+                       uint32_t t0, uint32_t ntl, uint32_t rounds, uint64_t round_base, const PeerCols &peers) {
+    unsigned long long *st = (unsigned long long *) E->d_swapstats;
+    const size_t smem = (size_t) (h2 ? 2 : 3) * ((size_t) 1 << tb) * sizeof(uint2);
+#define AMX_SWT(H, TB, NT) do { \
+        cudaFuncSetAttribute(k_swap_tiled<H, TB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        k_swap_tiled<H, TB, NT><<<ntl, NT, smem, E->stream>>>(col, prev, next, off, w, tm, t0, rounds, E->p.seed, round_base, st, peers); } while (0)
+    if (tb == 10) { if (h2) AMX_SWT(true, 10, 256); else AMX_SWT(false, 10, 256); }
+    else if (tb == 9) { if (h2) AMX_SWT(true, 9, 256); else AMX_SWT(false, 9, 256); }
+    else { if (h2) AMX_SWT(true, 8, 128); else AMX_SWT(false, 8, 128); }
+#undef AMX_SWT
+    E->launches++;
 }
 
 // owned slots of an epoch <-> contiguous buffer (multi-GPU: rank r runs tiles [r * T / N, (r + 1) * T / N))
@@ -256,6 +286,17 @@ k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, ui
     if (i >= n) return;
     uint32_t a = tile_atom(tm, i);
     if (a < w) col[off + a] = in[i];
+}
+
+void launch_pack_tiled(Engine *E, const pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, pword *out) {
+    if (n == 0) return;
+    k_pack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, out);
+    E->launches++;
+}
+void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t n, const pword *in) {
+    if (n == 0) return;
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, n, in);
+    E->launches++;
 }
 
 // ---- multi-GPU atom-range sharding (h = 2: a single free column) ----------------------
@@ -336,10 +377,10 @@ k_cost(const pword *__restrict__ table, const uint32_t *__restrict__ chain_of, c
     }
 }
 
-static unsigned ceil_log2(uint64_t w) { unsigned k = 0; while ((1ull << k) < w) ++k; return k; }
+unsigned ceil_log2(uint64_t w) { unsigned k = 0; while ((1ull << k) < w) ++k; return k; }
 
 // true when the chain is long enough for the shared-memory tiled path
-static bool tiled_ok(Engine *E, uint32_t chain) {
+bool tiled_ok(Engine *E, uint32_t chain) {
     uint64_t w = E->chain_off[chain + 1] - E->chain_off[chain];
     return w >= 4ull * TILE_ATOMS && w <= 0x80000000ull;
 }
@@ -359,21 +400,12 @@ int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
     pword *col = E->table + (size_t) y * E->A;
     const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
     const bool h2 = E->h == 2;
-    const size_t smem = (size_t) (h2 ? 2 : 3) * TILE_ATOMS * sizeof(uint2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_swap_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_ATOMS * (int) sizeof(uint2));
-        cudaFuncSetAttribute(k_swap_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_ATOMS * (int) sizeof(uint2));
-        attr_set = true;
-    }
-    unsigned long long *st = (unsigned long long *) E->d_swapstats;
+    PeerCols nopeers; nopeers.n = 0;
     // more than TILE_MAX_ROUNDS rounds: further launches on the SAME tiles (same bijection) with fresh pairing masks
     for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
         const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
         const uint64_t round_base = (epoch << 20) + done;
-        if (h2) k_swap_tiled<true><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, r, E->p.seed, round_base, st);
-        else    k_swap_tiled<false><<<t1 - t0, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, t0, r, E->p.seed, round_base, st);
-        E->launches++;
+        launch_swap_tiled(E, h2, TILE_BITS, col, prev, next, off, (uint32_t) w, tm, t0, t1 - t0, r, round_base, nopeers);
     }
     E->render_ready = false;
     return E->check("tiled swap epoch") ? AMX_ERR_CUDA : AMX_OK;
@@ -423,17 +455,12 @@ int engine_swap_local_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
     const uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
     const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
     const bool h2 = E->h == 2;
-    const size_t smem = (size_t) (h2 ? 2 : 3) * TILE_ATOMS * sizeof(uint2);
-    cudaFuncSetAttribute(k_swap_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_ATOMS * (int) sizeof(uint2));
-    cudaFuncSetAttribute(k_swap_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_ATOMS * (int) sizeof(uint2));
-    unsigned long long *st = (unsigned long long *) E->d_swapstats;
+    PeerCols nopeers; nopeers.n = 0;
     // the positions move while the tiles are refined: the order is rebuilt per epoch, further launches reuse it
     for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
         const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
         const uint64_t round_base = (epoch << 20) + done + (1ull << 19);
-        if (h2) k_swap_tiled<true><<<ntiles, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, 0u, r, E->p.seed, round_base, st);
-        else    k_swap_tiled<false><<<ntiles, TILE_THREADS, smem, E->stream>>>(col, prev, next, off, (uint32_t) w, tm, 0u, r, E->p.seed, round_base, st);
-        E->launches++;
+        launch_swap_tiled(E, h2, TILE_BITS, col, prev, next, off, (uint32_t) w, tm, 0u, ntiles, r, round_base, nopeers);
     }
     E->render_ready = false;
     return E->check("locality swap epoch") ? AMX_ERR_CUDA : AMX_OK;

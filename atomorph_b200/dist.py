@@ -1,14 +1,18 @@
 """Multi-GPU partitioning of the morph path: one process per GPU, launched with
-torchrun; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
+torchrun.  Every collective of the path is issued by the LIBRARY (atomorph_b200/csrc/amx_dist.cu) on the
+engine's own stream; `torch.distributed` is only used to hand the NCCL unique id to the ranks, for barriers
+and for reducing timings (gloo in the CPU tests).
 
 * rendering      : output frames are independent -> contiguous frame range per rank, no collective
-* matching, h>=4 : key-frame columns of equal parity are independent given frozen neighbours ->
-                   rank g owns columns {j : (j // 2) % G == g} of the current parity; after each
-                   half-sweep the updated columns are all-gathered
-* matching, h=2  : a single free column -> ATOM-range sharding: an epoch selects log2(G) index bits,
-                   rank r owns the atoms whose selected bits equal r and draws pairing masks that are
-                   zero on those bits; after the epoch the owned slices are exchanged with ONE
-                   all-gather of the per-atom trajectory-table column (the only collective)
+* matching, h>=3 : key-frame columns of one PHASE (even / odd / last column of an odd cycle) are independent
+                   given frozen neighbours -> rank g refines every G-th column of the phase, then the refined
+                   columns go to every replica (amx_swap_columns_step)
+* matching, h=2  : a single free column -> the ATOMS are split: a per-step bijection of the atom index gives
+                   rank r a pseudo-random 1/G of the atoms, which it refines for several re-tiled epochs in
+                   shared memory; then the parts are exchanged (amx_swap_part_step)
+
+The exchange is either written through peer-mapped replicas from inside the swap kernel (P2P over NVLink,
+amx_comm_enable_p2p) or pack -> ncclAllGather -> unpack / ncclBroadcast, both on the engine's stream.
 
 The index arithmetic (which atoms a rank owns, how the gathered buffers map back) is mirrored here in
 numpy so that the world_size-2 gloo tests can check it without a GPU.
@@ -38,13 +42,23 @@ def frame_times(total_frames, rank, world, finite=False, key_frames=2):
     return np.array(out, dtype=np.float64)
 
 
-# ------------------------------------------------------------------ column ownership (h >= 4)
-def owned_columns(height, parity, rank, world):
-    """Columns of `parity` (0 = even, 1 = odd) that `rank` refines in this half-sweep."""
-    cols = [j for j in range(height) if j % 2 == parity]
-    if height % 2 == 1 and parity == 0:
-        cols = cols[:-1]          # odd cycle: the last even column neighbours column 0 -> refine it with the odd ones
-    return [j for i, j in enumerate(cols) if i % world == rank]
+# ------------------------------------------------------------------ column ownership (h >= 3)
+def phase_count(height):
+    """Half-sweeps of a cycle of `height` key-frame columns (amx_swap_phase_count)."""
+    return 0 if height < 2 else (3 if height % 2 else 2)
+
+
+def phase_columns(height, phase):
+    """Columns refined together in `phase`: 0 = even, 1 = odd, 2 = the last column of an odd cycle (it neighbours
+    column 0, so it cannot join the even ones)."""
+    if phase == 2:
+        return [height - 1] if height % 2 and height >= 3 else []
+    return [j for j in range(phase, height, 2) if not (phase == 0 and height % 2 and height >= 3 and j == height - 1)]
+
+
+def owned_columns(height, phase, rank, world):
+    """Columns of `phase` that `rank` refines (every world-th one, amx_swap_columns_step)."""
+    return [j for i, j in enumerate(phase_columns(height, phase)) if i % world == rank]
 
 
 # ------------------------------------------------------------------ atom-range ownership (h = 2)
@@ -133,60 +147,99 @@ def tiled_supported(width):
     return width >= 4 * (1 << TILE_BITS)
 
 
+# ------------------------------------------------------------------ parts of a step (amx_dist.cu: engine_swap_part_step)
+def _affine_xorshift(u, k, r1, r2):
+    mask = (1 << k) - 1 if k < 32 else 0xffffffff
+    a1 = ((r1 & 0xffffffff) | 1) & mask
+    a2 = (((r1 >> 32) & 0xffffffff) | 1) & mask
+    c = (r2 & 0xffffffff) & mask
+    s1, s2 = max(1, k // 2), max(1, (k + 1) // 2)
+    v = (u * np.uint64(a1)) & np.uint64(mask)
+    v ^= v >> np.uint64(s1)
+    v = (v * np.uint64(a2) + np.uint64(c)) & np.uint64(mask)
+    v ^= v >> np.uint64(s2)
+    return v
+
+
+def part_slots(width, seed, chain, step):
+    """Atom index of every slot u in [0, 2^k) of a step's OUTER bijection.  Rank r of n owns the contiguous slot
+    range [r 2^k / n, (r + 1) 2^k / n): a pseudo-random 1/n of the atoms (slots whose atom is >= width are padding)."""
+    k = max(1, int(width - 1).bit_length())
+    st = 0x100 + chain
+    u = np.arange(1 << k, dtype=np.uint64)
+    return _affine_xorshift(u, k, _rng64(seed, 0x7111 + st, step), _rng64(seed, 0x7222 + st, step))
+
+
+def part_tile_atoms(width, seed, chain, step, sub, rank, world):
+    """Atoms of rank `rank` in sub-epoch `sub` of `step`, in tile order (consecutive runs of 2^tb are one tile): the
+    INNER bijection re-tiles the rank's slot range, the outer one names the atoms."""
+    k = max(1, int(width - 1).bit_length())
+    s = int(world).bit_length() - 1
+    kk = k - s
+    st = 0x100 + chain
+    lo = np.arange(1 << kk, dtype=np.uint64)
+    sub_id = step * 4096 + sub
+    lo = _affine_xorshift(lo, kk, _rng64(seed, 0x7333 + st, sub_id), _rng64(seed, 0x7444 + st, sub_id))
+    u = (np.uint64(rank) << np.uint64(kk)) | lo
+    return part_slots(width, seed, chain, step)[u.astype(np.int64)]
+
+
 # ------------------------------------------------------------------ device orchestration
-class ShardedMatcher:
-    """Atom-range sharded pair-swap rounds for a single-chain, h = 2 morph (BASELINE config 2)."""
-
-    def __init__(self, engine, rank, world, device=None, seed=0):
-        import torch
-        self.torch = torch
-        self.e, self.rank, self.world, self.seed = engine, rank, world, seed
-        self.width = engine.table_device_ptr(0)[1]
-        self.epoch = 0
-        k = max(1, int(self.width - 1).bit_length())
-        s = world.bit_length() - 1
-        self.slots = 1 << (k - s)
-        self.device = device
-        self.send = torch.empty(self.slots, dtype=torch.int64, device=device)
-        self.recv = torch.empty(self.slots * world, dtype=torch.int64, device=device)
-        ntiles = (1 << k) >> TILE_BITS
-        self.tiled = tiled_supported(self.width) and ntiles % world == 0
-
-    def run_epoch(self, rounds, column=1):
-        """`rounds` sharded rounds on `column`, then one all-gather of that column."""
-        import torch.distributed as dist
-        if self.world == 1:
-            self.e.swap_rounds(rounds, chain=0, column=column, want_stats=False)
-            return
-        if self.tiled:
-            # long chain: every rank refines its share of the epoch's shared-memory tiles, then the owned slots travel
-            ep = self.epoch
-            self.epoch += 1
-            self.e.swap_tiled_epoch(ep, rounds, column, rank=self.rank, nranks=self.world)
-            n = self.e.pack_tiled(ep, column, self.rank, self.world, self.send.data_ptr())
-            assert n == self.slots
-            dist.all_gather_into_tensor(self.recv, self.send)      # NCCL over NVLink: W*8 B per epoch
-            self.e.unpack_tiled(ep, column, self.recv.data_ptr())
-            return
-        mask = select_mask(self.width, self.world, self.epoch, self.seed)
-        self.epoch += 1
-        sel_val = int(deposit_bits(np.array([self.rank]), mask)[0])
-        self.e.swap_rounds_sharded(rounds, mask, sel_val, chain=0, column=column)
-        self.e.pack_owned(column, mask, sel_val, self.send.data_ptr())
-        dist.all_gather_into_tensor(self.recv, self.send)          # NCCL over NVLink: W*8 B per epoch
-        self.e.unpack_owned(column, mask, self.world, self.recv.data_ptr())
-
-
-def broadcast_table(engine, rank, world, device):
-    """Replicate rank 0's chain table on every rank (one-time, before rendering)."""
+def init_comm(engine, rank, world, device=None):
+    """Join the library's NCCL communicator: rank 0 creates the unique id, torch.distributed carries it."""
     import torch
     import torch.distributed as dist
     if world == 1:
         return
-    chains = engine.chains()
-    for c in chains:
-        t = torch.from_numpy(c["words"].astype(np.int64)).to(device)
-        dist.broadcast(t, src=0)
-        c["words"] = t.cpu().numpy().astype(np.uint64)
-    if rank != 0:
-        engine.import_chains(chains)
+    ident = engine.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    t = torch.from_numpy(ident.copy())
+    if device is not None and dist.get_backend() == "nccl":
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    engine.comm_init(t.cpu().numpy(), rank, world)
+
+
+class ShardedMatcher:
+    """The sharded pair-swap matcher: a thin caller of amx_swap_part_step (h = 2) / amx_swap_columns_step (h >= 3).
+    Pack, collective and unpack (or the P2P write-through and its flag barrier) all run inside the library on the
+    engine's stream -- nothing here touches a stream."""
+
+    def __init__(self, engine, rank, world, device=None, seed=0, p2p=True):
+        self.e, self.rank, self.world = engine, rank, world
+        self.step = 0
+        self.p2p = False
+        if world > 1:
+            if engine.comm_info()["nranks"] != world:
+                init_comm(engine, rank, world, device)
+            self.p2p = bool(p2p) and engine.comm_enable_p2p()
+
+    def run_step(self, sub_epochs=None, rounds=64, column=1, chain=0):
+        """h = 2: one step on `column` -- every rank refines its 1/world of the atoms for `sub_epochs` (default: world)
+        re-tiled epochs of `rounds` rounds, then the parts are exchanged.  Weak-scaling unit: a rank proposes
+        sub_epochs * rounds * (W / world) / 2 pairs per step, the same at every world size when sub_epochs = world."""
+        sub = self.world if sub_epochs is None else int(sub_epochs)
+        self.e.swap_part_step(self.step, sub, rounds, column=column, chain=chain)
+        self.step += 1
+
+    def run_sweep(self, epochs=1, rounds=64, chain=-1):
+        """h >= 3: one sweep = every phase once (each column refined for epochs * rounds rounds by its owner)."""
+        for phase in range(self.e.swap_phase_count()):
+            self.e.swap_columns_step(phase, self.step, epochs, rounds, chain=chain)
+        self.step += 1
+
+    # kept for callers of the round-1 interface
+    def run_epoch(self, rounds, column=1):
+        left = int(rounds)
+        while left > 0:
+            r = min(left, 64)
+            self.run_step(sub_epochs=1, rounds=r, column=column)
+            left -= r
+
+
+def broadcast_table(engine, rank, world, device=None):
+    """Replicate rank 0's chain table on every rank (one ncclBroadcast inside the library)."""
+    if world == 1:
+        return
+    if engine.comm_info()["nranks"] != world:
+        init_comm(engine, rank, world, device)
+    engine.table_broadcast(0)

@@ -82,6 +82,9 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.amx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
+    def get_stream(self):
+        return self.L.amx_get_stream(self.h) or 0
+
     def sync(self):
         self._ck(self.L.amx_device_sync(self.h), "sync")
 
@@ -273,6 +276,61 @@ class Engine:
 
     def unpack_tiled(self, epoch, column, d_in_ptr, chain=0):
         self._ck(self.L.amx_unpack_tiled(self.h, chain, column, int(epoch), C.c_void_p(d_in_ptr)), "unpack_tiled")
+
+    # ---- multi-GPU matcher (amx_dist.cu): every collective is issued by the library on the engine's stream
+    @staticmethod
+    def comm_unique_id():
+        ident = np.zeros(128, dtype=np.uint8)
+        rc = _lib.lib().amx_comm_unique_id(_p(ident))
+        if rc != 0:
+            raise AmxError("amx_comm_unique_id: %s (is libnccl.so.2 loadable?)" % _lib.STATUS.get(rc, rc))
+        return ident
+
+    def comm_init(self, ident, rank, nranks):
+        ident = np.ascontiguousarray(ident, dtype=np.uint8)
+        assert ident.size == 128
+        self._ck(self.L.amx_comm_init(self.h, _p(ident), int(rank), int(nranks)), "comm_init")
+
+    def comm_destroy(self):
+        self._ck(self.L.amx_comm_destroy(self.h), "comm_destroy")
+
+    def comm_enable_p2p(self):
+        """Collective.  True when every rank mapped every replica (write-through exchange), False when the box does not
+        allow peer mapping (the NCCL exchange stays in use)."""
+        rc = self.L.amx_comm_enable_p2p(self.h)
+        if rc == 3:      # AMX_ERR_STATE
+            return False
+        self._ck(rc, "comm_enable_p2p")
+        return True
+
+    def comm_disable_p2p(self):
+        self._ck(self.L.amx_comm_disable_p2p(self.h), "comm_disable_p2p")
+
+    def comm_info(self):
+        out = np.zeros(3, dtype=np.uint32)
+        self._ck(self.L.amx_comm_info(self.h, _p(out)), "comm_info")
+        return dict(rank=int(out[0]), nranks=int(out[1]), p2p=bool(out[2]))
+
+    def comm_check(self):
+        self._ck(self.L.amx_comm_check(self.h), "comm_check")
+
+    def table_broadcast(self, root=0):
+        self._ck(self.L.amx_table_broadcast(self.h, int(root)), "table_broadcast")
+
+    def swap_part_step(self, step, sub_epochs, rounds, column=1, chain=0):
+        self._ck(self.L.amx_swap_part_step(self.h, int(chain), int(column), int(step), int(sub_epochs), int(rounds)), "swap_part_step")
+
+    def swap_columns_step(self, phase, step, epochs, rounds, chain=-1):
+        self._ck(self.L.amx_swap_columns_step(self.h, int(chain), int(phase), int(step), int(epochs), int(rounds)), "swap_columns_step")
+
+    def swap_phase_count(self):
+        return int(self.L.amx_swap_phase_count(self.h))
+
+    def column_hash(self, column):
+        """(position-dependent hash, multiset hash) of one key-frame column of the table."""
+        out = np.zeros(2, dtype=np.uint64)
+        self._ck(self.L.amx_column_hash(self.h, int(column), _p(out)), "column_hash")
+        return int(out[0]), int(out[1])
 
     def swap_stats(self):
         st = np.zeros(3, dtype=np.uint64)

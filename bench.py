@@ -32,7 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SWAP_ROUNDS = 256         # rounds per step = per exchange on N > 1 GPUs (4 tiled launches of 64 rounds on the same tiles)
+SWAP_EPOCHS = 4           # matcher steps per timed step; one matcher step = `world` re-tiled epochs of 64 rounds on the rank's part + 1 exchange
+SWAP_ROUNDS = 64 * SWAP_EPOCHS
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -92,6 +93,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned buffer is allocated: page-locked
+    memory is placed on the node of the allocating thread, and a frame read back over PCIe into the other socket's
+    memory crosses the inter-socket link.  Returns a short description for the bench line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for %s" % bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as ex:
+        return {"numa_node": None, "note": "not bound: %r" % (ex,)}
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -137,24 +161,35 @@ def reference_tables(size, images):
     return [dict(key=0, words=np.stack(cols), max_surface=W)], blobs
 
 
-def cpu_reference_numbers(m, frames, frame_budget_s=25.0, morph_steps=16):
+def cpu_reference_numbers(m, frames, frame_budget_s=25.0, morph_steps=16, gpu_render=None):
     """Times the reference's own CPU path: get_pixels(t) on one thread (the reference renderer is
-    single-threaded) and thread::morph() with all host threads."""
+    single-threaded) and thread::morph() with all host threads.  The frames it renders are compared with the
+    GPU's frames at the same times on the same chain table (gpu_render(t) -> packed RGBA image)."""
     from oracle import amref
     cores = amref.hardware_concurrency()
     # render: frames until the budget is used (at least one)
     t_used, n = 0.0, 0
+    parity = {"frames": 0, "max_lsb": 0, "px_diff": 0, "pixels": 0}
     while n < frames and (n == 0 or t_used < frame_budget_s):
-        dt, _ = m.time_render(n / float(frames))
+        # spread the sampled frames over the morph (0, 1/2, 1/4, 3/4, ... of it) instead of its first frames only
+        k = [0, frames // 2, frames // 4, (3 * frames) // 4, frames // 8, (5 * frames) // 8][n] if n < 6 and frames >= 8 else n
+        dt, ref = m.time_render(k / float(frames))
         t_used += dt
         n += 1
+        if gpu_render is not None:
+            got = gpu_render(k / float(frames))
+            d = np.abs(amref.unpack_rgba(ref).astype(np.int16) - amref.unpack_rgba(got).astype(np.int16))
+            parity["frames"] += 1
+            parity["max_lsb"] = max(parity["max_lsb"], int(d.max()))
+            parity["px_diff"] += int((d.max(axis=-1) != 0).sum())
+            parity["pixels"] += int(ref.size)
     fps = n / t_used
     m.set(threads=cores, cycle_length=100000)
     m.sync()
     dt = m.time_morph_steps(morph_steps)
     pps = morph_steps * max(1, cores) * 100000 / dt
     m.sync()
-    return dict(fps=fps, frames=n, render_s=t_used, pps=pps, cores=int(cores), morph_s=dt)
+    return dict(fps=fps, frames=n, render_s=t_used, pps=pps, cores=int(cores), morph_s=dt, parity=parity)
 
 
 def run_reference(args):
@@ -212,14 +247,13 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank)
     peak, peak_kind = measured_peak()
 
     size, F = args.size, args.frames
     params = dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=100000)
     images = scenes.square_to_disc(size)
-    e = eng.Engine(local_rank, **params)
-    stream = torch.cuda.current_stream()
-    e.set_stream(stream.cuda_stream)
+    e = eng.Engine(local_rank, **params)          # private non-blocking stream: every kernel, copy AND collective of the engine runs on it
     e.load_images(images)
     e.step(8)                                     # blobify -> unify -> match -> init chains (all on device)
     assert e.state() == eng.STATE_ATOM_MORPHING
@@ -250,13 +284,15 @@ def run_b200(args):
 
     from atomorph_b200 import dist as amd
     if world > 1:
-        amd.broadcast_table(e, rank, world, dev)                 # every rank renders / refines the same table
+        amd.broadcast_table(e, rank, world, dev)                 # every rank renders / refines the same table (ncclBroadcast in the library)
         e.render_prepare()
-    matcher = amd.ShardedMatcher(e, rank, world, device=dev, seed=1)
+    matcher = amd.ShardedMatcher(e, rank, world, device=dev, seed=1, p2p=os.environ.get("AMX_DIST_NCCL") is None)
 
     def swap_step():
-        # weak scaling: every rank proposes SWAP_ROUNDS * W/2 pairs per step on its atom slice, then ONE all-gather
-        matcher.run_epoch(SWAP_ROUNDS * world, column=1)
+        # weak scaling: per step every rank refines its 1/world of the atoms for `world` re-tiled epochs of 64 rounds
+        # (= SWAP_ROUNDS/... proposals per rank as on one GPU), then ONE exchange of the column, issued by the library
+        for _ in range(SWAP_EPOCHS):
+            matcher.run_step(sub_epochs=world, rounds=64, column=1)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -286,9 +322,30 @@ def run_b200(args):
     timed(render_step, max(1, min(args.steps, 3)), 1)
     ktimes = e.kernel_times(False)                  # [k_bin, k_tile]
     timed.launches = counted                        # (the diagnostic pass is not part of the timed region)
+    # invariants of the sharded matcher, checked on every run at every N: each column stays the same multiset of key
+    # points, the cost never rises (thread.cpp:1014-1038), and all replicas of the table are identical afterwards
+    h = 2
+    hash_before = [e.column_hash(j) for j in range(h)]
+    cost_before = e.cost()
     st0 = e.swap_stats()
     ms_swap = timed(swap_step, args.steps, args.warmup)
     st1 = e.swap_stats()
+    if world > 1:
+        e.comm_check()
+    cost_after = e.cost()
+    hash_after = [e.column_hash(j) for j in range(h)]
+    same_multiset = all(a[1] == b[1] for a, b in zip(hash_before, hash_after))
+    cost_monotone = cost_after <= cost_before
+    replicas_equal = True
+    if world > 1:
+        hv = torch.tensor([[v[0] >> 32, v[0] & 0xffffffff] for v in hash_after] + [[int(same_multiset), int(cost_monotone)]],
+                          dtype=torch.int64, device=dev).reshape(-1)
+        lo, hi = hv.clone(), hv.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_equal = bool(torch.equal(lo[:-2], hi[:-2]))
+        same_multiset, cost_monotone = bool(lo[-2]), bool(lo[-1])
+    e.render_prepare()                              # the e2e / parity legs below render the table the swap steps left
     clocks = sampler.stop()
     launches = timed.launches
     proposals = int(st1[0] - st0[0]) * args.steps // (args.steps + args.warmup)
@@ -304,9 +361,20 @@ def run_b200(args):
     h2d = sum(c["words"].nbytes for c in chain_words)
     d2h = F * P * 4
 
-    def e2e_step():
-        e.import_chains(chain_words)
-        e.render_into(times, host_out.data_ptr(), False)
+    parts = {"h2d_table": 0.0, "render_prepare": 0.0, "render_and_d2h": 0.0}
+
+    def e2e_step(record=False):
+        t0 = time.perf_counter()
+        e.import_chains(chain_words)                # H2D of the step's input (the trajectory table), synchronous
+        t1 = time.perf_counter()
+        e.render_prepare()                          # per-table sort + gather of the render inputs
+        t2 = time.perf_counter()
+        e.render_into(times, host_out.data_ptr(), False)   # render; frames travel D2H on a second stream while later batches render
+        t3 = time.perf_counter()
+        if record:
+            parts["h2d_table"] += t1 - t0
+            parts["render_prepare"] += t2 - t1
+            parts["render_and_d2h"] += t3 - t2
 
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -314,9 +382,14 @@ def run_b200(args):
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        e2e_step()
+        e2e_step(True)
     barrier()
     s_e2e = time.perf_counter() - t0
+    e2e_parts = [1000.0 * parts[k] / e2e_steps for k in ("h2d_table", "render_prepare", "render_and_d2h")]
+    if world > 1:
+        tp = torch.tensor(e2e_parts, dtype=torch.float64, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_parts = [float(v) for v in tp]
 
     # max over ranks
     if world > 1:
@@ -370,11 +443,15 @@ def run_b200(args):
                               "traffic": None, "kernel": "k_swap_tiled", "bytes_per_unit": swap_bytes, "unit_name": "proposal",
                               "note": "tiles of 2048 atoms are refined for 64 rounds in shared memory per load: the algorithmic 32 B/proposal "
                                       "are served from shared memory, not DRAM (DRAM traffic is ~24 B per atom per 64 rounds)"}},
-        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step_max_over_ranks": {"h2d_table": e2e_parts[0], "render_prepare": e2e_parts[1], "render_and_d2h": e2e_parts[2]},
+                "d2h_gbs_per_gpu": d2h / (e2e_parts[2] / 1000.0) / 1e9 if e2e_parts[2] > 0 else None, "host_numa": numa},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "render_stats": dict(e.render_stats(), path_frames=e.render_path_frames(), tiled=e.render_tiled_stats()),
-        "match": {"rounds": int(args.match_rounds), "proposals_per_atom": args.match_rounds / 2.0, "cost_initial": cost0, "cost_matched": cost1},
+        "match": {"rounds": int(args.match_rounds), "proposals_per_atom": args.match_rounds / 2.0, "cost_initial": cost0, "cost_matched": cost1,
+                  "cost_after_swap_steps": cost_after, "cost_monotone": cost_monotone, "columns_same_multiset": same_multiset, "replicas_equal": replicas_equal,
+                  "exchange": ("p2p write-through + flag barrier" if matcher.p2p else "pack + ncclAllGather + unpack") if world > 1 else "none"},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -388,7 +465,9 @@ def run_b200(args):
                     blobs.append([dict(group=int(meta[0, 0]), stats=stats[0],
                                        surface=(ys.astype(np.uint64) * np.uint64(65536) + xs.astype(np.uint64)))])
                 m = build_reference(size, images, chain_words, blobs, dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE))
-                cpu = cpu_reference_numbers(m, F)
+                cpu = cpu_reference_numbers(m, F, gpu_render=lambda t: e.render([t])[0])
+                # full-size parity: the reference's frames against the GPU's at the same t on the same table (north star: bit-exact or <= 1 LSB)
+                line["parity"] = dict(cpu["parity"], against="am::morph::get_pixels of oracle/_ref on the same chain table, %dx%d" % (size, size))
                 line["cpu_baseline"] = {"value": cpu["fps"], "unit": "frames/s", "cores": 1, "kind": "reference",
                                         "sample": "%d of %d frames via am::morph::get_pixels on the same chain table (single-threaded renderer, %.1f s)"
                                                   % (cpu["frames"], F, cpu["render_s"]),

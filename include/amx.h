@@ -45,8 +45,12 @@ int  amx_create(amx_ctx **out, int device);
 void amx_destroy(amx_ctx *ctx);
 const char *amx_last_error(amx_ctx *ctx);
 const char *amx_version(void);                                   /* am::get_version, atomorph.cpp:1013 */
-/* Use an externally owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream. */
+/* Run every kernel / copy of this context on an externally owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream).
+ * NULL (0) is taken literally: the legacy default stream.  AMX_STREAM_PRIVATE returns to the private non-blocking stream
+ * the context was created with.  amx_get_stream returns the stream in use (cudaStream_t). */
+#define AMX_STREAM_PRIVATE ((void *) (intptr_t) -1)
 int  amx_set_stream(amx_ctx *ctx, void *cuda_stream);
+void *amx_get_stream(amx_ctx *ctx);
 int  amx_device_sync(amx_ctx *ctx);
 
 /* ---- parameters: one id per setter, morph.h:52-76, pushed like synchronize() morph.cpp:105-120 */
@@ -132,6 +136,43 @@ int  amx_set_swap_locality(amx_ctx *ctx, uint32_t every);
 int  amx_pack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, uint32_t rank, uint32_t nranks, void *d_out, uint64_t *count);
 int  amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epoch, const void *d_in);
 int  amx_cost(amx_ctx *ctx, double *cost);                       /* thread::get_energy(chain*), thread.cpp:1109-1125, summed over chains */
+
+/* ---- multi-GPU matcher: one process (context) per GPU; the all-gather of trajectory-table columns
+ *      is the only collective of the path and is issued by the library itself, on the context's stream -----------------
+ * amx_comm_unique_id: rank 0 creates the id, the caller hands it to every rank (any transport: MPI, torch.distributed, a
+ * file).  amx_comm_init joins the NCCL communicator (libnccl.so.2 is dlopen'ed on first use).  amx_comm_enable_p2p
+ * (collective, after every rank holds a table of the same geometry) maps the table replicas into each other with
+ * cudaIpc: from then on a step's refined tiles are written into every replica from inside the swap kernel over
+ * NVLink and a flag barrier in peer memory closes the step -- no collective call at all.  It returns AMX_ERR_STATE and
+ * leaves the NCCL exchange in place when peer mapping is not permitted.  Replacing the table (amx_import_chains with
+ * another geometry, amx_init_chains, amx_reset) drops the mappings; call amx_comm_enable_p2p again.
+ * amx_comm_info: [0] rank, [1] ranks, [2] 1 when the P2P exchange is active.  amx_comm_check: AMX_ERR_STATE when a peer
+ * never arrived at a flag barrier (its process died): the replicas may differ from then on. */
+#define AMX_UNIQUE_ID_BYTES 128
+int  amx_comm_unique_id(uint8_t id[AMX_UNIQUE_ID_BYTES]);
+int  amx_comm_init(amx_ctx *ctx, const uint8_t id[AMX_UNIQUE_ID_BYTES], uint32_t rank, uint32_t nranks);
+int  amx_comm_destroy(amx_ctx *ctx);
+int  amx_comm_enable_p2p(amx_ctx *ctx);
+int  amx_comm_disable_p2p(amx_ctx *ctx);
+int  amx_comm_info(amx_ctx *ctx, uint32_t info3[3]);
+int  amx_comm_check(amx_ctx *ctx);
+/* rank `root`'s table replaces everybody's (collective; before rendering / refining the same morph on every GPU) */
+int  amx_table_broadcast(amx_ctx *ctx, uint32_t root);
+/* h == 2 (a single free column): one STEP of the sharded matcher on `column` of `chain` -- morph_asynch, thread.cpp:990-1041,
+ * over the N ranks.  A bijection of the atom index drawn from (seed, chain, step) gives rank r a pseudo-random 1/N of the
+ * atoms; the rank refines its part for `sub_epochs` epochs (each re-tiling the part) of `rounds` (<= 64) rounds, then the
+ * parts are exchanged (P2P write-through or pack -> ncclAllGather -> unpack).  Same call, same arguments on every rank.
+ * With one rank (no communicator) it is `sub_epochs` ordinary epochs. */
+int  amx_swap_part_step(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t step, uint32_t sub_epochs, uint32_t rounds);
+/* h >= 3: the key-frame columns of one PHASE are refined concurrently, every N-th one on this rank, their neighbour
+ * columns frozen (the objective couples column j to j-1 and j+1 only, thread.cpp:1007-1020); then the refined columns go
+ * to every replica.  Phases: 0 = even columns, 1 = odd columns, 2 = the last column of an odd cycle (it neighbours
+ * column 0); amx_swap_phase_count = 2 or 3.  chain < 0: every chain.  `epochs` x `rounds` rounds per owned column. */
+int  amx_swap_columns_step(amx_ctx *ctx, int32_t chain, uint32_t phase, uint64_t step, uint32_t epochs, uint32_t rounds);
+uint32_t amx_swap_phase_count(amx_ctx *ctx);
+/* invariants of a sharded step: out2[0] = position-dependent hash of a column (equal on two ranks <=> same column),
+ * out2[1] = position-independent hash (unchanged <=> still the same multiset of key points, thread.cpp:1023-1038) */
+int  amx_column_hash(amx_ctx *ctx, uint32_t column, uint64_t out2[2]);
 
 /* ---- K6 renderer (row a-R): morph::get_pixels / draw_atoms, morph.cpp:452-678, 1302-1421 ------- */
 /* Refresh the per-atom render inputs from the chain table (the device analogue of the chain /

@@ -21,16 +21,41 @@ def test_frame_ranges_cover_exactly():
     assert np.array_equal(t, np.arange(64) / 64.0)
 
 
-def test_owned_columns_partition_each_parity():
-    for h in (4, 5, 8):
-        for world in (1, 2, 4):
-            for parity in (0, 1):
-                cols = sorted(sum((amd.owned_columns(h, parity, r, world) for r in range(world)), []))
-                assert all(c % 2 == parity for c in cols)
-                # no two columns refined together are cyclic neighbours
+def test_owned_columns_cover_every_column_and_never_touch_neighbours():
+    for h in (2, 3, 4, 5, 7, 8):
+        for world in (1, 2, 4, 8):
+            covered = []
+            for phase in range(amd.phase_count(h)):
+                cols = sorted(sum((amd.owned_columns(h, phase, r, world) for r in range(world)), []))
+                assert cols == sorted(amd.phase_columns(h, phase))
+                covered += cols
+                # no two columns refined together are cyclic neighbours (they are read-only for each other's proposals)
                 for a in cols:
                     for b in cols:
-                        assert a == b or (abs(a - b) % h not in (1, h - 1))
+                        assert a == b or ((a - b) % h not in (1, h - 1))
+            assert sorted(covered) == list(range(h)), "a key-frame column is never refined"
+    assert amd.phase_count(8) == 2 and amd.phase_count(5) == 3
+
+
+@pytest.mark.parametrize("width", [8192, 10000, 1 << 15])
+def test_parts_of_a_step_partition_the_chain(width):
+    """amx_swap_part_step: the outer bijection's contiguous slot ranges are disjoint pseudo-random parts; a sub-epoch's
+    inner bijection only permutes a part."""
+    k = int(width - 1).bit_length()
+    for step in range(3):
+        slots = amd.part_slots(width, seed=1, chain=0, step=step)
+        assert np.array_equal(np.sort(slots), np.arange(1 << k, dtype=np.uint64))
+        for world in (1, 2, 4, 8):
+            n = (1 << k) // world
+            for r in range(world):
+                for sub in range(2):
+                    atoms = amd.part_tile_atoms(width, 1, 0, step, sub, r, world)
+                    assert np.array_equal(np.sort(atoms), np.sort(slots[r * n:(r + 1) * n]))
+                a0, a1 = amd.part_tile_atoms(width, 1, 0, step, 0, r, world), amd.part_tile_atoms(width, 1, 0, step, 1, r, world)
+                assert not np.array_equal(a0, a1), "sub-epochs must re-tile the part"
+        live = np.sort(slots[: (1 << k) // 2][slots[: (1 << k) // 2] < width].astype(np.int64))
+        assert live[-1] - live[0] > width // 2                      # a part is spread over the whole chain
+    assert not np.array_equal(amd.part_slots(width, 1, 0, 0), amd.part_slots(width, 1, 0, 1))
 
 
 @pytest.mark.parametrize("width", [1 << 10, 1000, 37])
@@ -106,6 +131,26 @@ def _worker(rank, world, port, width, q):
             column[own] = vals[np.argsort(other[own] ^ np.uint64(epoch + 7), kind="stable")]
             send = np.zeros(n, dtype=np.int64)
             send[ok] = column[own].astype(np.int64)
+            recv = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(recv, torch.from_numpy(send))
+            allv = np.concatenate([r.numpy().astype(np.uint64) for r in recv])
+            okall = slots < width
+            column[slots[okall].astype(np.int64)] = allv[okall]
+    # parts of a step (amx_swap_part_step): rank r refines its slot range through two re-tiled sub-epochs, then all-gather
+    if width >= 64:
+        k = int(width - 1).bit_length()
+        n = (1 << k) // world
+        for step in range(3):
+            slots = amd.part_slots(width, seed=9, chain=0, step=step)
+            for sub in range(2):
+                atoms = amd.part_tile_atoms(width, 9, 0, step, sub, rank, world)
+                own = atoms[atoms < width].astype(np.int64)
+                vals = column[own]
+                column[own] = vals[np.argsort(other[own] ^ np.uint64(step * 2 + sub + 11), kind="stable")]
+            mine = slots[rank * n:(rank + 1) * n]
+            ok = mine < width
+            send = np.zeros(n, dtype=np.int64)
+            send[ok] = column[mine[ok].astype(np.int64)].astype(np.int64)
             recv = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(recv, torch.from_numpy(send))
             allv = np.concatenate([r.numpy().astype(np.uint64) for r in recv])

@@ -151,3 +151,40 @@ def test_tiled_path_with_several_chains_equals_general_path(reflib, monkeypatch)
         assert np.array_equal(a, b)
         n, mx = diff_stats(m.render(ts[4]), a[4])
         assert mx <= 1 and n <= 0.01 * a[4].size
+
+
+def test_full_size_frame_tiled_path_matches_reference(reflib):
+    """BASELINE config 2 at its real size: one 1024 x 1024 frame of the (partly matched) square -> disc morph through the
+    TILED path against am::morph::get_pixels of the reference fed the same chain table (about 10-15 s of reference time).
+    Bar: <= 1 LSB per channel, differing pixels (exact .5 ties) a small fraction; cost recomputed identically."""
+    size = 1024
+    images = scenes.square_to_disc(size)
+    params = dict(seed=1, motion=eng.SPLINE, fading=eng.COSINE)
+    e = eng.Engine(0, threads=0, cycle_length=100000, **params)
+    e.load_images(images)
+    e.step(8)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    e.swap_rounds(1024, want_stats=False)                 # a partly matched table: atoms cross paths, tiles are unevenly filled
+    chains = e.chains()
+    assert chains[0]["words"].shape == (2, size * size)
+    m = reflib.RefMorph(**params)
+    for k, im in enumerate(images):
+        m.add_image(k, im)
+    m.set_resolution(size, size)
+    for i in range(2):
+        ys, xs = np.nonzero(images[i][..., 3] != 0)
+        labels, stats, meta = e.export_blobs(i)
+        m.import_blobs(i, [dict(group=int(meta[0, 0]), stats=stats[0], surface=(ys.astype(np.uint64) * np.uint64(65536) + xs.astype(np.uint64)))])
+    for c in chains:
+        m.import_chain(c["key"], c["words"], c["max_surface"])
+    m.finish_import()
+    assert m.true_cost() == e.cost()
+    t = 0.37
+    got = e.render([t])[0]
+    paths, tiled = e.render_path_frames(), e.render_tiled_stats()
+    assert paths["tiled"] == 1 and paths["general"] == 0 and tiled["fallbacks"] == 0, (paths, tiled)
+    ref = m.render(t)
+    n, mx = diff_stats(ref, got)
+    assert mx <= 1, "channel diff %d" % mx
+    assert n <= 0.005 * size * size, "%d pixels differ" % n
+    print("1024^2 frame: %d of %d pixels differ by 1 LSB (max %d)" % (n, size * size, mx))
