@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libatomorph_b200.so")
+LIB_PATH = os.environ.get("AMX_LIB") or os.path.join(_HERE, "libatomorph_b200.so")     # AMX_LIB: a tuning build (build.py AMX_BUILD_TAG)
 
 AMX_OK = 0
 STATUS = {0: "AMX_OK", 1: "AMX_ERR_CUDA", 2: "AMX_ERR_ARG", 3: "AMX_ERR_STATE", 4: "AMX_ERR_NOMEM", 5: "AMX_ERR_BUSY"}

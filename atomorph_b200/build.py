@@ -14,8 +14,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "atomorph_b200", "csrc")
-OUT = os.path.join(ROOT, "atomorph_b200", "libatomorph_b200.so")
-OBJDIR = os.path.join(ROOT, "build", "obj")
+# AMX_BUILD_TAG=x (tuning experiments): objects in build/obj_x, library libatomorph_b200_x.so (picked up through AMX_LIB)
+_TAG = os.environ.get("AMX_BUILD_TAG", "")
+OUT = os.path.join(ROOT, "atomorph_b200", "libatomorph_b200%s.so" % ("_" + _TAG if _TAG else ""))
+OBJDIR = os.path.join(ROOT, "build", "obj" + ("_" + _TAG if _TAG else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -182,10 +182,12 @@ k_column_hash(const pword *__restrict__ col, uint64_t n, unsigned long long *__r
     if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
 }
 
-// tile size (log2 atoms) for a part of 2^kk slots: the largest of 1024 / 512 / 256 that still gives two CTAs per SM
+// tile size (log2 atoms) for a part of 2^kk slots.  The tiled kernel is latency-bound (one barrier per round): it needs
+// about six resident CTAs per SM to hide it, so a smaller part is cut into smaller tiles (1024 -> 512 -> 256 atoms)
+// rather than into fewer CTAs.  Measured at N = 2 with 1024-atom tiles: half the tiles took the time of all of them.
 static int pick_tile_bits(Engine *E, unsigned kk) {
     for (int tb = TILE_BITS; tb > 8; --tb)
-        if (kk >= (unsigned) tb && (1ull << (kk - tb)) >= 2ull * (uint64_t) E->sm_count) return tb;
+        if (kk >= (unsigned) tb && (1ull << (kk - tb)) >= 6ull * (uint64_t) E->sm_count) return tb;
     return kk >= 8 ? 8 : -1;
 }
 
