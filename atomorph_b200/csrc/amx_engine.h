@@ -157,12 +157,7 @@ struct Engine {
     uint32_t *tb_flag = nullptr;           // raised by the kernels when a bin / tile overflows
     uint32_t  tb_tiles_x = 0, tb_tiles_y = 0, tb_parity = 0, tb_dirty[2] = {0, 0};
     bool      tb_has_chain = false;
-    // row path (amx_render.cu: RowBins): record bins per (frame slot of a batch, tile, row of the tile), single-chain morphs
-    uint2    *rb_rec = nullptr;
-    uint32_t *rb_atom = nullptr, *rb_cnt = nullptr, *rb_flag = nullptr;
-    uint32_t  rb_tiles_x = 0, rb_tiles_y = 0, rb_parity = 0, rb_dirty[2] = {0, 0};
     bool      tiled_enabled = true;        // AMX_RENDER_TILED=0: general A-buffer path only (for comparisons)
-    bool      tile_v1 = false;             // AMX_TILE_V1=1: the tile kernels (k_bin + k_tile) for single-chain morphs too (comparisons)
     bool      tiled_multi = false;         // AMX_RENDER_TILED=2: tiled path for morphs with several chains as well
     bool      tiled_blocked = false;       // a bin overflowed with the current table: general path until the next refresh
     uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_path_frames)

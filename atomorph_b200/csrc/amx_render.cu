@@ -726,11 +726,10 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
 #define T_SREC   4096u                  // (12 B of shared memory per record, 54 KB per CTA: 4 CTAs per SM)
-#define T_CAP0   7168u
-// T_SREC: records a tile's shared memory takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities in global memory per class
-// (interior / last column or row / corner): 7 atoms per pixel of a tile before a record is dropped
-#define T_CAP1   1024u
-#define T_CAP3   256u
+#define T_CAP0   3584u
+// T_SREC: records a tile takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities per class (interior / last column or row / corner)
+#define T_CAP1   512u
+#define T_CAP3   128u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
 #define T_KEY_NONE 0xffffffffu
 
@@ -1136,407 +1135,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
 #undef T_PHASE
 }
 
-// ---------------------------------------------------------------------------------------- row path (single chain, feather == 0)
-// Third generation of the tiled renderer; the one BASELINE configs 2 and 5 run on.  What the profiles of the tile kernels
-// above said (profiles/r01b_*, r02_*): they are bound by instruction issue and by CTA-wide barriers around phases that each
-// wait for global memory -- read the nine bin counters, stage the records, sort them for the whole tile, only then fold.
-// Here the unit of work is small enough for ONE WARP, so nothing ever waits for another warp:
-//
-//   k_bin3   like k_bin, but a record is appended to the bin of its home's tile ROW (32 homes, R_CAP records) instead of
-//            its tile, and a record in the last column of a tile is written a second time into the neighbouring tile's row
-//            bin as that tile's halo column.  The consumer of a home row therefore reads exactly one contiguous bin; the
-//            halo ROW of a strip is simply the row bin above it.  One atomicAdd per (warp, row bin) as before.
-//   k_row    one warp per strip of 32 x 16 pixels of one frame, no __syncthreads, no shared state between warps.  For each
-//            of the strip's 17 home rows: the bin's records (prefetched into registers while the previous row was folded)
-//            are ordered by home column with a 33-bucket counting sort in the warp's own 1 KB of shared memory, lane x folds
-//            the records of home column x into exact integer sums of its four splat targets -- every record is visited once
-//            -- the sums for the pixel column on the right travel there with shuffles, and the pixel row that is complete
-//            is resolved and stored.  The sums of the row below stay in registers as the only carried state.
-//            Exact .5 ties and pixels reached by more than MAXK records are resolved on the spot by the whole warp
-//            (row_heavy): the contributions are gathered from the two sorted rows, their atoms fetched from the bin, and
-//            the reference's per-position normalisation replayed in atom order in double (morph.cpp:598-613).
-//
-// Capacity: a row bin holds R_CAP = 128 records (4 per pixel of its 32-pixel row); more raises the flag and the frames of
-// the call are rendered again by the general path.
-#define R_CAP    128u
-#define R_STRIP  16u                    // pixel rows per strip (work item of one warp)
-#define R_WARPS  8u
-
-struct RowBins {
-    uint2    *rec;        // [RBATCH][tiles * 32][R_CAP] {colour, x_fract | y_fract << 8 | home column << 16}, home column = lx + 1, 0 = halo
-    uint32_t *atom;       // same layout: original atom index (the reference's summation order)
-    uint32_t *cnt;        // [RBATCH][tiles * 32] records claimed per row bin in this batch (clean on entry)
-    uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_row
-    uint32_t *flag;       // [0] != 0: a bin overflowed; [1] largest row bin seen, [5] largest strip total (diagnostics)
-    uint32_t  tiles_x, tiles_y;
-};
-
-template <int MOTION, bool PERLIN, bool H2>
-__global__ void __launch_bounds__(256, 2)
-k_bin3(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, RowBins bn) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t A = rc.A;
-    const double inv256 = 0.00390625;
-    const uint32_t y = rb.f[0].y;
-    const uint32_t nbins = bn.tiles_x * bn.tiles_y * 32u;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    RawIn next = RawIn();
-    if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
-    // warp-uniform trip count: claiming bin slots is a warp collective
-    for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
-        const bool valid = i < n_live;
-        const RawIn raw = next;
-        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
-
-        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) { key[s] = T_KEY_NONE; col[s] = meta[s] = 0u; }
-        const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
-        if (use) {
-            AtomIn in;
-            in.pt1 = raw.pt1; in.pt2 = raw.pt2;
-            in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
-            in.x2 = u2d((uint32_t) pw_x256(raw.pt2)) * inv256; in.y2 = u2d((uint32_t) pw_y256(raw.pt2)) * inv256;
-            in.rc1 = raw.c1; in.rc2 = raw.c2;
-            in.c1 = col_d(raw.c1); in.c2 = col_d(raw.c2);
-            in.lag = raw.lag; in.slope = raw.slope;
-#pragma unroll
-            for (uint32_t s = 0; s < RBATCH; ++s) {
-                if (s >= nb) continue;
-                uint32_t fr, hx, hy;
-                // a home at x >= width or y >= height reaches no pixel of the image
-                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr) && hx < rc.width && hy < rc.height) {
-                    key[s] = ((((hy >> 5) * bn.tiles_x + (hx >> 5)) << 5) | (hy & 31u));      // row bin: tile, row of the tile
-                    // home column in the strip's coordinates; bit 31: last column of its tile with a pixel column to its right
-                    meta[s] = fr | (((hx & 31u) + 1u) << 16) | (((hx & 31u) == 31u && hx + 1u < rc.width) ? 0x80000000u : 0u);
-                }
-            }
-        }
-        // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots.  The claims of all frames
-        // are issued back to back before the first one is waited for.
-        uint32_t who[RBATCH], base[RBATCH];
-        uint32_t dupmask = 0u;
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) {
-            base[s] = 0u; who[s] = 0u;
-            if (s >= nb) continue;
-            const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
-            const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
-            who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * nbins + key[s]], (uint32_t) __popc(peers));
-            if (meta[s] >> 31) dupmask |= 1u << s;
-        }
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) {
-            if (s >= nb) continue;
-            const uint32_t pos = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u)) + (who[s] >> 8);
-            if (key[s] == T_KEY_NONE || pos >= R_CAP) continue;       // beyond the capacity: dropped, k_row sees the counter and raises the flag
-            const size_t o = ((size_t) s * nbins + key[s]) * R_CAP + pos;
-            bn.rec[o] = make_uint2(col[s], meta[s] & 0x7fffffffu);
-            bn.atom[o] = raw.atom;
-        }
-        // a home in the last column of its tile also reaches column 0 of the tile on the right: second copy, as that tile's halo
-        // column (home column 0 of the row bin next door).  About one warp in four has such a lane in a frame.
-        const uint32_t anydup = __reduce_or_sync(0xffffffffu, dupmask);
-        if (anydup) {
-#pragma unroll
-            for (uint32_t s = 0; s < RBATCH; ++s) {
-                base[s] = 0u; who[s] = 0u;
-                if (!((anydup >> s) & 1u)) continue;
-                const uint32_t key2 = ((dupmask >> s) & 1u) ? key[s] + 32u : T_KEY_NONE;
-                const uint32_t peers = __match_any_sync(0xffffffffu, key2);
-                const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
-                who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-                if (lane == leader && key2 != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * nbins + key2], (uint32_t) __popc(peers));
-            }
-#pragma unroll
-            for (uint32_t s = 0; s < RBATCH; ++s) {
-                if (!((anydup >> s) & 1u)) continue;
-                const uint32_t pos = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u)) + (who[s] >> 8);
-                if (!((dupmask >> s) & 1u) || pos >= R_CAP) continue;
-                const size_t o = ((size_t) s * nbins + key[s] + 32u) * R_CAP + pos;
-                bn.rec[o] = make_uint2(col[s], meta[s] & 0xffffu);          // home column 0
-                bn.atom[o] = raw.atom;
-            }
-        }
-    }
-}
-
-struct Sum5 { uint32_t R, G, B, A, N; };
-__device__ __forceinline__ void sum5_zero(Sum5 &s) { s.R = s.G = s.B = s.A = s.N = 0u; }
-// both records of a pair at once: weights w0 | w1 << 16 against the colour bytes c0 | c1 << 8 of one channel (IDP.2A)
-__device__ __forceinline__ void sum5_add(Sum5 &s, uint32_t ww, uint32_t cr, uint32_t cg, uint32_t cb, uint32_t ca) {
-    s.R = __dp2a_lo(ww, cr, s.R); s.G = __dp2a_lo(ww, cg, s.G); s.B = __dp2a_lo(ww, cb, s.B); s.A = __dp2a_lo(ww, ca, s.A);
-    s.N = __dp2a_lo(ww, 0x0101u, s.N);
-}
-__device__ __forceinline__ Sum5 sum5_shfl_up(const Sum5 &s) {
-    Sum5 t;
-    t.R = __shfl_up_sync(0xffffffffu, s.R, 1); t.G = __shfl_up_sync(0xffffffffu, s.G, 1); t.B = __shfl_up_sync(0xffffffffu, s.B, 1);
-    t.A = __shfl_up_sync(0xffffffffu, s.A, 1); t.N = __shfl_up_sync(0xffffffffu, s.N, 1);
-    return t;
-}
-
-// lane 0 only: the reference's normalisation of <= MAXK contributions in atom order (out of line: its local arrays must not
-// weigh on the row kernel's registers)
-__device__ __noinline__ uint32_t replay_sorted(const uint32_t *atom, const uint32_t *colv, const uint32_t *nv, uint32_t count, uint32_t density) {
-    uint32_t cc[MAXK], cn[MAXK], ca[MAXK];
-    for (uint32_t k = 0; k < count; ++k) {
-        const uint32_t at = atom[k];
-        int j = (int) k;
-        while (j > 0 && ca[j - 1] > at) { ca[j] = ca[j - 1]; cc[j] = cc[j - 1]; cn[j] = cn[j - 1]; --j; }
-        ca[j] = at; cc[j] = colv[k]; cn[j] = nv[k];
-    }
-    return resolve_fp(cc, cn, 0, (int) count, density);
-}
-
-// The whole warp resolves pixel column X of the pixel row between home rows `prev` (dy = 1) and `cur` (dy = 0): ties and
-// crowded pixels.  cur / prev: sorted records and offsets of the two rows; bin_cur / bin_prev: the rows' bins (for the atom
-// indices in global memory; a sorted record carries its position in the bin in bits 24..31).  Out of line: rare, and its
-// 64-bit sums must not weigh on the row kernel's registers.
-__device__ __noinline__ uint32_t row_heavy(uint32_t lane, uint32_t X, const uint2 *cur, const uint32_t *ocur, const uint2 *prev, const uint32_t *oprev,
-                                           const uint32_t *__restrict__ g_atom, uint32_t bin_cur, uint32_t bin_prev, uint32_t *scr, uint32_t density) {
-    uint32_t *sc_atom = scr, *sc_col = scr + MAXK, *sc_n = scr + 2 * MAXK;
-    const uint32_t c0 = ocur[X], cm = ocur[X + 1u], c1 = ocur[X + 2u];        // home columns X (dx = 1) and X + 1 (dx = 0) of the row
-    const uint32_t p0 = oprev[X], pm = oprev[X + 1u], p1 = oprev[X + 2u];
-    const uint32_t nc = c1 - c0, total = nc + (p1 - p0);
-    uint32_t kept = 0u;
-    unsigned long long R = 0, G = 0, B = 0, Av = 0, N = 0, cnt = 0;
-    for (uint32_t e0 = 0; e0 < total; e0 += 32u) {
-        const uint32_t e = e0 + lane;
-        uint32_t w = 0u, colr = 0u, at = 0u;
-        if (e < total) {
-            const bool in_cur = e < nc;
-            const uint32_t pos = in_cur ? c0 + e : p0 + (e - nc);
-            const uint2 r = in_cur ? cur[pos] : prev[pos];
-            const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
-            const bool dx1 = pos < (in_cur ? cm : pm);
-            w = (dx1 ? xf : 255u - xf) * (in_cur ? 255u - yf : yf);
-            colr = r.x;
-            if (w) at = g_atom[(size_t) (in_cur ? bin_cur : bin_prev) * R_CAP + (r.y >> 24)];
-        }
-        const uint32_t hit = __ballot_sync(0xffffffffu, w != 0u);
-        if (w) {
-            const uint32_t k = kept + (uint32_t) __popc(hit & ((1u << lane) - 1u));
-            if (k < MAXK) { sc_atom[k] = at; sc_col[k] = colr; sc_n[k] = w; }
-            R += (unsigned long long) c_r(colr) * w; G += (unsigned long long) c_g(colr) * w; B += (unsigned long long) c_b(colr) * w;
-            Av += (unsigned long long) c_a(colr) * w; N += w; cnt += 1ull;
-        }
-        kept += (uint32_t) __popc(hit);
-    }
-    uint32_t pxl = 0u;
-    if (kept > MAXK) {
-        // the rule of resolve_contributions for heavy positions: exact integer sums
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            R += __shfl_down_sync(0xffffffffu, R, o); G += __shfl_down_sync(0xffffffffu, G, o); B += __shfl_down_sync(0xffffffffu, B, o);
-            Av += __shfl_down_sync(0xffffffffu, Av, o); N += __shfl_down_sync(0xffffffffu, N, o); cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-        }
-        if (lane == 0u) pxl = resolve_int(R, G, B, Av, N, cnt, density);
-    } else {
-        __syncwarp();
-        if (lane == 0u && kept) pxl = replay_sorted(sc_atom, sc_col, sc_n, kept, density);
-    }
-    __syncwarp();
-    return __shfl_sync(0xffffffffu, pxl, 0);
-}
-
-#ifndef R_CTAS
-#define R_CTAS 4
-#endif
-template <bool COUNTED>
-__global__ void __launch_bounds__(R_WARPS * 32u, R_CTAS)
-k_row(const __grid_constant__ RowBins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-      const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-      const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats, uint32_t nitems) {
-    __shared__ __align__(16) uint2 s_sorted[R_WARPS][2][R_CAP];
-    __shared__ __align__(16) uint2 s_stage[R_WARPS][2][64];
-    __shared__ uint32_t s_offs[R_WARPS][2][36];
-    __shared__ uint32_t s_scr[R_WARPS][3 * MAXK];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t item = blockIdx.x * R_WARPS + warp;
-    if (item >= nitems) return;
-    const uint32_t ntiles = bn.tiles_x * bn.tiles_y, nbins = ntiles * 32u;
-    constexpr uint32_t STRIPS = T_TILE / R_STRIP;
-    // consecutive items = the strips of one tile, then the next tile of the same frame
-    const uint32_t strip = item % STRIPS, tile = (item / STRIPS) % ntiles, slot = item / (STRIPS * ntiles);
-    const uint32_t tx = tile % bn.tiles_x, ty = tile / bn.tiles_x;
-    const uint32_t y_frame = rb.f[slot].y;
-    const size_t np = (size_t) rc.width * rc.height;
-    uint32_t *outf = out + (size_t) rb.f[slot].dst * np;
-    const uint32_t *bgf = bg + (size_t) slot * np;
-    const uint32_t px = tx * T_TILE + lane, py0 = ty * T_TILE + strip * R_STRIP;
-
-    // home row r of the strip (r = 0: the halo row above it) = row bin `rbin(r)`; a strip at the top of the image has no halo row
-    const bool has_halo = strip > 0u || ty > 0u;
-    const uint32_t bin0 = strip > 0u ? (tile << 5) + strip * R_STRIP - 1u : ((tile - bn.tiles_x) << 5) + 31u;    // only used when has_halo
-    const uint32_t bin1 = (tile << 5) + strip * R_STRIP;                                                           // r >= 1: bin1 + r - 1
-    uint32_t n_mine = 0u;
-    if (lane <= R_STRIP && (lane > 0u || has_halo)) {
-        const uint32_t bin = lane ? bin1 + lane - 1u : bin0;
-        n_mine = bn.cnt[(size_t) slot * nbins + bin];
-        if (n_mine > R_CAP) { n_mine = R_CAP; atomicOr(bn.flag, 1u); }       // k_bin3 dropped records: the frames are rendered again
-        if (lane) bn.cnt_other[(size_t) slot * nbins + bin] = 0u;            // housekeeping: the strip's own rows in the other counter buffer
-        if (n_mine > 64u && n_mine > bn.flag[1]) atomicMax(&bn.flag[1], n_mine);
-    }
-    uint32_t tot = n_mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0u && tot > bn.flag[5]) atomicMax(&bn.flag[5], tot);
-    if (tot == 0u) {
-        // nothing lands here: background (or nothing) only
-        if (px < rc.width)
-            for (uint32_t p = 0; p < R_STRIP; ++p) {
-                const uint32_t py = py0 + p;
-                if (py >= rc.height) break;
-                const size_t i = (size_t) py * rc.width + px;
-                outf[i] = rc.keep_background ? bgf[i] : 0u;
-            }
-        return;
-    }
-    const uint2 *grec = bn.rec + (size_t) slot * nbins * R_CAP;
-    const uint32_t *gatom = bn.atom + (size_t) slot * nbins * R_CAP;
-
-    // software pipeline: the first 64 records of row r + 1 travel into the warp's staging buffer (cp.async, no registers held)
-    // while row r is sorted and folded
-    {
-        const uint32_t n0 = __shfl_sync(0xffffffffu, n_mine, 0);
-        const uint2 *src = grec + (size_t) bin0 * R_CAP;
-        if (lane < n0) __pipeline_memcpy_async(&s_stage[warp][0][lane], &src[lane], 8);
-        if (lane + 32u < n0) __pipeline_memcpy_async(&s_stage[warp][0][lane + 32u], &src[lane + 32u], 8);
-        __pipeline_commit();
-    }
-    Sum5 carry;                 // dy = 1 contributions of the previous home row to the pixel row below it
-    sum5_zero(carry);
-    uint32_t carry_n = 0u, carry_cnt = 0u;
-    uint32_t bin_prev = 0u;
-    for (uint32_t r = 0; r <= R_STRIP; ++r) {
-        const uint32_t n = __shfl_sync(0xffffffffu, n_mine, (int) r);
-        const uint32_t bin_cur = r ? bin1 + r - 1u : bin0;
-        const size_t gcur = (size_t) bin_cur * R_CAP;
-        __pipeline_wait_prior(0);
-        __syncwarp();
-        uint2 ra = make_uint2(0u, 0u), rb2 = make_uint2(0u, 0u);
-        if (lane < n) ra = s_stage[warp][r & 1u][lane];
-        if (lane + 32u < n) rb2 = s_stage[warp][r & 1u][lane + 32u];
-        if (r < R_STRIP) {
-            const uint32_t nn = __shfl_sync(0xffffffffu, n_mine, (int) r + 1);
-            const uint2 *src = grec + (size_t) (bin1 + r) * R_CAP;
-            if (lane < nn) __pipeline_memcpy_async(&s_stage[warp][(r & 1u) ^ 1u][lane], &src[lane], 8);
-            if (lane + 32u < nn) __pipeline_memcpy_async(&s_stage[warp][(r & 1u) ^ 1u][lane + 32u], &src[lane + 32u], 8);
-        }
-        __pipeline_commit();
-        uint2 *sorted = s_sorted[warp][r & 1u];
-        uint32_t *off = s_offs[warp][r & 1u];
-        const uint2 *sprev = s_sorted[warp][(r & 1u) ^ 1u];
-        const uint32_t *oprev = s_offs[warp][(r & 1u) ^ 1u];
-        // ---- order the row's records by home column: 33 buckets, one shared-memory atomic per record
-        off[lane] = 0u;
-        if (lane < 4u) off[32u + lane] = 0u;
-        __syncwarp();
-        uint32_t ka = 0u, kb = 0u, kc = 0u, kd = 0u;
-        uint2 rc3 = make_uint2(0u, 0u), rd3 = make_uint2(0u, 0u);
-        if (lane < n) ka = atomicAdd(&off[(ra.y >> 16) & 63u], 1u);
-        if (lane + 32u < n) kb = atomicAdd(&off[(rb2.y >> 16) & 63u], 1u);
-        if (n > 64u) {            // crowded row (warp-uniform, rare): the rest of the bin straight from global memory
-            if (lane + 64u < n) { rc3 = grec[gcur + lane + 64u]; kc = atomicAdd(&off[(rc3.y >> 16) & 63u], 1u); }
-            if (lane + 96u < n) { rd3 = grec[gcur + lane + 96u]; kd = atomicAdd(&off[(rd3.y >> 16) & 63u], 1u); }
-        }
-        __syncwarp();
-        {
-            const uint32_t c = off[lane], c32 = off[32];
-            uint32_t incl = c;
-#pragma unroll
-            for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-            const uint32_t t31 = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            off[lane] = incl - c;
-            if (lane == 0u) { off[32] = t31; off[33] = t31 + c32; }
-        }
-        __syncwarp();
-        if (lane < n) sorted[off[(ra.y >> 16) & 63u] + ka] = make_uint2(ra.x, (ra.y & 0xffffu) | (lane << 24));
-        if (lane + 32u < n) sorted[off[(rb2.y >> 16) & 63u] + kb] = make_uint2(rb2.x, (rb2.y & 0xffffu) | ((lane + 32u) << 24));
-        if (n > 64u) {
-            if (lane + 64u < n) sorted[off[(rc3.y >> 16) & 63u] + kc] = make_uint2(rc3.x, (rc3.y & 0xffffu) | ((lane + 64u) << 24));
-            if (lane + 96u < n) sorted[off[(rd3.y >> 16) & 63u] + kd] = make_uint2(rd3.x, (rd3.y & 0xffffu) | ((lane + 96u) << 24));
-        }
-        __syncwarp();
-        // ---- fold: lane x owns PIXEL column x.  The two homes of the row that reach it are neighbours in the sorted order
-        // (home column x: dx = 1, the halo column for lane 0; home column x + 1: dx = 0), so their records are ONE contiguous
-        // range, walked two records per iteration.  dy = 0 completes the pixel row above the home row (on top of the carried
-        // dy = 1 sums of the previous home row), dy = 1 starts the one below.
-        const uint32_t a = off[lane], mid = off[lane + 1u], b = off[lane + 2u];
-        const uint32_t nreach = b - a, nn2 = min(nreach, (uint32_t) MAXK + 1u);   // beyond MAXK the pixel takes row_heavy anyway
-        Sum5 L0 = carry, L1;
-        sum5_zero(L1);
-        uint32_t cL0 = carry_cnt, cL1 = 0u;                                       // COUNTED: contributions with a non-zero weight
-        for (uint32_t it = 0; __any_sync(0xffffffffu, it < nn2); it += 2u) {
-            const bool has0 = it < nn2, has1 = it + 1u < nn2;
-            const uint32_t p = a + it;
-            const uint2 r0 = sorted[has0 ? p : 0u], r1 = sorted[has1 ? p + 1u : 0u];
-            // dx = 1 ? x_fract : 255 - x_fract ; a record beyond the range gets weight 0
-            const uint32_t wx0 = has0 ? ((p < mid ? r0.y : ~r0.y) & 255u) : 0u, wx1 = has1 ? ((p + 1u < mid ? r1.y : ~r1.y) & 255u) : 0u;
-            const uint32_t fy0 = (r0.y >> 8) & 255u, fy1 = (r1.y >> 8) & 255u;
-            const uint32_t cr = __byte_perm(r0.x, r1.x, 0x4440), cg = __byte_perm(r0.x, r1.x, 0x4451), cb = __byte_perm(r0.x, r1.x, 0x4462), ca = __byte_perm(r0.x, r1.x, 0x4473);
-            const uint32_t w0 = wx0 * (255u - fy0) | (wx1 * (255u - fy1)) << 16, w1 = wx0 * fy0 | (wx1 * fy1) << 16;
-            sum5_add(L0, w0, cr, cg, cb, ca);
-            sum5_add(L1, w1, cr, cg, cb, ca);
-            if (COUNTED) { cL0 += ((w0 & 0xffffu) != 0u) + ((w0 >> 16) != 0u); cL1 += ((w1 & 0xffffu) != 0u) + ((w1 >> 16) != 0u); }
-        }
-        if (r > 0u) {
-            // pixel row r - 1 of the strip is complete
-            const uint32_t sR = L0.R, sG = L0.G, sB = L0.B, sA = L0.A, sN = L0.N;
-            const uint32_t reach = carry_n + nreach, cnt = COUNTED ? cL0 : reach;
-            const uint32_t py = py0 + r - 1u;
-            const bool inside = px < rc.width && py < rc.height;
-            const size_t i = (size_t) py * rc.width + px;
-            const uint32_t bgc = (inside && rc.keep_background) ? bgf[i] : 0u;
-            bool heavy = inside && reach > MAXK;
-            uint32_t colr = bgc;
-            bool plain = true;                               // colr is a final colour (background), not a resolved blob pixel
-            if (inside && !heavy && sN != 0u) {
-                // integer sums with exact rational rounding: the reference's result unless a quotient is an exact .5 tie
-                // (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits)
-                bool tie = false;
-                const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * sN));
-                const uint32_t qr = rdiv_small(sR, sN, rcp_d2, &tie), qg = rdiv_small(sG, sN, rcp_d2, &tie), qb = rdiv_small(sB, sN, rcp_d2, &tie);
-                uint32_t qa;
-                if (!COUNTED) qa = rc.density == 0 ? 0u : rdiv_small(sA, sN, rcp_d2, &tie);      // density 1: min(1, count/1) = 1
-                else if (cnt >= rc.density) qa = rdiv_small(sA, sN, rcp_d2, &tie);
-                else {
-                    const unsigned long long num = (unsigned long long) sA * cnt, den = (unsigned long long) sN * rc.density;   // round(cnt*A / (density*N))
-                    const unsigned long long n2 = 2ull * num + den, d2 = 2ull * den, q = n2 / d2;
-                    tie |= (n2 - q * d2 == 0ull);
-                    qa = (uint32_t) q;
-                }
-                colr = c_make(qr, qg, qb, qa);
-                plain = false;
-                heavy = tie;
-                if (tie && stats) atomicAdd(&stats->ties, 1ull);
-            }
-            // ties and crowded pixels: the warp replays them one at a time from the two sorted rows (rare: ~0.07 % of the pixels)
-            uint32_t todo = __ballot_sync(0xffffffffu, heavy);
-            while (todo) {
-                const uint32_t X = (uint32_t) __ffs((int) todo) - 1u;
-                todo &= todo - 1u;
-                const uint32_t v = row_heavy(lane, X, sorted, off, sprev, oprev, gatom, bin_cur, bin_prev, s_scr[warp], rc.density);
-                if (lane == X) { colr = v; plain = false; if (stats) atomicAdd(&stats->generic, 1ull); }
-            }
-            if (inside) {
-                if (!plain) {
-                    colr = entry_color(colr, 255u, 0u, rc, y_frame, blob_avg, blob_distinct);
-                    if (!rc.keep_background) colr = c_a(colr) ? colr : 0u;        // round((c/255.0)*255.0) == c for every byte c
-                    else { Over ov; ov.add(colr); colr = ov.finish(bgc, true); }
-                }
-                outf[i] = colr;
-            }
-        }
-        carry = L1; carry_n = nreach; carry_cnt = cL1;
-        bin_prev = bin_cur;
-    }
-}
-
 // gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
 template <bool SINGLE>
 __global__ void __launch_bounds__(256)
@@ -1778,8 +1376,6 @@ void engine_render_free(Engine *E) {
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
     dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
-    dev_free(E->rb_rec); dev_free(E->rb_atom); dev_free(E->rb_cnt); dev_free(E->rb_flag);
-    E->rb_rec = nullptr; E->rb_atom = E->rb_cnt = E->rb_flag = nullptr; E->rb_tiles_x = E->rb_tiles_y = 0;
     E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
@@ -2116,74 +1712,6 @@ static Bins make_bins(Engine *E) {
     return bn;
 }
 
-// ---- row path: row bins for RBATCH frames of the current resolution; false when the path cannot be used
-static bool ensure_rowbins(Engine *E) {
-    const uint32_t tx = div_up(E->width, T_TILE), ty = div_up(E->height, T_TILE);
-    if (E->rb_rec && E->rb_tiles_x == tx && E->rb_tiles_y == ty) return true;
-    const uint64_t nbins = (uint64_t) tx * ty * 32u, nrec = (uint64_t) RBATCH * nbins * R_CAP;
-    if (nbins == 0 || (uint64_t) RBATCH * nbins >= (1ull << 31)) return false;
-    dev_free(E->rb_rec); dev_free(E->rb_atom); dev_free(E->rb_cnt); dev_free(E->rb_flag);
-    E->rb_rec = nullptr; E->rb_atom = E->rb_cnt = E->rb_flag = nullptr; E->rb_tiles_x = E->rb_tiles_y = 0;
-    const size_t cnt_bytes = (size_t) 2 * RBATCH * nbins * sizeof(uint32_t);
-    if (!dev_alloc(E, (void **) &E->rb_rec, nrec * 8, "row bin records") || !dev_alloc(E, (void **) &E->rb_atom, nrec * 4, "row bin atoms") ||
-        !dev_alloc(E, (void **) &E->rb_cnt, cnt_bytes, "row bin counters") || !dev_alloc(E, (void **) &E->rb_flag, 8 * 4, "row bin flag")) {
-        E->err.clear();                                                   // not an error: the general path needs none of this
-        dev_free(E->rb_rec); dev_free(E->rb_atom); dev_free(E->rb_cnt); dev_free(E->rb_flag);
-        E->rb_rec = nullptr; E->rb_atom = E->rb_cnt = E->rb_flag = nullptr;
-        return false;
-    }
-    cudaMemsetAsync(E->rb_cnt, 0, cnt_bytes, E->stream);
-    cudaMemsetAsync(E->rb_flag, 0, 8 * 4, E->stream);
-    E->rb_tiles_x = tx; E->rb_tiles_y = ty;
-    E->rb_parity = 0; E->rb_dirty[0] = E->rb_dirty[1] = 0;
-    return true;
-}
-
-// one batch (<= RBATCH frames of one interval) through k_bin3 + k_row
-static void launch_rows(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb, const uint32_t *d_bg, uint32_t *d_dst) {
-    RIn ri;
-    ri.pts = E->rpts; ri.c1 = E->rc1; ri.c2 = E->rc2; ri.atom = E->ratom; ri.chain = E->rchain;
-    ri.lag = E->rlag; ri.slope = E->rslope; ri.npt = E->rnpt; ri.table = E->table;
-    const uint32_t n_live = E->r_live[rb.f[0].y];
-    const size_t per_slot = (size_t) E->rb_tiles_x * E->rb_tiles_y * 32u, per = (size_t) RBATCH * per_slot;
-    RowBins bn;
-    bn.rec = E->rb_rec; bn.atom = E->rb_atom; bn.flag = E->rb_flag;
-    bn.cnt = E->rb_cnt + (size_t) E->rb_parity * per;
-    bn.cnt_other = E->rb_cnt + (size_t) (E->rb_parity ^ 1u) * per;
-    bn.tiles_x = E->rb_tiles_x; bn.tiles_y = E->rb_tiles_y;
-    const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
-    g_ktime.begin(E->stream);
-    if (n_live > 0) {
-#define AMX_BIN3(M, P, H) do { \
-        static int per_sm_dev[64] = {0}; \
-        int &per_sm = per_sm_dev[E->device & 63]; \
-        if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin3<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
-        const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
-        k_bin3<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
-#define AMX_BIN3_M(M) do { if (perlin) { if (h2) AMX_BIN3(M, true, true); else AMX_BIN3(M, true, false); } \
-                           else        { if (h2) AMX_BIN3(M, false, true); else AMX_BIN3(M, false, false); } } while (0)
-        if (rc.motion == K_LINEAR) AMX_BIN3_M(M_LINEAR);
-        else if (rc.motion == K_SPLINE) AMX_BIN3_M(M_SPLINE);
-        else AMX_BIN3_M(M_NONE);
-#undef AMX_BIN3_M
-#undef AMX_BIN3
-        E->launches++;
-    }
-    g_ktime.end(E->stream, 0, nb);
-    // k_row clears slots [0, nb) of the other counter buffer; a longer dirty tail (previous batch was larger) is memset
-    const uint32_t p = E->rb_parity, q = p ^ 1u;
-    if (E->rb_dirty[q] > nb) cudaMemsetAsync(bn.cnt_other + (size_t) nb * per_slot, 0, (size_t) (E->rb_dirty[q] - nb) * per_slot * 4, E->stream);
-    RenderStats *st = (RenderStats *) E->d_render_stats;
-    const uint32_t nitems = E->rb_tiles_x * E->rb_tiles_y * (T_TILE / R_STRIP) * nb;
-    g_ktime.begin(E->stream);
-    if (rc.density > 1) k_row<true><<<div_up(nitems, R_WARPS), R_WARPS * 32u, 0, E->stream>>>(bn, rc, rb, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st, nitems);
-    else                k_row<false><<<div_up(nitems, R_WARPS), R_WARPS * 32u, 0, E->stream>>>(bn, rc, rb, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st, nitems);
-    g_ktime.end(E->stream, 1, nb);
-    E->launches++;
-    E->rb_dirty[q] = 0; E->rb_dirty[p] = nb; E->rb_parity = q;
-    E->tiled_frames += nb;
-}
-
 // one batch (<= RBATCH frames of one interval) through k_bin + k_tile
 static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t nb, const uint32_t *d_bg, uint32_t *d_dst) {
     RIn ri;
@@ -2280,10 +1808,7 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     // feather == 0 without fluid: the tiled path, unless it is switched off / has overflowed with this table
     // (several chains: pixels shared by several blobs take the ordered replay, which runs better in the general path's small
     // CTAs at full occupancy -- C4: 4.3 k against 1.8 k frames/s -- so the tiled path is for single-chain morphs unless forced)
-    const bool tiled_ok = have_chains && E->tiled_enabled && (E->nchains == 1 || E->tiled_multi) && !E->tiled_blocked && E->p.feather == 0 && E->p.fluid == 0;
-    // a single chain takes the row path (k_bin3 + k_row), several chains (when forced) the tile kernels (k_bin + k_tile)
-    const bool rows = tiled_ok && E->nchains == 1 && !E->tile_v1 && ensure_rowbins(E);
-    const bool tiled = rows || (tiled_ok && ensure_bins(E));
+    const bool tiled = have_chains && E->tiled_enabled && (E->nchains == 1 || E->tiled_multi) && !E->tiled_blocked && E->p.feather == 0 && E->p.fluid == 0 && ensure_bins(E);
     const uint32_t NB = std::max(1u, std::min<uint32_t>(E->render_batch, tiled ? RBATCH : GBATCH));
     if (E->p.keep_background && E->d_bg_cap < (size_t) NB * np) {
         dev_free(E->d_bg); E->d_bg = nullptr; E->d_bg_cap = 0;
@@ -2319,7 +1844,6 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     auto flush_batch = [&]() {
         // feather == 0: nb frames share one scatter and one fused gather/composite launch
         if (nb == 0) return;
-        if (rows) { launch_rows(E, rc, rb, nb, d_bg, d_dst); tiled_used = true; nb = 0; return; }
         if (tiled) { launch_tiled(E, rc, rb, nb, d_bg, d_dst); tiled_used = true; nb = 0; return; }
         E->general_frames += nb;
         launch_scatter(E, rc, rb, nb);
@@ -2389,20 +1913,15 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     if (rcode == AMX_OK && tiled_used) {
         // did every bin hold its records?  If not, the same frames go through the general path (identical results)
         uint32_t flag8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint32_t *d_flag = rows ? E->rb_flag : E->tb_flag;
-        if (E->fail(cudaMemcpyAsync(flag8, d_flag, sizeof flag8, cudaMemcpyDeviceToHost, E->stream), "bin flag") ||
+        if (E->fail(cudaMemcpyAsync(flag8, E->tb_flag, sizeof flag8, cudaMemcpyDeviceToHost, E->stream), "bin flag") ||
             E->fail(cudaStreamSynchronize(E->stream), "render")) return AMX_ERR_CUDA;
         for (int k = 0; k < 6; ++k) E->tb_demand[k] = std::max(E->tb_demand[k], flag8[1 + k]);
         if (flag8[0]) {
             E->tiled_fallbacks++;
-            cudaMemsetAsync(d_flag, 0, 4, E->stream);
-            if (rows) {
-                cudaMemsetAsync(E->rb_cnt, 0, (size_t) 2 * RBATCH * E->rb_tiles_x * E->rb_tiles_y * 32u * sizeof(uint32_t), E->stream);
-                E->rb_parity = 0; E->rb_dirty[0] = E->rb_dirty[1] = 0;
-            } else {
-                cudaMemsetAsync(E->tb_cnt, 0, (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t), E->stream);
-                E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
-            }
+            const size_t cnt_bytes = (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t);
+            cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
+            cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
+            E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
             E->tiled_blocked = true;
             return engine_render(E, times, n, out, out_is_device);
         }

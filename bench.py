@@ -265,6 +265,16 @@ def run_b200(args):
     cost0 = e.cost()
     e.swap_rounds(args.match_rounds, want_stats=False)
     cost1 = e.cost()
+    # north star: final transport cost no worse than 1 % above the reference's converged cost for the same seed and frames.
+    # tests/golden/c2_copt.json = BASELINE.md section 3 protocol run on the unmodified reference (tests/golden/make_copt.py)
+    copt = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "c2_copt.json")) as fh:
+            g = json.load(fh)
+        if int(g["size"]) == size:
+            copt = float(g["c_opt"])
+    except Exception:
+        pass
     e.render_prepare()
     e.sync()
 
@@ -450,6 +460,7 @@ def run_b200(args):
         "clocks": clocks,
         "render_stats": dict(e.render_stats(), path_frames=e.render_path_frames(), tiled=e.render_tiled_stats()),
         "match": {"rounds": int(args.match_rounds), "proposals_per_atom": args.match_rounds / 2.0, "cost_initial": cost0, "cost_matched": cost1,
+                  "reference_c_opt": copt, "cost_matched_over_c_opt": (cost1 / copt) if copt else None, "within_1pct_of_reference": (cost1 <= 1.01 * copt) if copt else None,
                   "cost_after_swap_steps": cost_after, "cost_monotone": cost_monotone, "columns_same_multiset": same_multiset, "replicas_equal": replicas_equal,
                   "exchange": ("p2p write-through + flag barrier" if matcher.p2p else "pack + ncclAllGather + unpack") if world > 1 else "none"},
     }
@@ -482,6 +493,157 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not (same_multiset and cost_monotone and replicas_equal):
+        raise SystemExit("sharded matcher invariant violated: %r" % (line["match"],))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm, BASELINE configs[4]
+def run_b200_c5(args):
+    """4096x4096 RGBA, 8 cyclic key frames (16.7 M atoms, 1 GiB trajectory table), 512 output frames.  STRONG scaling:
+    matching is sharded by key-frame column phases (rank g refines every world-th column of the even / odd phase, then
+    the refined columns go to every replica), rendering by contiguous output-frame range.  One step = one sweep of the
+    matcher over all 8 columns (64 rounds per column) + the rank's share of the 512 frames."""
+    import torch
+    from atomorph_b200 import engine as eng
+    from atomorph_b200 import scenes
+    from atomorph_b200 import dist as amd
+
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peak, peak_kind = measured_peak()
+    size = args.size if args.size != 1024 else 4096
+    F, H = 512, 8
+    images = scenes.rotating_shapes(size, H)
+    e = eng.Engine(local_rank, seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=100000)
+    e.load_images(images)
+    del images
+    e.step(8)
+    assert e.state() == eng.STATE_ATOM_MORPHING
+    A = e.table_device_ptr(0)[1]
+    P = size * size
+    matcher = amd.ShardedMatcher(e, rank, world, device=dev, seed=1, p2p=False)
+    if world > 1:
+        e.table_broadcast(0)
+        matcher.p2p = os.environ.get("AMX_DIST_NCCL") is None and e.comm_enable_p2p()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cost0 = e.cost()
+    for _ in range(4):                                  # untimed: a partly matched table (the tiles the renderer sees depend on it)
+        matcher.run_sweep(epochs=2, rounds=64)
+    cost1 = e.cost()
+    hash_before = [e.column_hash(j) for j in range(H)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        matcher.run_sweep(epochs=1, rounds=64)
+    st1 = e.swap_stats()
+    barrier()
+    ms_swap = 0.0
+    n0 = e.launch_count()
+    for _ in range(args.steps):
+        e.timer_start()
+        matcher.run_sweep(epochs=1, rounds=64)
+        ms_swap += e.timer_stop()
+        barrier()
+    st2 = e.swap_stats()
+    if world > 1:
+        e.comm_check()
+    cost2 = e.cost()
+    hash_after = [e.column_hash(j) for j in range(H)]
+    same_multiset = all(a[1] == b[1] for a, b in zip(hash_before, hash_after))
+    cost_monotone = cost2 <= cost1
+    replicas_equal = True
+    if world > 1:
+        hv = torch.tensor([[v[0] >> 32, v[0] & 0xffffffff] for v in hash_after] + [[int(same_multiset), int(cost_monotone)]],
+                          dtype=torch.int64, device=dev).reshape(-1)
+        lo, hi = hv.clone(), hv.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_equal = bool(torch.equal(lo[:-2], hi[:-2]))
+        same_multiset, cost_monotone = bool(lo[-2]), bool(lo[-1])
+    proposals = int(st2[0] - st1[0])                    # this rank's proposals in the timed sweeps
+
+    # render: this rank's frame range, in chunks of 16 frames through one device buffer (inputs resident, far larger than L2)
+    e.render_prepare()
+    a, b = amd.frame_range(F, rank, world)
+    CH = 16
+    out = torch.empty((CH, size, size), dtype=torch.int32, device=dev)
+    chunks = [np.arange(c, min(c + CH, b)) / float(F) for c in range(a, b, CH)]
+
+    def render_pass():
+        for ts in chunks:
+            e.render_into(ts, out.data_ptr(), True)
+    for _ in range(min(args.warmup, 1)):
+        render_pass()
+    barrier()
+    ms_render = 0.0
+    for _ in range(args.steps):
+        e.timer_start()
+        render_pass()
+        ms_render += e.timer_stop()
+        barrier()
+    launches = e.launch_count() - n0
+    # e2e: the same frames through the C-ABI into pinned HOST memory (one ring of 16 frames), table uploaded from the host first
+    chain_words = e.chains()
+    for c in chain_words:
+        t = torch.from_numpy(np.ascontiguousarray(c["words"]).view(np.int64)).pin_memory()
+        c["_pin"] = t
+        c["words"] = t.numpy().view(np.uint64)
+    host_out = torch.empty((CH, size, size), dtype=torch.int32).pin_memory()
+    h2d = sum(c["words"].nbytes for c in chain_words)
+    barrier()
+    t0 = time.perf_counter()
+    e.import_chains(chain_words)
+    e.render_prepare()
+    for ts in chunks:
+        e.render_into(ts, host_out.data_ptr(), False)
+    barrier()
+    s_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_render, ms_swap, s_e2e, float(proposals)], dtype=torch.float64, device=dev)
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_render, ms_swap, s_e2e = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        proposals = int(tsum[3])
+    fps = F * args.steps / (ms_render / 1000.0)
+    pps = proposals / (ms_swap / 1000.0)
+    render_bytes = A * 40 + P * 4                     # SURVEY.md section 8d: spline with h >= 4 -> 40 B/atom + 4 B/pixel
+    r_ach = render_bytes * (b - a) * args.steps / (ms_render / 1000.0) / 1e9      # per GPU
+    line = {
+        "metric": "morph frames/s at %d^2 RGBA, %d cyclic key frames (swap proposals/s in 'swap')" % (size, H),
+        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_render / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 synthetic %dx%d RGBA, %d cyclic key frames, %d atoms, spline+cosine, %d frames in total" % (size, size, H, A, F),
+                   "l2": "inputs (1 GiB table, 4 GiB sorted key points) and the output ring are larger than L2",
+                   "step": "render %d frames per GPU; swap: one sweep = 64 rounds on each of the %d columns" % (b - a, H),
+                   "parallelism": "frames: frame-range x%d; swap: key-frame columns of a phase x%d + exchange of the refined columns" % (world, world)},
+        "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "k_bin+k_tile (one launch each per batch of frames)", "bytes_per_unit": render_bytes, "unit_name": "frame", "per": "GPU"},
+        "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps,
+                 "exchange": ("p2p write-through + flag barrier" if matcher.p2p else "ncclBroadcast per column") if world > 1 else "none"},
+        "e2e": {"value": F / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int((b - a) * P * 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "render_stats": dict(e.render_stats(), path_frames=e.render_path_frames(), tiled=e.render_tiled_stats()),
+        "match": {"cost_initial": cost0, "cost_after_8_sweeps": cost1, "cost_after_timed_sweeps": cost2, "cost_monotone": cost_monotone,
+                  "columns_same_multiset": same_multiset, "replicas_equal": replicas_equal},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    if not (same_multiset and cost_monotone and replicas_equal):
+        raise SystemExit("sharded matcher invariant violated: %r" % (line["match"],))
 
 
 def main():
@@ -493,10 +655,13 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--match-rounds", type=int, default=24576, help="untimed pair-swap rounds before rendering")
+    ap.add_argument("--match-rounds", type=int, default=49152, help="untimed pair-swap rounds before rendering (C2: 24576 proposals per atom)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: BASELINE configs[1] (the bench line); c5: configs[4], 4096^2 x 8 key frames, strong scaling")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_b200_c5(args)
     else:
         run_b200(args)
 

@@ -88,3 +88,21 @@ def test_fluid_step():
         act = ref_rec[:, 7] != 0
         assert np.array_equal(rec[act][:, :22], ref_rec[act][:, :22])
         assert np.array_equal(nodes, ref_nodes)
+
+
+def test_reference_converged_cost_fixture_is_consistent():
+    """tests/golden/c2_copt.json (BASELINE.md section 3 protocol, run on the unmodified reference by make_copt.py): the legs
+    fall monotonically, and the recorded c_opt is the intercept of the least-squares line through (1/ppa, cost)."""
+    import json
+    import os
+    import numpy as np
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_copt.json")))
+    assert g["size"] == 1024 and g["atoms"] == 1024 * 1024
+    ppa = np.array([leg["proposals_per_atom"] for leg in g["legs"]], dtype=np.float64)
+    cost = np.array([leg["cost"] for leg in g["legs"]])
+    assert list(ppa) == [1000.0, 2000.0, 4000.0]
+    assert np.all(np.diff(cost) < 0) and cost[0] < g["cost_initial"] / 30
+    slope, icpt = np.polyfit(1.0 / ppa, cost, 1)
+    assert abs(icpt - g["c_opt"]) <= 1e-9 * g["c_opt"]
+    assert 100.0 < g["k"] < 140.0                      # SURVEY.md section 8c measured k ~ 110 on this scene type
+    assert g["c_opt"] < cost[-1] < 1.04 * g["c_opt"]
