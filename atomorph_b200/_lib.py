@@ -99,6 +99,8 @@ def lib():
     sig("amx_kernel_times", i32, vp, i32, vp, vp, vp)
     sig("amx_render_tiled_stats", i32, vp, vp)
     sig("amx_render_pixels", i32, vp, f64, vp)
+    sig("amx_set_lookahead", i32, vp, i32)
+    sig("amx_lookahead_stats", i32, vp, vp)
     sig("amx_background", i32, vp, f64, vp, i32)
     sig("amx_fluid_create", i32, vp, u32, u32, u32)
     sig("amx_fluid_set_particles", i32, vp, u32, vp)
@@ -120,7 +122,7 @@ AMX_SYMBOLS = [
     "amx_get_state", "amx_get_energy", "amx_blobify", "amx_blob_count", "amx_export_blobs", "amx_import_blobs",
     "amx_match_init", "amx_match_rounds", "amx_match_energy", "amx_init_chains", "amx_chain_count",
     "amx_chain_info", "amx_export_chain", "amx_import_chains", "amx_table_device_ptr", "amx_swap_rounds",
-    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_swap_local_epoch", "amx_set_swap_locality", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_comm_unique_id", "amx_comm_init", "amx_comm_destroy", "amx_comm_enable_p2p", "amx_comm_disable_p2p", "amx_comm_info", "amx_comm_check", "amx_table_broadcast", "amx_swap_part_step", "amx_swap_columns_step", "amx_swap_phase_count", "amx_column_hash", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_background",
+    "amx_swap_stats", "amx_swap_rounds_sharded", "amx_pack_owned", "amx_unpack_owned", "amx_swap_tiled_epoch", "amx_swap_local_epoch", "amx_set_swap_locality", "amx_pack_tiled", "amx_unpack_tiled", "amx_cost", "amx_comm_unique_id", "amx_comm_init", "amx_comm_destroy", "amx_comm_enable_p2p", "amx_comm_disable_p2p", "amx_comm_info", "amx_comm_check", "amx_table_broadcast", "amx_swap_part_step", "amx_swap_columns_step", "amx_swap_phase_count", "amx_column_hash", "amx_render_prepare", "amx_render", "amx_render_blob", "amx_render_stats", "amx_render_path_frames", "amx_kernel_times", "amx_render_tiled_stats", "amx_render_pixels", "amx_set_lookahead", "amx_lookahead_stats", "amx_background",
     "amx_fluid_create", "amx_fluid_set_particles", "amx_fluid_get_particles", "amx_fluid_step",
     "amx_fluid_get_nodes", "amx_launch_count", "amx_timer_start", "amx_timer_stop",
 ]

@@ -92,6 +92,7 @@ int amx_create(amx_ctx **out, int device) {
     c->e.swap_global_only = getenv("AMX_SWAP_GLOBAL") != nullptr;
     if (const char *lo = getenv("AMX_SWAP_LOCALITY")) c->e.swap_locality = (uint32_t) std::max(0, atoi(lo));   // every n-th tiled epoch pairs spatial neighbours
     if (const char *tl = getenv("AMX_RENDER_TILED")) { c->e.tiled_enabled = atoi(tl) != 0; c->e.tiled_multi = atoi(tl) >= 2; }   // 0: general A-buffer path only; 2: tiled path for multi-chain morphs too
+    if (const char *la = getenv("AMX_LOOKAHEAD")) c->e.lookahead = atoi(la) != 0;
     cudaEventCreate(&c->e.ev0);
     cudaEventCreate(&c->e.ev1);
     if (!dev_alloc(&c->e, (void **) &c->e.d_swapstats, 3 * sizeof(uint64_t), "swapstats")) { delete c; return AMX_ERR_NOMEM; }

@@ -74,6 +74,9 @@ struct Dist {
     bool p2p = false;
     pword *p2p_table = nullptr;                   // the local table the mappings belong to
     pword *peer_table[AMX_MAX_PEERS + 1] = {};    // by rank (own entry = local table)
+    pword *stage = nullptr;                       // [2][stage_cap] staging buffers the peers write their parts into (slot order), by step parity
+    pword *peer_stage[AMX_MAX_PEERS + 1] = {};
+    size_t stage_cap = 0;
     unsigned long long *flags = nullptr;          // [nranks] arrival counters written by the peers
     unsigned long long *peer_flags[AMX_MAX_PEERS + 1] = {};
     unsigned long long **d_peer_flags = nullptr;  // device copy of peer_flags
@@ -95,7 +98,9 @@ static void drop_p2p(Engine *E) {
         if (r == D->rank) continue;
         if (D->peer_table[r]) cudaIpcCloseMemHandle(D->peer_table[r]);
         if (D->peer_flags[r]) cudaIpcCloseMemHandle(D->peer_flags[r]);
+        if (D->peer_stage[r]) cudaIpcCloseMemHandle(D->peer_stage[r]);
     }
+    memset(D->peer_stage, 0, sizeof D->peer_stage);
     memset(D->peer_table, 0, sizeof D->peer_table);
     memset(D->peer_flags, 0, sizeof D->peer_flags);
     D->p2p = false; D->p2p_table = nullptr;
@@ -112,7 +117,7 @@ void engine_dist_free(Engine *E) {
     cudaStreamSynchronize(E->stream);
     drop_p2p(E);
     if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
-    dev_free(D->send); dev_free(D->recv); dev_free(D->flags); dev_free(D->d_peer_flags); dev_free(D->d_timeout); dev_free(D->d_hash);
+    dev_free(D->send); dev_free(D->recv); dev_free(D->stage); dev_free(D->flags); dev_free(D->d_peer_flags); dev_free(D->d_timeout); dev_free(D->d_hash);
     delete D;
     E->dist = nullptr;
 }
@@ -148,11 +153,19 @@ static int peer_barrier(Engine *E) {
 }
 
 static PeerCols peer_cols(Engine *E, uint32_t column) {
-    PeerCols pc; pc.n = 0;
+    PeerCols pc; pc.n = 0; pc.staged = 0;
     Dist *D = E->dist;
     if (!D || !D->p2p || D->p2p_table != E->table) return pc;
     for (uint32_t r = 0; r < D->nranks; ++r)
-        if (r != D->rank) pc.col[pc.n++] = D->peer_table[r] + (size_t) column * E->A;
+        if (r != D->rank) pc.dst[pc.n++] = D->peer_table[r] + (size_t) column * E->A;
+    return pc;
+}
+// the peers' staging buffers of parity `par` (a rank's part lands at the slot indices it owns)
+static PeerCols peer_stages(Engine *E, uint32_t par) {
+    PeerCols pc; pc.n = 0; pc.staged = 1;
+    Dist *D = E->dist;
+    for (uint32_t r = 0; r < D->nranks; ++r)
+        if (r != D->rank) pc.dst[pc.n++] = D->peer_stage[r] + (size_t) par * D->stage_cap;
     return pc;
 }
 
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(256)
 k_push_column(const pword *__restrict__ col, uint64_t n, PeerCols peers) {
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const pword w = col[i];
-        for (uint32_t p = 0; p < peers.n; ++p) peers.col[p][i] = w;
+        for (uint32_t p = 0; p < peers.n; ++p) peers.dst[p][i] = w;
     }
 }
 
@@ -210,18 +223,34 @@ int engine_swap_part_step(Engine *E, uint32_t chain, uint32_t y, uint64_t step, 
     const uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
     pword *col = E->table + (size_t) y * E->A;
     const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
-    const bool h2 = E->h == 2, p2p = N > 1 && p2p_ready(E);
-    PeerCols nopeers; nopeers.n = 0;
+    const bool h2 = E->h == 2;
+    const bool p2p = N > 1 && p2p_ready(E) && D->stage && D->stage_cap >= ((size_t) 1 << k);
+    const uint32_t par = (uint32_t) (step & 1ull);
+    PeerCols nopeers; nopeers.n = 0; nopeers.staged = 0;
     for (uint32_t j = 0; j < sub_epochs; ++j) {
         tilemap_set_inner(tm, E->p.seed, 0x100u + chain, step * 4096ull + j, kk);
         const bool last = j + 1 == sub_epochs;
+        // the last sub-epoch also writes every refined tile, as one contiguous run, into the staging buffer of every peer
         launch_swap_tiled(E, h2, tb, col, prev, next, off, (uint32_t) w, tm, tile0, ntl, rounds, (step << 24) + ((uint64_t) j << 8),
-                          (last && p2p) ? peer_cols(E, y) : nopeers);
+                          (last && p2p) ? peer_stages(E, par) : nopeers);
     }
     E->render_ready = false;
     if (E->check("sharded swap step")) return AMX_ERR_CUDA;
     if (N == 1) return AMX_OK;
-    if (p2p) return peer_barrier(E);
+    if (p2p) {
+        // everybody's tiles have arrived once the flag barrier is passed; the slots of the other ranks go to their atoms (the
+        // slot -> atom map of the step's LAST sub-epoch, identical on every rank).  Staging buffers alternate with the step
+        // parity, so a fast peer's next step never lands in the buffer this rank is still reading.
+        int rc = peer_barrier(E);
+        if (rc != AMX_OK) return rc;
+        const uint32_t n = 1u << kk;
+        const pword *stage = D->stage + (size_t) par * D->stage_cap;
+        for (uint32_t r = 0; r < N; ++r) {
+            if (r == rank) continue;
+            launch_unpack_tiled(E, col, off, (uint32_t) w, tm, r * n, n, stage);
+        }
+        return E->check("sharded swap unpack") ? AMX_ERR_CUDA : AMX_OK;
+    }
     // NCCL: the part is a contiguous slot range of the OUTER bijection -> pack, all-gather, unpack, all on E->stream
     if (!D->comm) { E->err = "sharded step: amx_comm_init first"; return AMX_ERR_STATE; }
     const size_t n = (size_t) 1 << kk;
@@ -233,7 +262,7 @@ int engine_swap_part_step(Engine *E, uint32_t chain, uint32_t y, uint64_t step, 
     tm.imask = 0u;                                   // slots of the outer bijection
     launch_pack_tiled(E, col, off, (uint32_t) w, tm, (uint32_t) (rank * n), (uint32_t) n, D->send);
     if (nccl_fail(E, g_nccl.AllGather(D->send, D->recv, n, ncclUint64, D->comm, E->stream), "ncclAllGather")) return AMX_ERR_CUDA;
-    launch_unpack_tiled(E, col, off, (uint32_t) w, tm, (uint32_t) (n * N), D->recv);
+    launch_unpack_tiled(E, col, off, (uint32_t) w, tm, 0u, (uint32_t) (n * N), D->recv);
     return E->check("sharded swap exchange") ? AMX_ERR_CUDA : AMX_OK;
 }
 
@@ -256,7 +285,7 @@ int engine_swap_columns_step(Engine *E, int32_t chain, uint32_t phase, uint64_t 
     dist_phase_columns(E->h, phase, cols);
     const bool p2p = N > 1 && p2p_ready(E);
     const bool h2 = E->h == 2;
-    PeerCols nopeers; nopeers.n = 0;
+    PeerCols nopeers; nopeers.n = 0; nopeers.staged = 0;
     for (size_t i = 0; i < cols.size(); ++i) {
         if (i % N != rank) continue;
         const uint32_t y = cols[i];
@@ -273,10 +302,10 @@ int engine_swap_columns_step(Engine *E, int32_t chain, uint32_t phase, uint64_t 
                 const int tb = pick_tile_bits(E, k);
                 for (uint32_t e = 0; e < epochs; ++e) {
                     TileMap tm = make_tilemap(E->p.seed, 0x200u + c, (step * 64ull + y) * 4096ull + e, k);
-                    const bool last = e + 1 == epochs;
+                    // (whole columns travel as one contiguous copy below: scattered 8-byte peer stores from inside the kernel
+                    // would fill NVLink packets to a quarter)
                     launch_swap_tiled(E, h2, tb, col, prev, next, off, (uint32_t) w, tm, 0u, 1u << (k - (unsigned) tb), rounds,
-                                      (step << 24) + ((uint64_t) y << 16) + ((uint64_t) e << 8), (last && p2p && c1 - c0 == 1) ? peer_cols(E, y) : nopeers);
-                    if (last && p2p && c1 - c0 == 1) pushed = true;
+                                      (step << 24) + ((uint64_t) y << 16) + ((uint64_t) e << 8), nopeers);
                 }
             } else {
                 int rc = engine_swap_rounds(E, (int32_t) c, (int32_t) y, (uint64_t) epochs * rounds);
@@ -369,11 +398,24 @@ int amx_comm_enable_p2p(amx_ctx *ctx) {
         cudaMemset(D->flags, 0, 64 * sizeof(unsigned long long));
         cudaMemset(D->d_timeout, 0, 4);
     }
-    // handles: [table | flags | ok] per rank
-    struct Rec { cudaIpcMemHandle_t table, flags; uint64_t ok, seq; };
+    // staging for the parts of a step (h == 2): two buffers of 2^k slots for the widest chain
+    if (E->h == 2) {
+        uint64_t wmax = 2;
+        for (uint32_t c = 0; c < E->nchains; ++c) wmax = std::max<uint64_t>(wmax, E->chain_off[c + 1] - E->chain_off[c]);
+        const size_t cap = (size_t) 1 << ceil_log2(wmax);
+        if (D->stage_cap < cap) {
+            dev_free(D->stage); D->stage = nullptr; D->stage_cap = 0;
+            if (!dev_alloc(E, (void **) &D->stage, 2 * cap * sizeof(pword), "peer staging")) return AMX_ERR_NOMEM;
+            D->stage_cap = cap;
+        }
+    }
+    // handles: [table | flags | stage | ok] per rank
+    struct Rec { cudaIpcMemHandle_t table, flags, stage; uint64_t ok, seq, stage_cap; };
     Rec mine;
     memset(&mine, 0, sizeof mine);
-    mine.ok = (cudaIpcGetMemHandle(&mine.table, E->table) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, D->flags) == cudaSuccess) ? 1u : 0u;
+    mine.ok = (cudaIpcGetMemHandle(&mine.table, E->table) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, D->flags) == cudaSuccess &&
+               (!D->stage || cudaIpcGetMemHandle(&mine.stage, D->stage) == cudaSuccess)) ? 1u : 0u;
+    mine.stage_cap = D->stage ? D->stage_cap : 0;
     mine.seq = D->barrier_seq;
     cudaGetLastError();
     Rec *d_recs = nullptr;
@@ -389,11 +431,16 @@ int amx_comm_enable_p2p(amx_ctx *ctx) {
     unsigned long long seq = 0;
     for (uint32_t r = 0; r < N; ++r) { ok = ok && all[r].ok; seq = std::max<unsigned long long>(seq, all[r].seq); }
     for (uint32_t r = 0; r < N && ok; ++r) {
-        if (r == D->rank) { D->peer_table[r] = E->table; D->peer_flags[r] = D->flags; continue; }
+        if (r == D->rank) { D->peer_table[r] = E->table; D->peer_flags[r] = D->flags; D->peer_stage[r] = D->stage; continue; }
         void *pt = nullptr, *pf = nullptr;
         if (cudaIpcOpenMemHandle(&pt, all[r].table, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
             cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; if (pt) cudaIpcCloseMemHandle(pt); break; }
         D->peer_table[r] = (pword *) pt; D->peer_flags[r] = (unsigned long long *) pf;
+        if (D->stage) {
+            void *ps = nullptr;
+            if (all[r].stage_cap != D->stage_cap || cudaIpcOpenMemHandle(&ps, all[r].stage, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+            D->peer_stage[r] = (pword *) ps;
+        }
     }
     cudaGetLastError();
     // everybody must agree: one rank that cannot map means the NCCL path for all

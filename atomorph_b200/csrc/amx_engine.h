@@ -125,6 +125,9 @@ struct Engine {
 
     // render
     bool      render_ready = false;
+    uint64_t  prepare_count = 0;           // table refreshes so far (a key of the frame look-ahead ring)
+    void     *pix_ring = nullptr;          // amx_render.cu: PixRing, the look-ahead of amx_render_pixels
+    bool      lookahead = true;            // amx_set_lookahead / AMX_LOOKAHEAD=0
     // render inputs per interval, atoms sorted by the tile of their mid-interval position (amx_render.cu: RIn)
     uint32_t *rc1 = nullptr, *rc2 = nullptr;
     double   *rlag = nullptr, *rslope = nullptr;

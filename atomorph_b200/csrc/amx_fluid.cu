@@ -3,19 +3,24 @@
  *
  * Reference: FluidModel::step (fluidmodel.cpp:165-580; Grant Kot's MPM with atomorph's
  * customisations: inactive particles, colour diffusion through nodes, attractor, freedom
- * radius).  The reference walks particles serially and scatters into AoS nodes; here every
- * pass is one kernel over particles (SoA doubles) or nodes (SoA doubles), scatters are double
- * atomicAdd into the 3x3 quadratic B-spline stencil, so node sums differ from the reference only
- * by summation order (<< 1e-5 relative).  The node colour, a strength-weighted running mean in
+ * radius).  The reference walks particles serially and scatters into AoS nodes.  Here the particles
+ * are ordered by base cell once per step (positions only move in the last pass) and every
+ * particle -> node transfer is a GATHER: one thread per node walks the particles of the 3 x 3
+ * base cells whose quadratic B-spline stencil covers the node -- three contiguous runs of the
+ * ordered list -- and sums their contributions in registers.  No atomics, a fixed summation order
+ * (results are reproducible run to run), and node sums that differ from the reference's only by
+ * that order (<< 1e-5 relative).  The node colour, a strength-weighted running mean in
  * the reference (fluidmodel.cpp:234-244), is kept as sum(w*c) and sum(w): the G2P pass only ever
  * uses mean*weight (fluidmodel.cpp:463-469), which is that sum.
  *
  * Passes per step (algorithmic bytes: Np*(120 read + 64 written) + Ng*2*104, section 8d):
- *   clear grid | P2G mass/gradients/colour | pressure+wall forces -> node acceleration |
- *   node a/=m | particle velocity update + momentum scatter | node v/=m | G2P gather + move
+ *   order by cell (keys, radix sort, cell starts) | nodes <- mass/gradients, cells <- colour | colour box sum |
+ *   particles: pressure + wall force | nodes <- acceleration / m | particles: velocity update |
+ *   nodes <- momentum / m | colour box sum | G2P gather + move
  *
  * Wall clamping uses the counter-based RNG where the reference calls rand() (fluidmodel.cpp:553-566).
  */
+#include <cub/cub.cuh>
 #include "amx_engine.h"
 #include "amx_fluid.h"
 
@@ -44,55 +49,113 @@ __device__ __forceinline__ void particle_weights(double x, double y, PW &w) {
 #define PFI(k) pf[(size_t) (k) * n + i]
 #define NODE(k, idx) nf[(size_t) (k) * ng + (idx)]
 
-// The colour part of the scatter (fluidmodel.cpp:229-246) adds the SAME five values (strength * r, g, b, a and strength) to
-// all nine nodes of a particle's 3x3 stencil.  Node (X, Y) therefore receives the sum over the particles whose base cell
-// (cx, cy) lies in [X-2, X] x [Y-2, Y]: a particle adds its five values ONCE to its base cell (`cell`, 5 atomics instead
-// of 45) and k_fluid_colour_box -- a 3x3 box sum over the cell sums, staged through shared memory -- turns them into the
-// node fields.  (The scatter is bound by the L2 atomic rate; the sums are re-associated: deviations ~1e-16 relative.)
-__global__ void __launch_bounds__(128)
-k_fluid_p2g(const double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
-            double *__restrict__ nf, double *__restrict__ cell, uint32_t gsx, uint32_t gsy) {
+// ---- ordering by base cell -------------------------------------------------------------------------------------------
+// key = base cell (cy * gsx + cx) of an active particle, gsx * gsy for an inactive one (sorted behind everything)
+__global__ void __launch_bounds__(256)
+k_fluid_keys(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, uint32_t gsx, uint32_t gsy,
+             uint32_t *__restrict__ key, uint32_t *__restrict__ idx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !active[i]) return;
-    size_t ng = (size_t) gsx * gsy;
-    PW w;
-    particle_weights(PFI(PF_X), PFI(PF_Y), w);
-    double strength = PFI(PF_STRENGTH);
-    bool colour = mature[i] && strength > 0.0;
-    double r = PFI(PF_R), g = PFI(PF_G), b = PFI(PF_B), a = PFI(PF_A);
-    // the whole stencil inside the grid (always, away from the walls): colour through the base cell
-    const bool boxed = colour && (uint32_t) w.cx + 2u < gsx && (uint32_t) w.cy + 2u < gsy && w.cx >= 0 && w.cy >= 0;
-    if (boxed) {
-        const size_t cidx = (size_t) w.cy * gsx + (size_t) w.cx;
-        atomicAdd(&cell[0 * ng + cidx], strength * r);
-        atomicAdd(&cell[1 * ng + cidx], strength * g);
-        atomicAdd(&cell[2 * ng + cidx], strength * b);
-        atomicAdd(&cell[3 * ng + cidx], strength * a);
-        atomicAdd(&cell[4 * ng + cidx], strength);
-        colour = false;
+    if (i >= n) return;
+    uint32_t k = gsx * gsy;
+    if (active[i]) {
+        const int cx = (int) (PFI(PF_X) - 0.5), cy = (int) (PFI(PF_Y) - 0.5);
+        if (cx >= 0 && cy >= 0 && (uint32_t) cx < gsx && (uint32_t) cy < gsy) k = (uint32_t) cy * gsx + (uint32_t) cx;
     }
-    for (int ii = 0; ii < 3; ++ii)
-        for (int jj = 0; jj < 3; ++jj) {
-            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
-            if (nx >= gsx || ny >= gsy) continue;
-            size_t idx = (size_t) ny * gsx + nx;
-            double phi = w.px[ii] * w.py[jj];
-            // mass and density of a node are the same sum (the particle mass is 1, fluidmodel.cpp:222-228): ONE atomic; the
-            // scatter is bound by the L2 atomic rate (~200 G double atomics/s), so every atomic saved counts.  NF_D stays unused.
-            atomicAdd(&NODE(NF_M, idx), phi * 1.0);
-            atomicAdd(&NODE(NF_GX, idx), w.gx[ii] * w.py[jj]);
-            atomicAdd(&NODE(NF_GY, idx), w.px[ii] * w.gy[jj]);
-            if (colour) {
-                atomicAdd(&NODE(NF_R, idx), strength * r);
-                atomicAdd(&NODE(NF_G, idx), strength * g);
-                atomicAdd(&NODE(NF_B, idx), strength * b);
-                atomicAdd(&NODE(NF_A, idx), strength * a);
-                atomicAdd(&NODE(NF_W, idx), strength);
-            }
-        }
+    key[i] = k;
+    idx[i] = i;
 }
 
-// node colour fields += 3x3 box sum of the cell sums: node (X, Y) <- cells [X-2, X] x [Y-2, Y].  One CTA = a 32x8 block of
+// cs[c] = number of particles with a key below c (first sorted particle of cell c), c in [0, ng]; rank = inverse of perm;
+// sorted copies of the positions
+__global__ void __launch_bounds__(256)
+k_fluid_bounds(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ perm, const double *__restrict__ pf, uint32_t n, uint32_t ng,
+               uint32_t *__restrict__ cs, uint32_t *__restrict__ rank, double *__restrict__ sx, double *__restrict__ sy) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t k = skey[s], i = perm[s];
+    const uint32_t first = s ? skey[s - 1] + 1u : 0u;
+    for (uint32_t c = first; c <= k && c <= ng; ++c) cs[c] = s;
+    if (s == n - 1u) for (uint32_t c = k + 1u; c <= ng; ++c) cs[c] = n;
+    rank[i] = s;
+    sx[s] = PFI(PF_X);
+    sy[s] = PFI(PF_Y);
+}
+
+// quadratic B-spline weight and gradient of stencil offset o (0, 1, 2) at t = cell - position, exactly the expressions of
+// particle_weights: ((a t) t + b t) + c and g t + h with a = -1, b = 0 for the middle one
+__device__ __forceinline__ void bspline(double t0, int o, double *p, double *g) {
+    double t = t0;
+    if (o >= 1) t += 1.0;
+    if (o >= 2) t += 1.0;
+    if (o == 1) { *p = (-t * t + 0.75); *g = (-2.0 * t); }
+    else {
+        const double lin = o == 0 ? 1.5 : -1.5;
+        *p = (0.5 * t * t + lin * t + 1.125);
+        *g = (t + lin);
+    }
+}
+
+// One thread per NODE (X, Y): the particles whose 3 x 3 stencil covers it sit in base cells [X-2, X] x [Y-2, Y], i.e. in three
+// contiguous runs of the ordered list.  MODE 0: mass, mass gradients (fluidmodel.cpp:222-228) and, for the node's own cell,
+// the colour sums strength * (r, g, b, a, 1) of its mature particles (229-246: the same five values go to all nine nodes
+// of a stencil, so node (X, Y) receives the 3 x 3 box sum of the cell sums -- k_fluid_colour_box).  MODE 1: acceleration
+// from pressure and wall forces, divided by the mass (349-369); q0 = pressure, q1 = fx, q2 = fy.  MODE 2: momentum divided
+// by the mass (423-443); q0 = u * mass, q1 = v * mass (zero for immature particles).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_fluid_nodes(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ q0, const double *__restrict__ q1,
+              const double *__restrict__ q2, const uint32_t *__restrict__ cs, const uint32_t *__restrict__ perm, const double *__restrict__ pf,
+              const uint8_t *__restrict__ mature, uint32_t n, double *__restrict__ nf, double *__restrict__ cell, uint32_t gsx, uint32_t gsy) {
+    const uint32_t X = blockIdx.x * 32u + (threadIdx.x & 31u), Y = blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (X >= gsx || Y >= gsy) return;
+    const size_t ng = (size_t) gsx * gsy, idx = (size_t) Y * gsx + X;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const uint32_t xa = X >= 2u ? X - 2u : 0u;
+    for (uint32_t jj = 0; jj < 3u && jj <= Y; ++jj) {
+        const uint32_t cy = Y - jj;
+        const uint32_t s0 = cs[cy * gsx + xa], s1 = cs[cy * gsx + X + 1u];
+        for (uint32_t s = s0; s < s1; ++s) {
+            const double x = sx[s], y = sy[s];
+            const int cx = (int) (x - 0.5);
+            double px, gx, py, gy;
+            bspline((double) (unsigned) cx - x, (int) X - cx, &px, &gx);
+            bspline((double) cy - y, (int) jj, &py, &gy);
+            if (MODE == 0) {
+                a0 += (px * py) * 1.0;
+                a1 += gx * py;
+                a2 += px * gy;
+            } else if (MODE == 1) {
+                const double phi = px * py, pressure = q0[s];
+                a0 += -((gx * py) * pressure) + q1[s] * phi;
+                a1 += -((px * gy) * pressure) + q2[s] * phi;
+            } else {
+                const double phi = px * py;
+                a0 += phi * q0[s];
+                a1 += phi * q1[s];
+            }
+        }
+    }
+    if (MODE == 0) {
+        NODE(NF_M, idx) = a0; NODE(NF_GX, idx) = a1; NODE(NF_GY, idx) = a2;
+        // the node's own base cell: colour sums of its mature particles
+        double cr = 0.0, cg = 0.0, cb = 0.0, ca = 0.0, cw = 0.0;
+        for (uint32_t s = cs[idx], s1 = cs[idx + 1u]; s < s1; ++s) {
+            const uint32_t i = perm[s];
+            const double strength = PFI(PF_STRENGTH);
+            if (mature[i] && strength > 0.0) {
+                cr += strength * PFI(PF_R); cg += strength * PFI(PF_G); cb += strength * PFI(PF_B); ca += strength * PFI(PF_A); cw += strength;
+            }
+        }
+        cell[0 * ng + idx] = cr; cell[1 * ng + idx] = cg; cell[2 * ng + idx] = cb; cell[3 * ng + idx] = ca; cell[4 * ng + idx] = cw;
+    } else {
+        const double m = NODE(NF_M, idx);
+        if (m > 0.0) { a0 /= m; a1 /= m; }
+        NODE(MODE == 1 ? NF_AX : NF_U, idx) = a0;
+        NODE(MODE == 1 ? NF_AY : NF_V, idx) = a1;
+    }
+}
+
+// node colour fields = 3x3 box sum of the cell sums: node (X, Y) <- cells [X-2, X] x [Y-2, Y].  One CTA = a 32x8 block of
 // nodes; the 34x10 cells it needs are staged in shared memory per field.
 __global__ void __launch_bounds__(256)
 k_fluid_colour_box(const double *__restrict__ cell, double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
@@ -113,7 +176,7 @@ k_fluid_colour_box(const double *__restrict__ cell, double *__restrict__ nf, uin
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) sum += s[ty + dy][tx + dx];
-            if (sum != 0.0) NODE(NF_R + f, (size_t) Y * gsx + X) += sum;
+            NODE(NF_R + f, (size_t) Y * gsx + X) = sum;
         }
         __syncthreads();
     }
@@ -150,13 +213,12 @@ k_fluid_colour_gather(const double *__restrict__ nf, double *__restrict__ cell, 
 }
 
 __global__ void __launch_bounds__(128)
-k_fluid_forces(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
+k_fluid_forces(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, const double *__restrict__ nf, uint32_t gsx, uint32_t gsy,
+               const uint32_t *__restrict__ rank, double *__restrict__ q0, double *__restrict__ q1, double *__restrict__ q2) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !active[i]) return;
     size_t ng = (size_t) gsx * gsy;
     double x = PFI(PF_X), y = PFI(PF_Y);
-    PW w;
-    particle_weights(x, y, w);
     // fluidmodel.cpp:275-317 cubic density interpolant from the 4 corner nodes
     uint32_t cx = (uint32_t) (int) x, cy = (uint32_t) (int) y;
     uint32_t cxi = cx + 1, cyi = cy + 1;
@@ -188,22 +250,9 @@ k_fluid_forces(const double *__restrict__ pf, const uint8_t *__restrict__ active
     else if (x > (double) (gsx - 5)) fx += 1.0 * ((double) (gsx - 5) - x);
     if (y < 4.0) fy += 1.0 * (4.0 - y);
     else if (y > (double) (gsy - 5)) fy += 1.0 * ((double) (gsy - 5) - y);
-    for (int ii = 0; ii < 3; ++ii)
-        for (int jj = 0; jj < 3; ++jj) {
-            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
-            if (nx >= gsx || ny >= gsy) continue;
-            size_t idx = (size_t) ny * gsx + nx;
-            double phi = w.px[ii] * w.py[jj];
-            atomicAdd(&NODE(NF_AX, idx), -((w.gx[ii] * w.py[jj]) * pressure) + fx * phi);
-            atomicAdd(&NODE(NF_AY, idx), -((w.px[ii] * w.gy[jj]) * pressure) + fy * phi);
-        }
-}
-
-__global__ void __launch_bounds__(256) k_fluid_node_div(double *__restrict__ nf, size_t ng, int ka, int kb) {
-    size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ng) return;
-    double m = NODE(NF_M, idx);
-    if (m > 0.0) { NODE(ka, idx) /= m; NODE(kb, idx) /= m; }
+    // the scatter of -(gradient * pressure) + force * phi into the nine nodes is done by k_fluid_nodes<1> as a gather
+    const uint32_t s = rank[i];
+    q0[s] = pressure; q1[s] = fx; q2[s] = fy;
 }
 
 // attractor pull, shared by the velocity and the move pass (fluidmodel.cpp:385-413 / 505-548)
@@ -224,7 +273,7 @@ __device__ __forceinline__ void pull_towards(double x1, double y1, double x2, do
 
 __global__ void __launch_bounds__(128)
 k_fluid_velocity(double *__restrict__ pf, const uint8_t *__restrict__ active, const uint8_t *__restrict__ mature, uint32_t n,
-                 double *__restrict__ nf, uint32_t gsx, uint32_t gsy) {
+                 const double *__restrict__ nf, uint32_t gsx, uint32_t gsy, const uint32_t *__restrict__ rank, double *__restrict__ q0, double *__restrict__ q1) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !active[i]) return;
     size_t ng = (size_t) gsx * gsy;
@@ -247,15 +296,9 @@ k_fluid_velocity(double *__restrict__ pf, const uint8_t *__restrict__ active, co
     PFI(PF_V) = v;
     double mu = 1.0 * u, mv = 1.0 * v;
     if (!mature[i]) { mu *= 0.0; mv *= 0.0; }
-    for (int ii = 0; ii < 3; ++ii)
-        for (int jj = 0; jj < 3; ++jj) {
-            uint32_t nx = (uint32_t) (w.cx + ii), ny = (uint32_t) (w.cy + jj);
-            if (nx >= gsx || ny >= gsy) continue;
-            size_t idx = (size_t) ny * gsx + nx;
-            double phi = w.px[ii] * w.py[jj];
-            atomicAdd(&NODE(NF_U, idx), phi * mu);
-            atomicAdd(&NODE(NF_V, idx), phi * mv);
-        }
+    // the momentum scatter phi * (mu, mv) into the nine nodes is done by k_fluid_nodes<2> as a gather
+    const uint32_t s = rank[i];
+    q0[s] = mu; q1[s] = mv;
 }
 
 __global__ void __launch_bounds__(128)
@@ -329,30 +372,40 @@ void engine_fluid_free(Engine *E) {
     Fluid *F = E->fluid;
     fluid_draw_free(F);
     dev_free(F->pf); dev_free(F->active); dev_free(F->mature); dev_free(F->owner); dev_free(F->aux); dev_free(F->nf); dev_free(F->cell);
+    dev_free(F->sortbuf); dev_free(F->cs); dev_free(F->sq); dev_free(F->sort_tmp);
     delete F;
     E->fluid = nullptr;
 }
 
 int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
     Fluid *F = E->fluid;
-    size_t ng = (size_t) F->gx * F->gy;
-    uint32_t n = F->n;
-    cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream);
-    cudaMemsetAsync(F->cell, 0, ng * 5 * 8, E->stream);
-    if (n) {
-        k_fluid_p2g<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->cell, F->gx, F->gy);
-        k_fluid_colour_box<<<dim3(div_up(F->gx, 32), div_up(F->gy, 8)), 256, 0, E->stream>>>(F->cell, F->nf, F->gx, F->gy);
-        E->launches++;
-        k_fluid_forces<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, n, F->nf, F->gx, F->gy);
-        k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_AX, NF_AY);
-        k_fluid_velocity<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy);
-        k_fluid_node_div<<<div_up(ng, 256), 256, 0, E->stream>>>(F->nf, ng, NF_U, NF_V);
-        k_fluid_colour_gather<<<dim3(div_up(F->gx, 32), div_up(F->gy, 8)), 256, 0, E->stream>>>(F->nf, F->cell, F->gx, F->gy);
-        E->launches++;
-        k_fluid_g2p<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->cell, F->gx, F->gy, (double) steps_left, freedom_radius,
-                                                          E->p.seed, F->step_counter++);
-        E->launches += 6;
-    }
+    const size_t ng = (size_t) F->gx * F->gy;
+    const uint32_t n = F->n;
+    if (n == 0) { cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream); return E->check("fluid step") ? AMX_ERR_CUDA : AMX_OK; }
+    uint32_t *key = F->sortbuf, *skey = key + n, *idx = skey + n, *perm = idx + n, *rank = perm + n;
+    double *sx = F->sq, *sy = sx + n, *q0 = sy + n, *q1 = q0 + n, *q2 = q1 + n;
+    int key_bits = 1;
+    while ((1ull << key_bits) <= ng) ++key_bits;               // keys are 0 .. ng
+    const dim3 ngrid(div_up(F->gx, 32), div_up(F->gy, 8));
+    // order the particles by base cell: their positions do not change before the last pass of the step
+    k_fluid_keys<<<div_up(n, 256), 256, 0, E->stream>>>(F->pf, F->active, n, F->gx, F->gy, key, idx);
+    size_t tmp = F->sort_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(F->sort_tmp, tmp, key, skey, idx, perm, (int) n, 0, key_bits, E->stream);
+    k_fluid_bounds<<<div_up(n, 256), 256, 0, E->stream>>>(skey, perm, F->pf, n, (uint32_t) ng, F->cs, rank, sx, sy);
+    // P2G: mass, gradients; colour through the cell sums and their 3 x 3 box sum
+    k_fluid_nodes<0><<<ngrid, 256, 0, E->stream>>>(sx, sy, q0, q1, q2, F->cs, perm, F->pf, F->mature, n, F->nf, F->cell, F->gx, F->gy);
+    k_fluid_colour_box<<<ngrid, 256, 0, E->stream>>>(F->cell, F->nf, F->gx, F->gy);
+    // forces -> node acceleration
+    k_fluid_forces<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, n, F->nf, F->gx, F->gy, rank, q0, q1, q2);
+    k_fluid_nodes<1><<<ngrid, 256, 0, E->stream>>>(sx, sy, q0, q1, q2, F->cs, perm, F->pf, F->mature, n, F->nf, F->cell, F->gx, F->gy);
+    // particle velocities -> node velocity
+    k_fluid_velocity<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->gx, F->gy, rank, q0, q1);
+    k_fluid_nodes<2><<<ngrid, 256, 0, E->stream>>>(sx, sy, q0, q1, q2, F->cs, perm, F->pf, F->mature, n, F->nf, F->cell, F->gx, F->gy);
+    // G2P
+    k_fluid_colour_gather<<<ngrid, 256, 0, E->stream>>>(F->nf, F->cell, F->gx, F->gy);
+    k_fluid_g2p<<<div_up(n, 128), 128, 0, E->stream>>>(F->pf, F->active, F->mature, n, F->nf, F->cell, F->gx, F->gy, (double) steps_left, freedom_radius,
+                                                      E->p.seed, F->step_counter++);
+    E->launches += 11;
     return E->check("fluid step") ? AMX_ERR_CUDA : AMX_OK;
 }
 
@@ -365,10 +418,15 @@ int fluid_alloc(Engine *E, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle
     if (!dev_alloc(E, (void **) &F->pf, n * PF_COUNT * 8, "fluid particles") || !dev_alloc(E, (void **) &F->active, n, "fluid active") ||
         !dev_alloc(E, (void **) &F->mature, n, "fluid mature") || !dev_alloc(E, (void **) &F->owner, n, "fluid owner") ||
         !dev_alloc(E, (void **) &F->aux, n * 3 * 8, "fluid aux") || !dev_alloc(E, (void **) &F->nf, ng * NF_COUNT * 8, "fluid nodes") ||
-        !dev_alloc(E, (void **) &F->cell, ng * 5 * 8, "fluid cell sums")) {
+        !dev_alloc(E, (void **) &F->cell, ng * 5 * 8, "fluid cell sums") ||
+        !dev_alloc(E, (void **) &F->sortbuf, (n ? n : 1) * 5 * 4, "fluid order") || !dev_alloc(E, (void **) &F->cs, (ng + 1) * 4, "fluid cell starts") ||
+        !dev_alloc(E, (void **) &F->sq, (n ? n : 1) * 5 * 8, "fluid ordered factors")) {
         engine_fluid_free(E);
         return AMX_ERR_NOMEM;
     }
+    F->sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, F->sort_tmp_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (int) n, 0, 32, E->stream);
+    if (!dev_alloc(E, &F->sort_tmp, F->sort_tmp_bytes, "fluid sort workspace")) { engine_fluid_free(E); return AMX_ERR_NOMEM; }
     cudaMemsetAsync(F->pf, 0, n * PF_COUNT * 8 + 0, E->stream);
     cudaMemsetAsync(F->active, 0, n, E->stream);
     cudaMemsetAsync(F->mature, 0, n, E->stream);

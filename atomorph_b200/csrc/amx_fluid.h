@@ -22,6 +22,12 @@ struct Fluid {
     double *aux = nullptr;       // [3][n] frame_key, source_pos, destination_pos (as handed in / out by the C-ABI)
     double *nf = nullptr;        // [NF_COUNT][gx*gy]
     double *cell = nullptr;      // [5][gx*gy] colour sums per base cell of a step (k_fluid_p2g -> k_fluid_colour_box)
+    // particles ordered by base cell, rebuilt every step (amx_fluid.cu: the node passes gather instead of scattering)
+    uint32_t *sortbuf = nullptr; // key, key sorted, index, perm (sorted -> particle), rank (particle -> sorted): [5][n]
+    uint32_t *cs = nullptr;      // [gx*gy + 1] first sorted particle of every base cell (monotone; [gx*gy] = active particles)
+    double   *sq = nullptr;      // [5][n] in sorted order: x, y and up to three per-particle factors of the pass at hand
+    void     *sort_tmp = nullptr;
+    size_t    sort_tmp_bytes = 0;
     uint64_t step_counter = 0;
     FluidDraw *draw = nullptr;   // driver state, allocated on the first fluid frame
 };

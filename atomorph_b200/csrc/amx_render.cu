@@ -41,6 +41,9 @@
 #include <random>
 #include <numeric>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cub/cub.cuh>
 #include <cuda_pipeline.h>
 #include "amx_engine.h"
@@ -1361,7 +1364,10 @@ k_prepare(const pword *__restrict__ table, const uint32_t *__restrict__ perm, co
 
 // ------------------------------------------------------------------------------------------ host side
 
+void engine_pixring_free(Engine *E);
+
 void engine_render_free(Engine *E) {
+    if (E->pix_ring) { if (E->copy_stream) cudaStreamSynchronize(E->copy_stream); engine_pixring_free(E); }
     dev_free(E->rc1); dev_free(E->rc2); dev_free(E->rlag); dev_free(E->rslope);
     E->rc1 = E->rc2 = nullptr; E->rlag = E->rslope = nullptr;
     dev_free(E->rpts); dev_free(E->ratom); dev_free(E->rchain);
@@ -1524,6 +1530,7 @@ int engine_render_prepare(Engine *E) {
     bool bad = !okay || E->fail(cudaStreamSynchronize(E->stream), "render prepare") || E->check("render prepare");
     if (bad) return okay ? AMX_ERR_CUDA : AMX_ERR_NOMEM;
     E->render_ready = true;
+    E->prepare_count++;
     E->tiled_blocked = false;                 // a new table gets a new chance on the tiled path
     return AMX_OK;
 }
@@ -2016,6 +2023,110 @@ int engine_render_blob(Engine *E, uint32_t blob, double t, uint64_t cap, uint16_
     return AMX_OK;
 }
 
+// ---- frame fetch with look-ahead (the get_pixels path of the facade) --------------------------------
+// morph::get_pixels(t, &vector) is called one frame at a time, usually on a regular grid t = f / N.  Rendering one frame
+// per call wastes the batch renderer (8 frames per launch pair) and serialises render -> convert -> copy -> wait.  The ring
+// below turns a miss into ONE batch: the requested frame plus the next ones at the caller's observed stride are rendered,
+// converted to am::pixel records on the device and copied to pinned host slots on the copy stream; the call returns as
+// soon as ITS frame has arrived, the others keep travelling while the caller consumes.  Later calls are served from the
+// ring (one event wait + a host copy, split over a few threads).  A hit requires the requested time to be BIT-equal to a
+// predicted one -- times are predicted as (f + k) / N only when the last two requests are reproduced exactly by that
+// formula -- so a served frame is exactly the frame a direct render of that time gives.  Anything that changes the picture
+// (table refresh, parameters, resolution) invalidates the ring.
+struct RingKey { uint64_t prepare; uint32_t w, h, motion, fading, density, feather, keepbg, show, fluid, seed, finite, nframes; };
+struct PixRing {
+    static const uint32_t MAXD = 8;
+    uint32_t depth = 0;
+    size_t np = 0;
+    uint32_t *d_rgba = nullptr;          // [depth][np]
+    uint2 *d_rec = nullptr;              // [depth][np]
+    uint64_t *h_rec = nullptr;           // pinned [depth][np]
+    cudaEvent_t ev[MAXD] = {};
+    double t[MAXD] = {};
+    bool valid[MAXD] = {};
+    RingKey key = {};
+    bool have_last = false;
+    double last_t = 0.0;
+    uint64_t hits = 0, misses = 0;
+    // host copy helpers
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    const char *src = nullptr; char *dst = nullptr; size_t bytes = 0;
+    uint32_t ticket = 0, pending = 0;
+    bool quit = false;
+    void worker(uint32_t id, uint32_t nworkers) {
+        uint32_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return quit || ticket != seen; });
+            if (quit) return;
+            seen = ticket;
+            const size_t chunk = (bytes / (nworkers + 1) + 63) & ~(size_t) 63;
+            const size_t o = std::min(bytes, (size_t) (id + 1) * chunk), e = std::min(bytes, o + chunk);
+            const char *s = src; char *d = dst;
+            lk.unlock();
+            if (e > o) memcpy(d + o, s + o, e - o);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void copy(void *d, const void *s, size_t n) {
+        const uint32_t nw = (uint32_t) pool.size();
+        if (nw == 0 || n < (1u << 20)) { memcpy(d, s, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = (const char *) s; dst = (char *) d; bytes = n; pending = nw; ++ticket;
+        }
+        cv.notify_all();
+        const size_t chunk = (n / (nw + 1) + 63) & ~(size_t) 63;
+        memcpy(d, s, std::min(n, chunk));                       // the caller's thread takes the first part
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~PixRing() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        for (auto &th : pool) th.join();
+        for (uint32_t k = 0; k < MAXD; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+        dev_free(d_rgba); dev_free(d_rec);
+        if (h_rec) cudaFreeHost(h_rec);
+    }
+};
+
+void engine_pixring_free(Engine *E) {
+    delete (PixRing *) E->pix_ring;
+    E->pix_ring = nullptr;
+}
+
+static RingKey ring_key(Engine *E) {
+    RingKey k;
+    memset(&k, 0, sizeof k);
+    k.prepare = E->prepare_count; k.w = E->width; k.h = E->height; k.motion = E->p.motion; k.fading = E->p.fading; k.density = E->p.density;
+    k.feather = (uint32_t) E->p.feather; k.keepbg = E->p.keep_background; k.show = E->p.show_blobs; k.fluid = E->p.fluid; k.seed = E->p.seed;
+    k.finite = E->p.finite; k.nframes = (uint32_t) E->frames.size();
+    return k;
+}
+
+// the one-frame path (fluid frames are stateful; very large frames do not get a ring)
+static int render_pixels_direct(Engine *E, double t, uint64_t *pixels_out) {
+    const size_t np = (size_t) E->width * E->height;
+    // staging: [np] packed RGBA followed by [np] 8-byte pixel records
+    if (E->d_pix_cap < np) {
+        dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
+        if (!dev_alloc(E, (void **) &E->d_pix, np * 12 + 8, "pixel staging")) return AMX_ERR_NOMEM;
+        E->d_pix_cap = np;
+    }
+    int rcode = engine_render(E, &t, 1, E->d_pix, 1);
+    if (rcode != AMX_OK) return rcode;
+    uint2 *d_rec = (uint2 *) (E->d_pix + np + (np & 1));          // 8-byte aligned
+    k_to_pixels<<<div_up(np, 256), 256, 0, E->stream>>>(E->d_pix, E->width, np, d_rec);
+    E->launches++;
+    if (E->fail(cudaMemcpyAsync(pixels_out, d_rec, np * 8, cudaMemcpyDeviceToHost, E->stream), "pixels D2H") ||
+        E->fail(cudaStreamSynchronize(E->stream), "render pixels") || E->check("render pixels")) return AMX_ERR_CUDA;
+    return AMX_OK;
+}
+
 } // namespace amx
 
 using namespace amx;
@@ -2042,19 +2153,82 @@ int amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out) {
     cudaSetDevice(E->device);
     const size_t np = (size_t) E->width * E->height;
     if (np == 0) { E->err = "resolution not set"; return AMX_ERR_STATE; }
-    // staging: [np] packed RGBA followed by [np] 8-byte pixel records
-    if (E->d_pix_cap < np) {
-        dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
-        if (!dev_alloc(E, (void **) &E->d_pix, np * 12 + 8, "pixel staging")) return AMX_ERR_NOMEM;
-        E->d_pix_cap = np;
+    const size_t ring_budget = (size_t) 256 << 20;                 // pinned bytes the ring may take
+    const uint32_t depth = (uint32_t) std::min<size_t>(PixRing::MAXD, ring_budget / (np * 8));
+    if (E->p.fluid > 0 || depth < 2 || !E->lookahead || E->nchains == 0) return render_pixels_direct(E, t, pixels_out);
+    if (!E->render_ready) { int rcode = engine_render_prepare(E); if (rcode != AMX_OK) return rcode; }
+    PixRing *R = (PixRing *) E->pix_ring;
+    if (R && (R->np != np || R->depth != depth)) { engine_pixring_free(E); R = nullptr; }
+    if (!R) {
+        R = new PixRing();
+        R->np = np; R->depth = depth;
+        bool ok = dev_alloc(E, (void **) &R->d_rgba, (size_t) depth * np * 4, "ring rgba") && dev_alloc(E, (void **) &R->d_rec, (size_t) depth * np * 8, "ring records") &&
+                  cudaHostAlloc((void **) &R->h_rec, (size_t) depth * np * 8, cudaHostAllocDefault) == cudaSuccess;
+        for (uint32_t k = 0; ok && k < depth; ++k) ok = cudaEventCreateWithFlags(&R->ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (ok && !E->copy_stream) {
+            ok = cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+            for (int k = 0; ok && k < 4; ++k) cudaEventCreateWithFlags(&E->copy_ev[k], cudaEventDisableTiming);
+        }
+        if (!ok) { cudaGetLastError(); E->err.clear(); R->h_rec = nullptr; delete R; return render_pixels_direct(E, t, pixels_out); }
+        if (np * 8 >= (4u << 20)) for (uint32_t w = 0; w < 3; ++w) R->pool.emplace_back(&PixRing::worker, R, w, 3u);
+        R->key = ring_key(E);
+        E->pix_ring = R;
     }
-    int rcode = engine_render(E, &t, 1, E->d_pix, 1);
-    if (rcode != AMX_OK) return rcode;
-    uint2 *d_rec = (uint2 *) (E->d_pix + np + (np & 1));          // 8-byte aligned
-    k_to_pixels<<<div_up(np, 256), 256, 0, E->stream>>>(E->d_pix, E->width, np, d_rec);
-    E->launches++;
-    if (E->fail(cudaMemcpyAsync(pixels_out, d_rec, np * 8, cudaMemcpyDeviceToHost, E->stream), "pixels D2H") ||
-        E->fail(cudaStreamSynchronize(E->stream), "render pixels") || E->check("render pixels")) return AMX_ERR_CUDA;
+    const RingKey now = ring_key(E);
+    if (memcmp(&now, &R->key, sizeof now) != 0) {
+        // the picture changed: frames in flight must land before their slots are reused
+        cudaStreamSynchronize(E->copy_stream);
+        for (uint32_t k = 0; k < depth; ++k) R->valid[k] = false;
+        R->key = now; R->have_last = false;
+    }
+    int slot = -1;
+    for (uint32_t k = 0; k < depth; ++k) if (R->valid[k] && memcmp(&R->t[k], &t, sizeof t) == 0) { slot = (int) k; break; }
+    if (slot < 0) {
+        R->misses++;
+        // predict the caller's next times: t = f / N is accepted only if it reproduces the last two requests bit by bit
+        double times[PixRing::MAXD];
+        uint32_t nb = 1;
+        times[0] = t;
+        if (R->have_last && t > R->last_t) {
+            const double d = t - R->last_t;
+            const long long N = llround(1.0 / d), f1 = N >= 2 && N <= (1 << 22) ? llround(t * (double) N) : 0;
+            if (N >= 2 && N <= (1 << 22) && (double) f1 / (double) N == t && (double) (f1 - 1) / (double) N == R->last_t)
+                for (; nb < depth; ++nb) times[nb] = (double) (f1 + nb) / (double) N;
+        }
+        cudaStreamSynchronize(E->copy_stream);                      // no slot of the ring is still being written
+        for (uint32_t k = 0; k < depth; ++k) R->valid[k] = false;
+        int rcode = engine_render(E, times, nb, R->d_rgba, 1);
+        if (rcode != AMX_OK) return rcode;
+        for (uint32_t k = 0; k < nb; ++k) {
+            k_to_pixels<<<div_up(np, 256), 256, 0, E->stream>>>(R->d_rgba + (size_t) k * np, E->width, np, R->d_rec + (size_t) k * np);
+            E->launches++;
+            cudaEvent_t ev = E->copy_ev[E->copy_ev_next++ & 3];
+            cudaEventRecord(ev, E->stream);
+            cudaStreamWaitEvent(E->copy_stream, ev, 0);
+            cudaMemcpyAsync(R->h_rec + (size_t) k * np, R->d_rec + (size_t) k * np, np * 8, cudaMemcpyDeviceToHost, E->copy_stream);
+            cudaEventRecord(R->ev[k], E->copy_stream);
+            R->t[k] = times[k]; R->valid[k] = true;
+        }
+        if (E->check("render pixels")) return AMX_ERR_CUDA;
+        slot = 0;
+    } else R->hits++;
+    if (E->fail(cudaEventSynchronize(R->ev[slot]), "pixels D2H")) return AMX_ERR_CUDA;
+    R->copy(pixels_out, R->h_rec + (size_t) slot * np, np * 8);
+    R->last_t = t; R->have_last = true;
+    return AMX_OK;
+}
+
+int amx_set_lookahead(amx_ctx *ctx, int enable) {
+    if (!ctx) return AMX_ERR_ARG;
+    ctx->e.lookahead = enable != 0;
+    if (!enable) { cudaSetDevice(ctx->e.device); if (ctx->e.copy_stream) cudaStreamSynchronize(ctx->e.copy_stream); engine_pixring_free(&ctx->e); }
+    return AMX_OK;
+}
+
+int amx_lookahead_stats(amx_ctx *ctx, uint64_t stats2[2]) {
+    if (!ctx || !stats2) return AMX_ERR_ARG;
+    PixRing *R = (PixRing *) ctx->e.pix_ring;
+    stats2[0] = R ? R->hits : 0; stats2[1] = R ? R->misses : 0;
     return AMX_OK;
 }
 

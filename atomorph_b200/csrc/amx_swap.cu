@@ -251,7 +251,9 @@ k_swap_tiled(pword *__restrict__ col, const pword *__restrict__ prev, const pwor
         if (a < w) {
             const pword word = kp_pack(s_col[j]);
             col[off + a] = word;
-            for (uint32_t p = 0; p < peers.n; ++p) peers.col[p][off + a] = word;      // NVLink stores, fire and forget
+            // NVLink stores, fire and forget: contiguous per tile into the peers' staging buffers, or straight to the atom's place
+            const size_t at = peers.staged ? (size_t) ubase + j : (size_t) off + a;
+            for (uint32_t p = 0; p < peers.n; ++p) peers.dst[p][at] = word;
         }
     }
     warp_add_stats(stats, prop, acc, gain);
@@ -281,9 +283,10 @@ k_pack_tiled(const pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm
     out[i] = a < w ? col[off + a] : 0ull;
 }
 __global__ void __launch_bounds__(256)
-k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t n, const pword *__restrict__ in) {
+k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t u0, uint32_t n, const pword *__restrict__ in) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    i += u0;                                   // slots [u0, u0 + n) of the buffer (indexed by slot)
     uint32_t a = tile_atom(tm, i);
     if (a < w) col[off + a] = in[i];
 }
@@ -293,9 +296,9 @@ void launch_pack_tiled(Engine *E, const pword *col, uint64_t off, uint32_t w, co
     k_pack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, out);
     E->launches++;
 }
-void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t n, const pword *in) {
+void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, const pword *in) {
     if (n == 0) return;
-    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, n, in);
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, in);
     E->launches++;
 }
 
@@ -400,7 +403,7 @@ int engine_swap_tiled_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
     pword *col = E->table + (size_t) y * E->A;
     const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
     const bool h2 = E->h == 2;
-    PeerCols nopeers; nopeers.n = 0;
+    PeerCols nopeers; nopeers.n = 0; nopeers.staged = 0;
     // more than TILE_MAX_ROUNDS rounds: further launches on the SAME tiles (same bijection) with fresh pairing masks
     for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
         const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
@@ -455,7 +458,7 @@ int engine_swap_local_epoch(Engine *E, uint32_t chain, uint32_t y, uint64_t epoc
     const uint32_t yn = (y + 1) % E->h, yp = (y + E->h - 1) % E->h;
     const pword *prev = E->table + (size_t) yp * E->A, *next = E->table + (size_t) yn * E->A;
     const bool h2 = E->h == 2;
-    PeerCols nopeers; nopeers.n = 0;
+    PeerCols nopeers; nopeers.n = 0; nopeers.staged = 0;
     // the positions move while the tiles are refined: the order is rebuilt per epoch, further launches reuse it
     for (uint32_t done = 0; done < rounds; done += TILE_MAX_ROUNDS) {
         const uint32_t r = std::min<uint32_t>(rounds - done, TILE_MAX_ROUNDS);
@@ -643,7 +646,7 @@ int amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epo
     const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
     const unsigned k = ceil_log2(w);
     const uint32_t n = 1u << k;
-    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), n, (const pword *) d_in);
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), 0u, n, (const pword *) d_in);
     E->launches++;
     E->render_ready = false;
     return E->check("unpack tiled") ? AMX_ERR_CUDA : AMX_OK;

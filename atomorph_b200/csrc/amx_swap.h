@@ -25,10 +25,14 @@ struct TileMap {
     uint32_t ia1, ia2, ic, is1, is2, imask;
     const uint32_t *perm; uint32_t shift;
 };
-// the same column on the other GPUs of the box (peer-mapped device memory, amx_dist.cu): a tile's refined key points are
-// written straight into every replica of the table while the next tiles are still being refined -- the exchange of the
-// multi-GPU matcher happens inside this kernel, over NVLink, instead of in a collective after it
-struct PeerCols { pword *col[AMX_MAX_PEERS]; uint32_t n; };
+// Where a tile's refined key points go besides the local column (peer-mapped device memory of the other GPUs of the box,
+// amx_dist.cu): the exchange of the multi-GPU matcher happens inside the swap kernel, tile by tile over NVLink, while the
+// next tiles are still being refined -- not in a collective after it.
+//   staged == 0: dst[p] is the same column of peer p's table; a key point is stored at its atom index (scattered 8-byte
+//                stores; used where a rank refines whole columns and the copy is done by k_push_column instead)
+//   staged == 1: dst[p] is peer p's staging buffer; a tile's key points are stored in SLOT order, i.e. as one contiguous
+//                8 KB run per tile (full NVLink write packets); the peer scatters them into its column after the barrier
+struct PeerCols { pword *dst[AMX_MAX_PEERS]; uint32_t n, staged; };
 
 
 unsigned ceil_log2(uint64_t w);
@@ -38,7 +42,7 @@ void tilemap_set_inner(TileMap &tm, uint64_t seed, uint64_t stream, uint64_t sub
 void launch_swap_tiled(Engine *E, bool h2, int tb, pword *col, const pword *prev, const pword *next, uint64_t off, uint32_t w, const TileMap &tm,
                        uint32_t t0, uint32_t ntl, uint32_t rounds, uint64_t round_base, const PeerCols &peers);
 void launch_pack_tiled(Engine *E, const pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, pword *out);
-void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t n, const pword *in);
+void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, const pword *in);
 
 } // namespace amx
 #endif

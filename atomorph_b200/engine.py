@@ -356,6 +356,23 @@ class Engine:
         times = np.ascontiguousarray(np.atleast_1d(times), dtype=np.float64)
         self._ck(self.L.amx_render(self.h, _p(times), len(times), C.c_void_p(out_ptr), 1 if is_device else 0), "render")
 
+    def render_pixels(self, t):
+        """One frame as width*height am::pixel records (u16 x, u16 y, r, g, b, a), what morph::get_pixels(t) hands out."""
+        out = np.zeros((self.height, self.width), dtype=np.uint64)
+        self._ck(self.L.amx_render_pixels(self.h, float(t), _p(out)), "render_pixels")
+        return out
+
+    def render_pixels_into(self, t, out_ptr):
+        self._ck(self.L.amx_render_pixels(self.h, float(t), C.c_void_p(out_ptr)), "render_pixels")
+
+    def set_lookahead(self, enable):
+        self._ck(self.L.amx_set_lookahead(self.h, 1 if enable else 0), "set_lookahead")
+
+    def lookahead_stats(self):
+        st = np.zeros(2, dtype=np.uint64)
+        self._ck(self.L.amx_lookahead_stats(self.h, _p(st)), "lookahead_stats")
+        return dict(hits=int(st[0]), misses=int(st[1]))
+
     def render_stats(self):
         st = np.zeros(3, dtype=np.uint64)
         self._ck(self.L.amx_render_stats(self.h, _p(st)), "render_stats")

@@ -396,6 +396,24 @@ def run_b200(args):
     barrier()
     s_e2e = time.perf_counter() - t0
     e2e_parts = [1000.0 * parts[k] / e2e_steps for k in ("h2d_table", "render_prepare", "render_and_d2h")]
+    # the drop-in call: am::morph::get_pixels(t, &vector) = amx_render_pixels, one frame of 8-byte am::pixel records per call
+    # into pageable host memory (a std::vector in the reference's API), with and without the look-ahead ring
+    facade = {}
+    pix = np.zeros((size, size), dtype=np.uint64)
+    for mode in ("lookahead", "one_frame_per_call"):
+        e.set_lookahead(mode == "lookahead")
+        for f in range(min(F, 16)):
+            e.render_pixels_into(times[f], pix.ctypes.data)
+        barrier()
+        t0 = time.perf_counter()
+        for f in range(F):
+            e.render_pixels_into(times[f], pix.ctypes.data)
+        facade[mode] = F / (time.perf_counter() - t0)
+    e.set_lookahead(True)
+    if world > 1:
+        tf = torch.tensor([facade["lookahead"], facade["one_frame_per_call"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.SUM)
+        facade = {"lookahead": float(tf[0]), "one_frame_per_call": float(tf[1])}
     if world > 1:
         tp = torch.tensor(e2e_parts, dtype=torch.float64, device=dev)
         dist.all_reduce(tp, op=dist.ReduceOp.MAX)
@@ -456,6 +474,8 @@ def run_b200(args):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step_max_over_ranks": {"h2d_table": e2e_parts[0], "render_prepare": e2e_parts[1], "render_and_d2h": e2e_parts[2]},
                 "d2h_gbs_per_gpu": d2h / (e2e_parts[2] / 1000.0) / 1e9 if e2e_parts[2] > 0 else None, "host_numa": numa},
+        "e2e_facade": {"value": facade["lookahead"], "unit": "frames/s", "call": "amx_render_pixels = am::morph::get_pixels(t, &vector): 8 B am::pixel records, one frame per call",
+                       "one_frame_per_call": facade["one_frame_per_call"], "d2h_bytes_per_frame": int(P * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "render_stats": dict(e.render_stats(), path_frames=e.render_path_frames(), tiled=e.render_tiled_stats()),

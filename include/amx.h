@@ -184,6 +184,13 @@ int  amx_render(amx_ctx *ctx, const double *times, uint32_t n, uint32_t *out, in
  * morph::get_pixels(double, std::vector<pixel>*) returns (morph.cpp:1405-1421), built on the device so that the
  * host side is one copy into the caller's vector */
 int  amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out);
+/* amx_render_pixels looks ahead: a call that is not served from its ring renders the requested frame and the next ones at
+ * the caller's stride (times predicted as (f + k) / N, only when that reproduces the last two requests bit by bit) as one
+ * batch into pinned host slots; later calls are served from there.  Served frames are bit-identical to direct renders; any
+ * change of table, parameters or resolution empties the ring.  On by default (off: amx_set_lookahead(ctx, 0) or
+ * AMX_LOOKAHEAD=0; fluid frames and frames above 128 MiB never use it).  stats2: [0] calls served from the ring, [1] misses. */
+int  amx_set_lookahead(amx_ctx *ctx, int enable);
+int  amx_lookahead_stats(amx_ctx *ctx, uint64_t stats2[2]);
 /* renderer diagnostics, cumulative since the render buffers were (re)built: [0] pixels resolved by the ordered double
  * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
  * went to an overflow list */

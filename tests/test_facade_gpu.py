@@ -162,3 +162,45 @@ def test_facade_fluid_frames(reflib):
     assert mx <= 2 and n <= 0.02 * 40 * 40, (n, mx)
     later = m.get_pixels(0.25)
     assert ((later >> 24) != 0).sum() > 0
+
+
+def test_frame_fetch_lookahead_serves_bit_identical_frames():
+    """amx_render_pixels (= morph::get_pixels(t, &vector), morph.cpp:1405-1421) with its look-ahead ring: frames requested on
+    a regular grid are served from batches rendered ahead; they are bit-identical to direct renders, the records carry the
+    pixel coordinates, and a parameter change empties the ring."""
+    import numpy as np
+    from atomorph_b200 import engine as eng
+    from atomorph_b200 import scenes
+    e = eng.Engine(0, seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=2000)
+    e.load_images(scenes.ellipses(96, 2, seed=5))
+    e.step(8)
+    e.step(10)
+    N = 24
+    times = [f / float(N) for f in range(N)]
+    direct = e.render(times)
+    yy, xx = np.mgrid[0:96, 0:96]
+    coords = (xx.astype(np.uint64) | (yy.astype(np.uint64) << np.uint64(16)))
+    for f, t in enumerate(times):
+        rec = e.render_pixels(t)
+        assert np.array_equal(rec & np.uint64(0xffffffff), coords)
+        assert np.array_equal((rec >> np.uint64(32)).astype(np.uint32), direct[f]), "frame %d differs from the direct render" % f
+    st = e.lookahead_stats()
+    assert st["hits"] >= N - 6 and st["misses"] <= 6, st          # two misses to learn the stride, then one per batch of 8
+    # a parameter change must not be served from frames rendered before it
+    e.set(keep_background=1)
+    with_bg = e.render([times[5], times[6]])
+    assert not np.array_equal(with_bg[0], direct[5])
+    for k, f in enumerate((5, 6)):
+        rec = e.render_pixels(times[f])
+        assert np.array_equal((rec >> np.uint64(32)).astype(np.uint32), with_bg[k])
+    # an irregular sequence never predicts: every call is a miss, results stay right
+    e.set(keep_background=0)
+    m0 = e.lookahead_stats()["misses"]
+    for t in (0.11, 0.5, 0.37, 0.93):
+        rec = e.render_pixels(t)
+        assert np.array_equal((rec >> np.uint64(32)).astype(np.uint32), e.render([t])[0])
+    assert e.lookahead_stats()["misses"] == m0 + 4
+    # switched off: the one-frame path
+    e.set_lookahead(False)
+    rec = e.render_pixels(times[3])
+    assert np.array_equal((rec >> np.uint64(32)).astype(np.uint32), direct[3])
