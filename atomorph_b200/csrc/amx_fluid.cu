@@ -7,14 +7,14 @@
  * are ordered by base cell once per step (positions only move in the last pass) and every
  * particle -> node transfer is a GATHER: one thread per node walks the particles of the 3 x 3
  * base cells whose quadratic B-spline stencil covers the node -- three contiguous runs of the
- * ordered list -- and sums their contributions in registers.  No atomics, a fixed summation order
- * (results are reproducible run to run), and node sums that differ from the reference's only by
- * that order (<< 1e-5 relative).  The node colour, a strength-weighted running mean in
+ * ordered list -- and sums their contributions in registers.  No floating-point atomics: the node
+ * sums differ from the reference's only by summation order (<< 1e-5 relative; the only run-to-run
+ * freedom left is the order of the few particles inside one cell).  The node colour, a strength-weighted running mean in
  * the reference (fluidmodel.cpp:234-244), is kept as sum(w*c) and sum(w): the G2P pass only ever
  * uses mean*weight (fluidmodel.cpp:463-469), which is that sum.
  *
  * Passes per step (algorithmic bytes: Np*(120 read + 64 written) + Ng*2*104, section 8d):
- *   order by cell (keys, radix sort, cell starts) | nodes <- mass/gradients, cells <- colour | colour box sum |
+ *   order by cell (count, scan, place) | nodes <- mass/gradients, cells <- colour | colour box sum |
  *   particles: pressure + wall force | nodes <- acceleration / m | particles: velocity update |
  *   nodes <- momentum / m | colour box sum | G2P gather + move
  *
@@ -49,11 +49,13 @@ __device__ __forceinline__ void particle_weights(double x, double y, PW &w) {
 #define PFI(k) pf[(size_t) (k) * n + i]
 #define NODE(k, idx) nf[(size_t) (k) * ng + (idx)]
 
-// ---- ordering by base cell -------------------------------------------------------------------------------------------
-// key = base cell (cy * gsx + cx) of an active particle, gsx * gsy for an inactive one (sorted behind everything)
+// ---- ordering by base cell: a counting sort -----------------------------------------------------------------------------
+// key = base cell (cy * gsx + cx) of an active particle, gsx * gsy for an inactive one (ordered behind everything).  One 32-bit
+// atomic per particle counts the cell's particles and hands out the particle's place inside its cell (arrival order: the
+// order of the few particles of ONE cell is the only thing that varies from run to run, i.e. node sums to ~1e-16).
 __global__ void __launch_bounds__(256)
-k_fluid_keys(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, uint32_t gsx, uint32_t gsy,
-             uint32_t *__restrict__ key, uint32_t *__restrict__ idx) {
+k_fluid_count(const double *__restrict__ pf, const uint8_t *__restrict__ active, uint32_t n, uint32_t gsx, uint32_t gsy,
+              uint32_t *__restrict__ key, uint32_t *__restrict__ within, uint32_t *__restrict__ cnt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k = gsx * gsy;
@@ -62,20 +64,18 @@ k_fluid_keys(const double *__restrict__ pf, const uint8_t *__restrict__ active, 
         if (cx >= 0 && cy >= 0 && (uint32_t) cx < gsx && (uint32_t) cy < gsy) k = (uint32_t) cy * gsx + (uint32_t) cx;
     }
     key[i] = k;
-    idx[i] = i;
+    within[i] = atomicAdd(&cnt[k], 1u);
 }
 
-// cs[c] = number of particles with a key below c (first sorted particle of cell c), c in [0, ng]; rank = inverse of perm;
-// sorted copies of the positions
+// cs = exclusive scan of the counts: first ordered particle of every cell.  perm: ordered -> particle, rank: its inverse;
+// ordered copies of the positions.
 __global__ void __launch_bounds__(256)
-k_fluid_bounds(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ perm, const double *__restrict__ pf, uint32_t n, uint32_t ng,
-               uint32_t *__restrict__ cs, uint32_t *__restrict__ rank, double *__restrict__ sx, double *__restrict__ sy) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t k = skey[s], i = perm[s];
-    const uint32_t first = s ? skey[s - 1] + 1u : 0u;
-    for (uint32_t c = first; c <= k && c <= ng; ++c) cs[c] = s;
-    if (s == n - 1u) for (uint32_t c = k + 1u; c <= ng; ++c) cs[c] = n;
+k_fluid_place(const uint32_t *__restrict__ key, const uint32_t *__restrict__ within, const uint32_t *__restrict__ cs, const double *__restrict__ pf,
+              uint32_t n, uint32_t *__restrict__ perm, uint32_t *__restrict__ rank, double *__restrict__ sx, double *__restrict__ sy) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = cs[key[i]] + within[i];
+    perm[s] = i;
     rank[i] = s;
     sx[s] = PFI(PF_X);
     sy[s] = PFI(PF_Y);
@@ -372,7 +372,7 @@ void engine_fluid_free(Engine *E) {
     Fluid *F = E->fluid;
     fluid_draw_free(F);
     dev_free(F->pf); dev_free(F->active); dev_free(F->mature); dev_free(F->owner); dev_free(F->aux); dev_free(F->nf); dev_free(F->cell);
-    dev_free(F->sortbuf); dev_free(F->cs); dev_free(F->sq); dev_free(F->sort_tmp);
+    dev_free(F->sortbuf); dev_free(F->cs); dev_free(F->cnt); dev_free(F->sq); dev_free(F->sort_tmp);
     delete F;
     E->fluid = nullptr;
 }
@@ -382,16 +382,15 @@ int fluid_step(Engine *E, uint64_t steps_left, double freedom_radius) {
     const size_t ng = (size_t) F->gx * F->gy;
     const uint32_t n = F->n;
     if (n == 0) { cudaMemsetAsync(F->nf, 0, ng * NF_COUNT * 8, E->stream); return E->check("fluid step") ? AMX_ERR_CUDA : AMX_OK; }
-    uint32_t *key = F->sortbuf, *skey = key + n, *idx = skey + n, *perm = idx + n, *rank = perm + n;
+    uint32_t *key = F->sortbuf, *within = key + n, *perm = within + n, *rank = perm + n;
     double *sx = F->sq, *sy = sx + n, *q0 = sy + n, *q1 = q0 + n, *q2 = q1 + n;
-    int key_bits = 1;
-    while ((1ull << key_bits) <= ng) ++key_bits;               // keys are 0 .. ng
     const dim3 ngrid(div_up(F->gx, 32), div_up(F->gy, 8));
     // order the particles by base cell: their positions do not change before the last pass of the step
-    k_fluid_keys<<<div_up(n, 256), 256, 0, E->stream>>>(F->pf, F->active, n, F->gx, F->gy, key, idx);
+    cudaMemsetAsync(F->cnt, 0, (ng + 1) * 4, E->stream);
+    k_fluid_count<<<div_up(n, 256), 256, 0, E->stream>>>(F->pf, F->active, n, F->gx, F->gy, key, within, F->cnt);
     size_t tmp = F->sort_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(F->sort_tmp, tmp, key, skey, idx, perm, (int) n, 0, key_bits, E->stream);
-    k_fluid_bounds<<<div_up(n, 256), 256, 0, E->stream>>>(skey, perm, F->pf, n, (uint32_t) ng, F->cs, rank, sx, sy);
+    cub::DeviceScan::ExclusiveSum(F->sort_tmp, tmp, F->cnt, F->cs, (int) (ng + 1), E->stream);
+    k_fluid_place<<<div_up(n, 256), 256, 0, E->stream>>>(key, within, F->cs, F->pf, n, perm, rank, sx, sy);
     // P2G: mass, gradients; colour through the cell sums and their 3 x 3 box sum
     k_fluid_nodes<0><<<ngrid, 256, 0, E->stream>>>(sx, sy, q0, q1, q2, F->cs, perm, F->pf, F->mature, n, F->nf, F->cell, F->gx, F->gy);
     k_fluid_colour_box<<<ngrid, 256, 0, E->stream>>>(F->cell, F->nf, F->gx, F->gy);
@@ -419,13 +418,13 @@ int fluid_alloc(Engine *E, uint32_t gsize_x, uint32_t gsize_y, uint32_t particle
         !dev_alloc(E, (void **) &F->mature, n, "fluid mature") || !dev_alloc(E, (void **) &F->owner, n, "fluid owner") ||
         !dev_alloc(E, (void **) &F->aux, n * 3 * 8, "fluid aux") || !dev_alloc(E, (void **) &F->nf, ng * NF_COUNT * 8, "fluid nodes") ||
         !dev_alloc(E, (void **) &F->cell, ng * 5 * 8, "fluid cell sums") ||
-        !dev_alloc(E, (void **) &F->sortbuf, (n ? n : 1) * 5 * 4, "fluid order") || !dev_alloc(E, (void **) &F->cs, (ng + 1) * 4, "fluid cell starts") ||
+        !dev_alloc(E, (void **) &F->sortbuf, (n ? n : 1) * 5 * 4, "fluid order") || !dev_alloc(E, (void **) &F->cs, (ng + 2) * 4, "fluid cell starts") || !dev_alloc(E, (void **) &F->cnt, (ng + 2) * 4, "fluid cell counts") ||
         !dev_alloc(E, (void **) &F->sq, (n ? n : 1) * 5 * 8, "fluid ordered factors")) {
         engine_fluid_free(E);
         return AMX_ERR_NOMEM;
     }
     F->sort_tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, F->sort_tmp_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr, (int) n, 0, 32, E->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, F->sort_tmp_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (int) (ng + 1), E->stream);
     if (!dev_alloc(E, &F->sort_tmp, F->sort_tmp_bytes, "fluid sort workspace")) { engine_fluid_free(E); return AMX_ERR_NOMEM; }
     cudaMemsetAsync(F->pf, 0, n * PF_COUNT * 8 + 0, E->stream);
     cudaMemsetAsync(F->active, 0, n, E->stream);

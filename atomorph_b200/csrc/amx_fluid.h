@@ -23,8 +23,9 @@ struct Fluid {
     double *nf = nullptr;        // [NF_COUNT][gx*gy]
     double *cell = nullptr;      // [5][gx*gy] colour sums per base cell of a step (k_fluid_p2g -> k_fluid_colour_box)
     // particles ordered by base cell, rebuilt every step (amx_fluid.cu: the node passes gather instead of scattering)
-    uint32_t *sortbuf = nullptr; // key, key sorted, index, perm (sorted -> particle), rank (particle -> sorted): [5][n]
-    uint32_t *cs = nullptr;      // [gx*gy + 1] first sorted particle of every base cell (monotone; [gx*gy] = active particles)
+    uint32_t *sortbuf = nullptr; // cell key, place inside the cell, perm (ordered -> particle), rank (particle -> ordered): [5][n]
+    uint32_t *cs = nullptr;      // [gx*gy + 1] first ordered particle of every base cell (monotone; [gx*gy] = active particles)
+    uint32_t *cnt = nullptr;     // [gx*gy + 1] particles per base cell
     double   *sq = nullptr;      // [5][n] in sorted order: x, y and up to three per-particle factors of the pass at hand
     void     *sort_tmp = nullptr;
     size_t    sort_tmp_bytes = 0;

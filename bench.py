@@ -449,11 +449,27 @@ def run_b200(args):
         kernels = None
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")) as fh:
             traffic = json.load(fh).get("k_bin+k_tile_dram_bytes_per_launch_pair")
     except Exception:
         pass
     s_ach = swap_bytes * (proposals / world) / (ms_swap / 1000.0) / 1e9
+    # the tiled swap kernel runs out of shared memory and is bound by instruction issue, not by bytes: what it reaches of the
+    # SM issue rate = warp-instructions per proposal (one ncu capture of the shipped kernel, profiles/r02_swap.json) x
+    # proposals/s per GPU / (SMs x 4 schedulers x SM clock)
+    swap_issue = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_swap.json")) as fh:
+            sw = json.load(fh)
+        wipp = sw["warp_instructions_per_launch"] / float(sw["proposals_per_launch"])
+        sm_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
+        issue_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_hz
+        swap_issue = {"thread_instructions_per_proposal": 32.0 * wipp, "warp_instructions_per_proposal": wipp,
+                      "issue_rate_frac": (proposals / world) / (ms_swap / 1000.0) * wipp / issue_peak,
+                      "issue_peak_warp_instr_per_s": issue_peak, "ncu_issue_slots_busy_pct": sw.get("issue_slots_busy_pct"),
+                      "source": "profiles/r02_swap.json, profiles/r02_ncu_swap.txt"}
+    except Exception:
+        pass
 
     line = {
         "metric": "morph frames/s at %d^2 RGBA (swap proposals/s in 'swap')" % size,
@@ -467,10 +483,11 @@ def run_b200(args):
                      "peak_kind": peak_kind, "kernel": "k_bin+k_tile (one launch each per batch of frames)",
                      "bytes_per_unit": render_bytes, "unit_name": "frame", "kernels": kernels},
         "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps, "rounds_per_step": SWAP_ROUNDS,
+                 "issue": swap_issue,
                  "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
                               "traffic": None, "kernel": "k_swap_tiled", "bytes_per_unit": swap_bytes, "unit_name": "proposal",
-                              "note": "tiles of 2048 atoms are refined for 64 rounds in shared memory per load: the algorithmic 32 B/proposal "
-                                      "are served from shared memory, not DRAM (DRAM traffic is ~24 B per atom per 64 rounds)"}},
+                              "note": "NOT a bound for this kernel: tiles of 1024 atoms are refined for 64 rounds in shared memory per load, so the "
+                                      "algorithmic 32 B/proposal never reach DRAM (~24 B per atom per 64 rounds do); see 'issue' for what limits it"}},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step_max_over_ranks": {"h2d_table": e2e_parts[0], "render_prepare": e2e_parts[1], "render_and_d2h": e2e_parts[2]},
                 "d2h_gbs_per_gpu": d2h / (e2e_parts[2] / 1000.0) / 1e9 if e2e_parts[2] > 0 else None, "host_numa": numa},
