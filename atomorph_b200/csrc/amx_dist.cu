@@ -245,10 +245,7 @@ int engine_swap_part_step(Engine *E, uint32_t chain, uint32_t y, uint64_t step, 
         if (rc != AMX_OK) return rc;
         const uint32_t n = 1u << kk;
         const pword *stage = D->stage + (size_t) par * D->stage_cap;
-        for (uint32_t r = 0; r < N; ++r) {
-            if (r == rank) continue;
-            launch_unpack_tiled(E, col, off, (uint32_t) w, tm, r * n, n, stage);
-        }
+        launch_unpack_tiled(E, col, off, (uint32_t) w, tm, 0u, n * N, rank * n, (rank + 1u) * n, stage);     // one launch: every slot but the own part
         return E->check("sharded swap unpack") ? AMX_ERR_CUDA : AMX_OK;
     }
     // NCCL: the part is a contiguous slot range of the OUTER bijection -> pack, all-gather, unpack, all on E->stream
@@ -262,7 +259,7 @@ int engine_swap_part_step(Engine *E, uint32_t chain, uint32_t y, uint64_t step, 
     tm.imask = 0u;                                   // slots of the outer bijection
     launch_pack_tiled(E, col, off, (uint32_t) w, tm, (uint32_t) (rank * n), (uint32_t) n, D->send);
     if (nccl_fail(E, g_nccl.AllGather(D->send, D->recv, n, ncclUint64, D->comm, E->stream), "ncclAllGather")) return AMX_ERR_CUDA;
-    launch_unpack_tiled(E, col, off, (uint32_t) w, tm, 0u, (uint32_t) (n * N), D->recv);
+    launch_unpack_tiled(E, col, off, (uint32_t) w, tm, 0u, (uint32_t) (n * N), (uint32_t) (rank * n), (uint32_t) ((rank + 1u) * n), D->recv);
     return E->check("sharded swap exchange") ? AMX_ERR_CUDA : AMX_OK;
 }
 

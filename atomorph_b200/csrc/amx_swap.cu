@@ -283,10 +283,12 @@ k_pack_tiled(const pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm
     out[i] = a < w ? col[off + a] : 0ull;
 }
 __global__ void __launch_bounds__(256)
-k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t u0, uint32_t n, const pword *__restrict__ in) {
+k_unpack_tiled(pword *__restrict__ col, uint64_t off, uint32_t w, TileMap tm, uint32_t u0, uint32_t n, uint32_t skip0, uint32_t skip1,
+               const pword *__restrict__ in) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    i += u0;                                   // slots [u0, u0 + n) of the buffer (indexed by slot)
+    i += u0;                                   // slots [u0, u0 + n) of the buffer (indexed by slot), without [skip0, skip1)
+    if (i >= skip0 && i < skip1) return;       // (the caller's own part: already in place)
     uint32_t a = tile_atom(tm, i);
     if (a < w) col[off + a] = in[i];
 }
@@ -296,9 +298,10 @@ void launch_pack_tiled(Engine *E, const pword *col, uint64_t off, uint32_t w, co
     k_pack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, out);
     E->launches++;
 }
-void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, const pword *in) {
+void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, uint32_t skip0, uint32_t skip1,
+                         const pword *in) {
     if (n == 0) return;
-    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, in);
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(col, off, w, tm, u0, n, skip0, skip1, in);
     E->launches++;
 }
 
@@ -646,7 +649,7 @@ int amx_unpack_tiled(amx_ctx *ctx, uint32_t chain, uint32_t column, uint64_t epo
     const uint64_t off = E->chain_off[chain], w = E->chain_off[chain + 1] - off;
     const unsigned k = ceil_log2(w);
     const uint32_t n = 1u << k;
-    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), 0u, n, (const pword *) d_in);
+    k_unpack_tiled<<<div_up(n, 256), 256, 0, E->stream>>>(E->table + (size_t) column * E->A, off, (uint32_t) w, make_tilemap(E->p.seed, chain, epoch, k), 0u, n, 0u, 0u, (const pword *) d_in);
     E->launches++;
     E->render_ready = false;
     return E->check("unpack tiled") ? AMX_ERR_CUDA : AMX_OK;

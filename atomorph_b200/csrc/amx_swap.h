@@ -42,7 +42,8 @@ void tilemap_set_inner(TileMap &tm, uint64_t seed, uint64_t stream, uint64_t sub
 void launch_swap_tiled(Engine *E, bool h2, int tb, pword *col, const pword *prev, const pword *next, uint64_t off, uint32_t w, const TileMap &tm,
                        uint32_t t0, uint32_t ntl, uint32_t rounds, uint64_t round_base, const PeerCols &peers);
 void launch_pack_tiled(Engine *E, const pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, pword *out);
-void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, const pword *in);
+void launch_unpack_tiled(Engine *E, pword *col, uint64_t off, uint32_t w, const TileMap &tm, uint32_t u0, uint32_t n, uint32_t skip0, uint32_t skip1,
+                         const pword *in);
 
 } // namespace amx
 #endif
