@@ -737,13 +737,15 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #define T_KEY_NONE 0xffffffffu
 
 struct Bins {
-    uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | home << 16}, home = (ly + 1) * 33 + lx + 1
+    uint2    *rec;        // [RBATCH][tiles][T_STRIDE] {colour, x_fract | y_fract << 8 | home << 16}, home = ly << 5 | lx (pixel inside its tile)
     uint32_t *atom;       // same layout: original atom index (the reference's summation order)
     uint32_t *chain;      // same layout: chain of the atom; nullptr for a single chain
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
     uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
     uint32_t *flag;       // [0] != 0: something overflowed, the frames must be rendered again by the general path;
                           // [1..4] largest bin count seen per class, [5] largest tile total (diagnostics)
+    uint32_t *fix;        // [1 + fix_cap] (tile, frame slot) pairs k_acc leaves to k_tile_fix: [0] = count (cleared by k_bin)
+    uint32_t  fix_cap;
     uint32_t  tiles_x, tiles_y;
 };
 __device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls ? T_CAP0 + (cls - 1u) * T_CAP1 : 0u; }
@@ -763,6 +765,7 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
     const uint32_t y = rb.f[0].y;
     const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0u && bn.fix) bn.fix[0] = 0u;                       // the list of this batch's degenerate tiles (k_acc) starts empty
     RawIn next = RawIn();
     if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
     // warp-uniform trip count: claiming bin slots is a warp collective
@@ -792,7 +795,7 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
                     const uint32_t lx = hx & 31u, ly = hy & 31u;
                     const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
                     key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
-                    meta[s] = fr | (((ly + 1u) * T_SW + lx + 1u) << 16);    // home in the tile's shared-memory coordinates
+                    meta[s] = fr | (((ly << 5) | lx) << 16);                // home pixel inside its tile
                 }
             }
         }
@@ -821,6 +824,134 @@ k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
             bn.rec[o] = make_uint2(col[s], meta[s]);
             bn.atom[o] = raw.atom;
             if (bn.chain) bn.chain[o] = raw.chain;
+        }
+    }
+}
+
+// ---- the binning kernel, second generation.  Same inputs, same bins, fewer instructions per atom and frame (k_bin: 183):
+// * one branch-free sample per frame: floor / fraction of a coordinate with round-down adds of 2^52 (the HIGH word of
+//   2^52 + v tells whether v lies in [0, 2^32), so negative or huge spline samples fall out to the generic code without
+//   a double compare), colour bytes packed without masks;
+// * `__match_any_sync` costs 41 SM cycles per warp instruction on B200 (profiles/micro_ops.cu).  The 32 atoms of a warp are
+//   neighbours on the canvas, so all of them usually append to ONE bin: a shuffle and a vote detect that, lane 0 claims 32
+//   slots.  Otherwise the warp walks its distinct bins (two to four) with a ballot each;
+// * capacity / offset of a bin class from selects instead of 64-bit table shifts.
+__device__ __forceinline__ uint32_t pack_bytes(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return r + (g << 8) + (b << 16) + (a << 24); }   // every value <= 255
+
+// Lean sample for the two-key-frame spline with one colour weight per frame (C2).  With two key frames the Catmull-Rom
+// controls alternate between the end points, p(t) = x1 + (x2 - x1)(3 t^2 - 2 t^3): the sample never leaves [min, max] of
+// two coordinates in [0, 65536), and the evaluation order (p1 b1 + p2 b2) + p3 b3 + p4 b4 with b1, b4 <= 0 <= b2, b3 and
+// monotone rounding cannot produce a negative value either (b3 >= -b1, b2 >= -b4).  So floor and fraction need no range
+// test: 2^52 + v rounded down holds floor(v) in its low word.
+__device__ __forceinline__ void split_h2(const double v, uint32_t *i, uint32_t *f) {
+    const double t = __dadd_rd(v, 4503599627370496.0);                      // 2^52 + floor(v)
+    *i = (uint32_t) __double2loint(t);
+    *f = d2u_round((v - (t - 4503599627370496.0)) * 255.0);                 // the fraction is exact
+}
+
+#ifndef BIN2_CTAS
+#define BIN2_CTAS 2
+#endif
+// FULL: the batch has all RBATCH frames (no per-frame test); LEAN: two key frames, spline, colour weight in [0, 1] for every
+// frame of the batch (checked on the host)
+template <int MOTION, bool PERLIN, bool H2, bool FULL, bool LEAN>
+__global__ void __launch_bounds__(256, BIN2_CTAS)
+k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb, const uint32_t n_live, const uint32_t nb_arg, const __grid_constant__ Bins bn) {
+    const uint32_t nb = FULL ? RBATCH : nb_arg;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t A = rc.A;
+    const double inv256 = 0.00390625;
+    const uint32_t y = rb.f[0].y;
+    const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0u && bn.fix) bn.fix[0] = 0u;                       // the list of this batch's degenerate tiles (k_acc) starts empty
+    RawIn next = RawIn();
+    if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
+    // warp-uniform trip count: claiming bin slots is a warp collective
+    for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
+        const bool valid = i < n_live;
+        const RawIn raw = next;
+        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
+        const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
+        AtomIn in;
+        in.pt1 = raw.pt1; in.pt2 = raw.pt2;
+        in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
+        in.x2 = u2d((uint32_t) pw_x256(raw.pt2)) * inv256; in.y2 = u2d((uint32_t) pw_y256(raw.pt2)) * inv256;
+        in.rc1 = raw.c1; in.rc2 = raw.c2;
+        in.c1 = col_d(raw.c1); in.c2 = col_d(raw.c2);
+        in.lag = raw.lag; in.slope = raw.slope;
+
+        // key = (tile << 2 | class) of the bin, T_KEY_NONE when the atom draws nothing in that frame
+        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            key[s] = T_KEY_NONE; col[s] = meta[s] = 0u;
+            if (!FULL && s >= nb) continue;
+            uint32_t fr, hx, hy;
+            bool ok;
+            if (LEAN) {
+                const RFrame &rf = rb.f[s];
+                // the controls alternate between the two end points (spline.cpp:29-38, operation order kept)
+                double vx, vy;
+                if (!rf.h2_swapped) {
+                    vx = cr_eval(in.x2, in.x1, in.x2, in.x1, rf.b1, rf.b2, rf.b3, rf.b4);
+                    vy = cr_eval(in.y2, in.y1, in.y2, in.y1, rf.b1, rf.b2, rf.b3, rf.b4);
+                } else {
+                    vx = cr_eval(in.x1, in.x2, in.x1, in.x2, rf.b1, rf.b2, rf.b3, rf.b4);
+                    vy = cr_eval(in.y1, in.y2, in.y1, in.y2, rf.b1, rf.b2, rf.b3, rf.b4);
+                }
+                uint32_t xf, yf;
+                split_h2(vx, &hx, &xf);
+                split_h2(vy, &hy, &yf);
+                const double str = rf.str, iw = 1.0 - str;
+                col[s] = pack_bytes(d2u_round(str * in.c1.r + iw * in.c2.r), d2u_round(str * in.c1.g + iw * in.c2.g),
+                                    d2u_round(str * in.c1.b + iw * in.c2.b), d2u_round(str * in.c1.a + iw * in.c2.a));
+                fr = xf + (yf << 8);
+                ok = use;
+            } else {
+                ok = use && atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr);
+            }
+            // a home at x >= width or y >= height reaches no pixel of the image (clip: morph.cpp:552-555)
+            ok = ok && hx < rc.width && hy < rc.height;
+            const uint32_t lx = hx & 31u, ly = hy & 31u;
+            const uint32_t cls = (lx == 31u ? 1u : 0u) + (ly == 31u ? 2u : 0u);
+            const uint32_t k = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) + cls;
+            meta[s] = fr + ((ly * 32u + lx) << 16);                         // home pixel inside its tile
+            if (ok) key[s] = k;
+        }
+        // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots.  who = leader | rank << 8
+        uint32_t who[RBATCH], base[RBATCH];
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            base[s] = 0u; who[s] = lane << 8;
+            if (!FULL && s >= nb) continue;
+            const uint32_t k0 = __shfl_sync(0xffffffffu, key[s], 0);
+            if (__all_sync(0xffffffffu, key[s] == k0)) {
+                // the whole warp appends to one bin (or has nothing at all)
+                if (lane == 0u && k0 != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * ntiles * 4u + k0], 32u);
+            } else {
+                const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
+                const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
+                who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
+                if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
+            }
+        }
+#pragma unroll
+        for (uint32_t s = 0; s < RBATCH; ++s) {
+            if (!FULL && s >= nb) continue;
+            const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));      // the leader's claim
+            const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
+            const uint32_t cap = cls == 0u ? T_CAP0 : cls == 3u ? T_CAP3 : T_CAP1;
+            const uint32_t off = cls == 0u ? 0u : T_CAP0 + (cls - 1u) * T_CAP1;
+            // beyond the capacity the record is dropped: the tile kernel sees the counter and raises the flag
+            if (key[s] != T_KEY_NONE && pos < cap) {
+                const uint32_t o = (s * ntiles + (key[s] >> 2)) * T_STRIDE + off + pos;      // < 2^32 records (ensure_bins)
+                bn.rec[o] = make_uint2(col[s], meta[s]);
+                bn.atom[o] = raw.atom;
+                if (bn.chain) bn.chain[o] = raw.chain;
+            }
         }
     }
 }
@@ -925,17 +1056,18 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
 
 // pass 2: one CTA per (tile, frame of the batch); thread = pixel column lx of a band of four rows
 template <bool SINGLE, bool COUNTED>
-__global__ void __launch_bounds__(256, SINGLE ? T_CTAS : 3)
-k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-       const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
-       const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-       const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+__device__ __forceinline__ void
+tile_body(const Bins &bn, const RConst &rc, const RBatch &rb,
+          const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+          const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+          const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats,
+          const uint32_t tx, const uint32_t ty, const uint32_t slot) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint2 *s_rec = (uint2 *) (smem + T_SMEM_REC);
     TileCtx *cx = (TileCtx *) (smem + T_SMEM_CTX);
     uint16_t *s_chain = (uint16_t *) (smem + T_SMEM_CHAIN);
 
-    const uint32_t tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y, slot = blockIdx.z;
+    const uint32_t tid = threadIdx.x;
     const uint32_t ntiles = bn.tiles_x * bn.tiles_y, tile = ty * bn.tiles_x + tx;
     const uint32_t y_frame = rb.f[slot].y;
 #ifdef T_PROFILE
@@ -1016,14 +1148,18 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
-    // a neighbour's record sits in ITS last column / row: that is this tile's halo column / row 0
+    // home pixel (ly << 5 | lx) -> shared-memory coordinates (ly + 1) * 33 + lx + 1; a neighbour's record sits in ITS last
+    // column / row: that is this tile's halo column / row 0
     {
         const uint32_t w0 = seg[4], w1 = seg[6], n1 = seg[8], e1 = seg[9];
-        for (uint32_t j = w0 + tid; j < e1; j += 256u) {
+        for (uint32_t j = tid; j < e1; j += 256u) {
             uint32_t back = 0u;
-            if (j < w1 || j >= n1) back += 32u;                   // western and north-western neighbour: x 32 -> 0
-            if (j >= w1) back += 32u * T_SW;                      // northern and north-western neighbour: y 32 -> 0
-            s_rec[j].y -= back << 16;
+            if (j >= w0) {
+                if (j < w1 || j >= n1) back += 32u;               // western and north-western neighbour: x 32 -> 0
+                if (j >= w1) back += 32u * T_SW;                  // northern and north-western neighbour: y 32 -> 0
+            }
+            const uint32_t meta = s_rec[j].y, v = meta >> 16;
+            s_rec[j].y = (meta & 0xffffu) | ((v + (v >> 5) + T_SW + 1u - back) << 16);
         }
     }
     __syncthreads();
@@ -1136,6 +1272,338 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     if (tid == 0u) atomicAdd((unsigned long long *) (bn.flag + 8) + 5, 1ull);
 #endif
 #undef T_PHASE
+}
+
+template <bool SINGLE, bool COUNTED>
+__global__ void __launch_bounds__(256, SINGLE ? T_CTAS : 3)
+k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+       const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+       const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+       const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+    tile_body<SINGLE, COUNTED>(bn, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, stats, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// the same, for the (tile, frame slot) pairs the accumulating kernel k_acc could not finish (fix[0] = number of entries,
+// fix[1 + e] = tile | slot << 28): a small persistent grid walks the list, which is empty in all but degenerate frames
+template <bool COUNTED>
+__global__ void __launch_bounds__(256, T_CTAS)
+k_tile_fix(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+           const uint32_t *__restrict__ fix, const uint32_t fix_cap,
+           const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+           const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+           const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+    const uint32_t n = min(fix[0], fix_cap);
+    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t w = fix[1u + e], tile = w & 0x0fffffffu;
+        tile_body<true, COUNTED>(bn, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, stats, tile % bn.tiles_x, tile / bn.tiles_x, w >> 28);
+        __syncthreads();                                         // the next entry reuses the shared memory
+    }
+}
+
+// ---------------------------------------------------------------------------------------- tiled path, accumulating variant
+// Single chain (C2, C5).  Measured on B200 (profiles/micro_ops.cu): a shared-memory atomicAdd on 32 scattered words costs
+// about 3 SM cycles per warp instruction -- no more than a plain scattered store -- so a tile does not have to ORDER its
+// records by home pixel to sum them.  One CTA per (tile, frame): five (six with density > 1) 32 x 32 planes of 32-bit
+// accumulators in shared memory -- sum(c * n) for red, green, blue, the alpha DEFICIT sum((255 - a) * n), sum(n) [, the
+// number of contributions] -- every record is read ONCE, straight from its bin in global memory (coalesced, no staging),
+// and adds its four bilinear contributions with shared-memory atomics; then a thread resolves four pixels from the exact
+// integer sums (same exact rational rounding as k_tile).  Compared with k_tile (stage, counting sort, ragged fold at 34 %
+// SIMD efficiency): 2.5 x fewer instructions, no capacity limit per tile besides the bins'.
+//
+// * Plane layout: row stride 40 words, so that the records of a warp -- neighbours on the canvas, a blob about 8 x 4 pixels --
+//   fall into different banks (bank = x + 8 y mod 32).
+// * Opaque atoms (a = 255, the usual case) have no alpha deficit: a warp whose 32 records are all opaque skips those
+//   atomics (sum(a * n) = 255 sum(n) - deficit).
+// * Border classes: a segment's records reach only the pixels inside this tile -- a compile-time subset of the four
+//   splat targets per segment (MASK), no run-time test.
+// * Exact .5 ties (about 0.7 per tile and frame on C2) need the reference's double sums in atom order: the tie pixels are
+//   marked in a 32 x 32 bit mask, the CTA scans the tile's records once more (L2 hits) and collects the contributions of
+//   up to A_TIE_MAX ties, one thread per tie replays them (resolve_fp).  A tile with more ties, or with a pixel whose
+//   sums may have wrapped (sum(n) >= 2^24: more than 257 atoms on one pixel), is put on a list and rendered again by
+//   k_tile_fix (the ordering kernel above): degenerate frames only, e.g. a key frame full of duplicate atoms.
+#ifndef A_STRIDE
+#define A_STRIDE  40u
+#endif
+#define A_PLANE   (32u * A_STRIDE)
+#define A_TIE_MAX 64u                   // ties of one tile replayed inside k_acc (their contribution lists reuse the accumulator planes)
+#define A_CON     (MAXK + 1u)            // contribution slots per tie (one more than the replay takes: "too many" is visible)
+
+struct AccCtx {
+    uint32_t seg_n[9], seg_first[9];
+    uint32_t rest_end[9];                // [s]: end of segment s in the merged index space of segments 1..8 ([0] = 0)
+    uint32_t tie_mask[34];               // [1 + row]: tie pixels of a row; rows -1 and 32 are guards (always 0)
+    uint32_t tie_rows;                   // bit r: row r has a tie pixel
+    uint32_t ntie, fix;
+    uint16_t tie_px[A_TIE_MAX];          // pixel (ly << 5 | lx) of tie t
+    uint32_t con_cnt[A_TIE_MAX];
+    uint8_t  tie_of[1024];               // pixel -> tie index (valid where tie_mask has the bit)
+};
+static_assert(A_TIE_MAX * A_CON * 3u <= 5u * A_PLANE, "the contribution lists must fit into the accumulator planes");
+
+// the four bilinear contributions of one record.  MASK >= 0: bit (dx + 2 dy) set = that target lies in this tile (compile
+// time); MASK < 0: the same bits in `rmask` (the small border segments share one loop)
+template <int MASK, bool COUNTED>
+__device__ __forceinline__ void acc_add(uint32_t *__restrict__ s_acc, const uint2 r, const int shift, const bool translucent, const uint32_t rmask) {
+    const uint32_t meta = r.y, v = meta >> 16;
+    uint32_t *p = s_acc + ((int) (v + (v >> 5) * (A_STRIDE - 32u)) + shift);
+    const uint32_t xf = meta & 255u, yf = (meta >> 8) & 255u, ix = xf ^ 255u, iy = yf ^ 255u;
+    const uint32_t cr = r.x & 255u, cg = (r.x >> 8) & 255u, cb = (r.x >> 16) & 255u;
+    uint32_t n[4];
+    n[0] = ix * iy; n[1] = xf * iy; n[2] = ix * yf; n[3] = xf * yf;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (MASK >= 0 ? !(MASK & (1 << k)) : !(rmask & (1u << k))) continue;
+        uint32_t *q = p + (k & 1) + (k >> 1) * (int) A_STRIDE;
+        atomicAdd(q, cr * n[k]);
+        atomicAdd(q + A_PLANE, cg * n[k]);
+        atomicAdd(q + 2u * A_PLANE, cb * n[k]);
+        atomicAdd(q + 4u * A_PLANE, n[k]);
+        if (COUNTED) atomicAdd(q + 5u * A_PLANE, n[k] != 0u ? 1u : 0u);
+    }
+    if (translucent) {
+        const uint32_t da = 255u - (r.x >> 24);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (MASK >= 0 ? !(MASK & (1 << k)) : !(rmask & (1u << k))) continue;
+            atomicAdd(p + (k & 1) + (k >> 1) * (int) A_STRIDE + 3u * A_PLANE, da * n[k]);
+        }
+    }
+}
+
+// segment of a record of the merged border segments 1..8, from its index j in their concatenation
+__device__ __forceinline__ uint32_t acc_rest_segment(const AccCtx &cx, const uint32_t j) {
+    uint32_t s = 1u;
+#pragma unroll
+    for (uint32_t k = 1; k < 8u; ++k) s += (j >= cx.rest_end[k]) ? 1u : 0u;
+    return s;
+}
+
+// round(S / N) (half up) for S <= 255 N, 0 < N < 2^23: float estimate of S / N + 1/2 (absolute error < 1e-4) rounded down.
+// The caller checks the remainder 2 S + N - q * 2 N: in [0, 2 N) when q is right, 0 on an exact .5 tie.
+__device__ __forceinline__ uint32_t rdiv_guess(const uint32_t S, const float rcpN) {
+    const float x = __fmaf_rn(__uint2float_rn(S), rcpN, 0.5f);
+    return __float_as_uint(__fadd_rd(x, 8388608.0f)) & 0x3ffu;               // 2^23 + x rounded down keeps floor(x) in the low mantissa bits
+}
+// the guess was off by one (|error| < 1e-4, so only next to an integer): corrected quotient and remainder
+__device__ __forceinline__ void rdiv_correct(uint32_t &q, uint32_t &rem, const uint32_t d2) {
+    if (rem < d2) return;
+    if ((int32_t) rem < 0) { --q; rem += d2; } else { ++q; rem -= d2; }
+}
+
+// PLAIN: keep_background off and show_blobs == SHOW_TEXTURE (the frame is the resolved pixel itself)
+template <bool COUNTED, bool PLAIN>
+__global__ void __launch_bounds__(256, 5)
+k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+      uint32_t *__restrict__ fix, const uint32_t fix_cap,
+      const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+      const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+    constexpr uint32_t NPL = COUNTED ? 6u : 5u;
+    __shared__ __align__(16) uint32_t s_acc[NPL * A_PLANE];
+    __shared__ AccCtx cx;
+
+    const uint32_t tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y, slot = blockIdx.z;
+    const uint32_t ntiles = bn.tiles_x * bn.tiles_y, tile = ty * bn.tiles_x + tx;
+    const uint32_t y_frame = rb.f[slot].y;
+
+    // the nine segments, as in k_tile: 0..3 own bins; 4, 5 western neighbour (last column, corner); 6, 7 northern one
+    // (last row, corner); 8 north-western one (corner)
+    if (tid < 9u) {
+        const int dtx = (tid == 4u || tid == 5u || tid == 8u) ? -1 : 0, dty = tid >= 6u ? -1 : 0;
+        const uint32_t cls = tid < 4u ? tid : tid == 4u ? 1u : tid == 6u ? 2u : 3u;
+        uint32_t n = 0, first = 0;
+        if ((int) tx + dtx >= 0 && (int) ty + dty >= 0) {
+            const uint32_t t2 = (uint32_t) ((int) ty + dty) * bn.tiles_x + (uint32_t) ((int) tx + dtx);
+            n = bn.cnt[((size_t) slot * ntiles + t2) * 4u + cls];
+            if (tid < 4u && n > bn.flag[1u + cls]) atomicMax(&bn.flag[1u + cls], n);
+            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); }
+            first = (slot * ntiles + t2) * T_STRIDE + bin_off(cls);
+        }
+        cx.seg_n[tid] = n;
+        cx.seg_first[tid] = first;
+        // ends of the border segments in their concatenation (warp scan over lanes 1..8)
+        uint32_t e = tid >= 1u ? n : 0u;
+#pragma unroll
+        for (uint32_t d = 1; d < 8u; d <<= 1) { const uint32_t u = __shfl_up_sync(0x1ffu, e, d); if (tid >= d) e += u; }
+        cx.rest_end[tid] = e;
+    }
+    if (tid >= 32u && tid < 36u) bn.cnt_other[((size_t) slot * ntiles + tile) * 4u + (tid - 32u)] = 0u;
+    if (tid >= 64u && tid < 98u) cx.tie_mask[tid - 64u] = 0u;
+    if (tid >= 128u && tid < 128u + A_TIE_MAX) cx.con_cnt[tid - 128u] = 0u;
+    if (tid == 255u) { cx.ntie = 0u; cx.fix = 0u; cx.tie_rows = 0u; }
+    for (uint32_t w = tid; w < NPL * A_PLANE / 4u; w += 256u) ((uint4 *) s_acc)[w] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    const uint32_t n0 = cx.seg_n[0], nrest = cx.rest_end[8], m = n0 + nrest;
+    if (tid == 0u && m > bn.flag[5]) atomicMax(&bn.flag[5], m);
+
+    const uint32_t lane = tid & 31u, lx = lane, band = tid >> 5;
+    const uint32_t px = tx * T_TILE + lx;
+    const size_t np = (size_t) rc.width * rc.height;
+    uint32_t *outf = out + (size_t) rb.f[slot].dst * np;
+    if (m == 0u) {
+        if (px < rc.width) {
+#pragma unroll
+            for (uint32_t p = 0; p < 4u; ++p) {
+                const uint32_t py = ty * T_TILE + band * 4u + p;
+                if (py >= rc.height) continue;
+                const size_t i = (size_t) py * rc.width + px;
+                outf[i] = (!PLAIN && rc.keep_background) ? bg[(size_t) slot * np + i] : 0u;
+            }
+        }
+        return;
+    }
+
+    // ---- accumulate: the interior bin with all four targets, then the eight border segments in one merged loop.  Warp-uniform
+    // trip counts (the opacity vote); the next record is in flight while this one is added
+    {
+        const uint2 none = make_uint2(0xff000000u, 0u);
+        const uint2 *rec = bn.rec + cx.seg_first[0];
+        uint32_t i = tid;
+        uint2 nxt = i < n0 ? __ldcs(rec + i) : none;
+        for (uint32_t i0 = tid - lane; i0 < n0; i0 += 256u, i += 256u) {
+            const uint2 r = nxt;
+            const bool valid = i < n0;
+            nxt = i + 256u < n0 ? __ldcs(rec + i + 256u) : none;
+            const bool translucent = __any_sync(0xffffffffu, (r.x >> 24) != 255u);
+            if (valid) acc_add<15, COUNTED>(s_acc, r, 0, translucent, 0u);
+        }
+        for (uint32_t j0 = tid - lane; j0 < nrest; j0 += 256u) {
+            const uint32_t j = j0 + lane;
+            const bool valid = j < nrest;
+            uint2 r = none;
+            uint32_t sgm = 1u;
+            if (valid) {
+                sgm = acc_rest_segment(cx, j);
+                r = __ldcs(bn.rec + (cx.seg_first[sgm] + (j - cx.rest_end[sgm - 1u])));
+            }
+            const bool translucent = __any_sync(0xffffffffu, (r.x >> 24) != 255u);
+            // targets inside this tile per segment 1..8: 5, 3, 1, 10, 2, 12, 4, 8 (one nibble each)
+            const uint32_t rmask = (0x84C2A135u >> (4u * (sgm - 1u))) & 15u;
+            const int shift = ((sgm == 4u || sgm == 5u || sgm == 8u) ? -32 : 0) + (sgm >= 6u ? -32 * (int) A_STRIDE : 0);
+            if (valid) acc_add<-1, COUNTED>(s_acc, r, shift, translucent, rmask);
+        }
+    }
+    __syncthreads();
+
+    // ---- resolve: thread = pixel column lx of rows band * 4 .. band * 4 + 3
+    auto finish = [&](uint32_t pxl, uint32_t bgc) -> uint32_t {
+        if (PLAIN) return c_a(pxl) ? pxl : 0u;                          // round((c/255.0)*255.0) == c for every byte c
+        const uint32_t colr = entry_color(pxl, 255u, 0u, rc, y_frame, blob_avg, blob_distinct);
+        if (!rc.keep_background) return c_a(colr) ? colr : 0u;
+        Over ov;
+        ov.add(colr);
+        return ov.finish(bgc, true);
+    };
+    const bool col_in = px < rc.width;
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) {
+        const uint32_t ly = band * 4u + p, py = ty * T_TILE + ly;
+        const uint32_t a = ly * A_STRIDE + lx;
+        const uint32_t N = s_acc[4u * A_PLANE + a];
+        const uint32_t R = s_acc[a], G = s_acc[A_PLANE + a], B = s_acc[2u * A_PLANE + a], D = s_acc[3u * A_PLANE + a];
+        const uint32_t cnt = COUNTED ? s_acc[5u * A_PLANE + a] : rc.density;
+        const bool inside = col_in && py < rc.height;
+        const size_t i = (size_t) py * rc.width + px;
+        uint32_t bgc = 0u;
+        if (!PLAIN) { if (inside && rc.keep_background) bgc = bg[(size_t) slot * np + i]; }
+        uint32_t res = bgc;
+        if (N != 0u) {                                                  // (else: no contribution with a non-zero weight)
+            uint32_t pxl;
+            if (N >= (1u << 23)) {
+                // more than 128 atoms on one pixel: 64-bit quotients (exact sums as long as sum(n) < 2^24), no tie replay --
+                // the same rule as resolve_contributions beyond MAXK contributions
+                if (N >= (1u << 24)) cx.fix = 1u;
+                pxl = resolve_int(R, G, B, 255ull * N - D, N, cnt, rc.density);
+            } else {
+                float rcpN;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcpN) : "f"(__uint2float_rn(N)));
+                const uint32_t A = 255u * N - D, d2 = 2u * N;
+                uint32_t qr = rdiv_guess(R, rcpN), qg = rdiv_guess(G, rcpN), qb = rdiv_guess(B, rcpN), qa = rdiv_guess(A, rcpN);
+                uint32_t er = 2u * R + N - qr * d2, eg = 2u * G + N - qg * d2, eb = 2u * B + N - qb * d2, ea = 2u * A + N - qa * d2;
+                if (max(max(er, eg), max(eb, ea)) >= d2) {              // a guess next to an integer was off by one: rare
+                    rdiv_correct(qr, er, d2); rdiv_correct(qg, eg, d2); rdiv_correct(qb, eb, d2); rdiv_correct(qa, ea, d2);
+                }
+                bool tie;
+                if (rc.density == 0u) { qa = 0u; tie = min(min(er, eg), eb) == 0u; }
+                else if (!COUNTED || cnt >= rc.density) tie = min(min(er, eg), min(eb, ea)) == 0u;
+                else {
+                    const unsigned long long num = (unsigned long long) A * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
+                    const unsigned long long n2 = 2ull * num + den, dd = 2ull * den, q = n2 / dd;
+                    tie = min(min(er, eg), eb) == 0u || n2 - q * dd == 0ull;
+                    qa = (uint32_t) q;
+                }
+                pxl = qr | (qg << 8) | (qb << 16) | (qa << 24);
+                if (tie && inside) {
+                    if (stats) atomicAdd(&stats->ties, 1ull);
+                    const uint32_t k = atomicAdd(&cx.ntie, 1u);
+                    if (k < A_TIE_MAX) {
+                        cx.tie_px[k] = (uint16_t) ((ly << 5) | lx); cx.tie_of[(ly << 5) | lx] = (uint8_t) k;
+                        atomicOr(&cx.tie_mask[1u + ly], 1u << lx); atomicOr(&cx.tie_rows, 1u << ly);
+                    }
+                }
+            }
+            res = finish(pxl, bgc);
+        }
+        if (inside) outf[i] = res;                                      // (a tie pixel is written again below)
+    }
+    __syncthreads();
+    const uint32_t nt = cx.ntie;
+    if (nt == 0u && cx.fix == 0u) return;
+    if (nt > A_TIE_MAX || cx.fix != 0u) {
+        // degenerate tile: the ordering kernel renders it again
+        if (tid == 0u) {
+            const uint32_t e = atomicAdd(fix, 1u);
+            if (e < fix_cap) fix[1u + e] = tile | (slot << 28); else atomicOr(bn.flag, 1u);
+        }
+        return;
+    }
+    // ---- ties: collect the contributions of the marked pixels (second pass over the records, which filters on the rows that
+    // have a tie), replay in atom order.  The lists live in the accumulator planes, which nobody reads any more.
+    uint32_t *con_atom = s_acc, *con_col = s_acc + A_TIE_MAX * A_CON, *con_n = s_acc + 2u * A_TIE_MAX * A_CON;
+    {
+        const unsigned long long rows2 = (unsigned long long) cx.tie_rows << 1;      // bit 1 + r
+        for (uint32_t j = tid; j < m; j += 256u) {
+            uint32_t sgm = 0u, g = cx.seg_first[0] + j;
+            if (j >= n0) { sgm = acc_rest_segment(cx, j - n0); g = cx.seg_first[sgm] + (j - n0 - cx.rest_end[sgm - 1u]); }
+            const uint2 r = bn.rec[g];
+            const uint32_t v = r.y >> 16;
+            const int hy = (int) (v >> 5) + (sgm >= 6u ? -32 : 0);                   // home row in this tile's pixel coordinates, -1 .. 31
+            if (((rows2 >> (hy + 1)) & 3ull) == 0ull) continue;                      // neither row hy nor hy + 1 has a tie
+            const int hx = (int) (v & 31u) + ((sgm == 4u || sgm == 5u || sgm == 8u) ? -32 : 0);
+            const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int qx = hx + (k & 1), qy = hy + (k >> 1);
+                if (qx < 0 || qx > 31) continue;
+                if (!((cx.tie_mask[1 + qy] >> qx) & 1u)) continue;                   // (guard rows: qy = -1 and 32 read zeros)
+                const uint32_t nn = ((k & 1) ? xf : 255u - xf) * ((k >> 1) ? yf : 255u - yf);
+                if (nn == 0u) continue;
+                const uint32_t t = cx.tie_of[(qy << 5) | qx];
+                const uint32_t c = atomicAdd(&cx.con_cnt[t], 1u);
+                if (c < A_CON) { con_atom[t * A_CON + c] = bn.atom[g]; con_col[t * A_CON + c] = r.x; con_n[t * A_CON + c] = nn; }
+            }
+        }
+    }
+    __syncthreads();
+    // one thread per tie, spread over the warps (tie t: lane t / 8 of warp t % 8)
+    if (lane < A_TIE_MAX / 8u) {
+        const uint32_t t = lane * 8u + band;
+        const uint32_t c = t < nt ? cx.con_cnt[t] : 0u;
+        if (c >= 1u && c <= MAXK) {                                   // beyond MAXK contributions the integer result stands
+            uint32_t key[MAXK], cc[MAXK], cn[MAXK];
+            for (uint32_t e = 0; e < c; ++e) {                        // insertion sort by atom: the reference's summation order
+                const uint32_t at = con_atom[t * A_CON + e];
+                int q = (int) e;
+                while (q > 0 && key[q - 1] > at) { key[q] = key[q - 1]; cc[q] = cc[q - 1]; cn[q] = cn[q - 1]; --q; }
+                key[q] = at; cc[q] = con_col[t * A_CON + e]; cn[q] = con_n[t * A_CON + e];
+            }
+            const uint32_t qx = cx.tie_px[t] & 31u, qy = cx.tie_px[t] >> 5;
+            const size_t i = (size_t) (ty * T_TILE + qy) * rc.width + (tx * T_TILE + qx);
+            const uint32_t bgc = (!PLAIN && rc.keep_background) ? bg[(size_t) slot * np + i] : 0u;
+            if (stats) atomicAdd(&stats->generic, 1ull);
+            outf[i] = finish(resolve_fp(cc, cn, 0, (int) c, rc.density), bgc);
+        }
+    }
 }
 
 // gather into per-(pixel, blob) entries (feather / per-blob fetch): one thread per CANVAS pixel, batch slot 0
@@ -1381,8 +1849,8 @@ void engine_render_free(Engine *E) {
     dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
-    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
-    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
@@ -1690,19 +2158,22 @@ static bool ensure_bins(Engine *E) {
     if (E->tb_rec && E->tb_tiles_x == tx && E->tb_tiles_y == ty && E->tb_has_chain == want_chain) return true;
     const uint64_t ntiles = (uint64_t) tx * ty, nrec = (uint64_t) RBATCH * ntiles * T_STRIDE;
     if (ntiles == 0 || nrec >= (1ull << 32)) return false;               // record indices are 32-bit
-    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
-    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     const size_t cnt_bytes = (size_t) 2 * RBATCH * ntiles * 4 * sizeof(uint32_t);
+    E->tb_fix_cap = (uint32_t) std::min<uint64_t>(RBATCH * ntiles, 1u << 27);
     if (!dev_alloc(E, (void **) &E->tb_rec, nrec * 8, "bin records") || !dev_alloc(E, (void **) &E->tb_atom, nrec * 4, "bin atoms") ||
         (want_chain && !dev_alloc(E, (void **) &E->tb_chain, nrec * 4, "bin chains")) ||
-        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4 + 8 * 8, "bin flag")) {
+        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4 + 8 * 8, "bin flag") ||
+        !dev_alloc(E, (void **) &E->tb_fix, ((size_t) E->tb_fix_cap + 1) * 4, "tile fix list")) {
         E->err.clear();                                                   // not an error: the general path needs none of this
-        dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
-        E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr;
+        dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
+        E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr;
         return false;
     }
     cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
     cudaMemsetAsync(E->tb_flag, 0, 8 * 4 + 8 * 8, E->stream);
+    cudaMemsetAsync(E->tb_fix, 0, 4, E->stream);
     E->tb_tiles_x = tx; E->tb_tiles_y = ty; E->tb_has_chain = want_chain;
     E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
     return true;
@@ -1715,6 +2186,7 @@ static Bins make_bins(Engine *E) {
     bn.cnt = E->tb_cnt + (size_t) E->tb_parity * per;
     bn.cnt_other = E->tb_cnt + (size_t) (E->tb_parity ^ 1u) * per;
     bn.flag = E->tb_flag;
+    bn.fix = E->tb_fix; bn.fix_cap = E->tb_fix_cap;
     bn.tiles_x = E->tb_tiles_x; bn.tiles_y = E->tb_tiles_y;
     return bn;
 }
@@ -1727,6 +2199,10 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     const uint32_t n_live = E->r_live[rb.f[0].y];
     const Bins bn = make_bins(E);
     const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
+    // the lean sample of k_bin2: two key frames, spline, every frame's colour weight inside [0, 1]
+    bool lean = h2 && !perlin && rc.motion == K_SPLINE;
+    for (uint32_t s = 0; s < nb; ++s) lean = lean && rb.f[s].str >= 0.0 && rb.f[s].str <= 1.0;
+    const bool full = nb == RBATCH;
     g_ktime.begin(E->stream);
     if (n_live > 0) {
 #define AMX_BIN(M, P, H) do { \
@@ -1734,7 +2210,17 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
         int &per_sm = per_sm_dev[E->device & 63]; \
         if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
         const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
-        k_bin<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
+        if (E->bin_v1) k_bin<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); \
+        else if (lean && full) AMX_BIN2(M, P, H, true, true); \
+        else if (lean) AMX_BIN2(M, P, H, false, true); \
+        else if (full) AMX_BIN2(M, P, H, true, false); \
+        else AMX_BIN2(M, P, H, false, false); } while (0)
+#define AMX_BIN2(M, P, H, F, L) do { \
+        static int per_sm2_dev[64] = {0}; \
+        int &per_sm2 = per_sm2_dev[E->device & 63]; \
+        if (!per_sm2) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && (H) && !(P)>, 256, 0); if (per_sm2 < 1) per_sm2 = 1; } \
+        const uint32_t blocks2 = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm2 * (uint32_t) E->sm_count); \
+        k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && (H) && !(P)><<<blocks2, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
 #define AMX_BIN_M(M) do { if (perlin) { if (h2) AMX_BIN(M, true, true); else AMX_BIN(M, true, false); } \
                           else        { if (h2) AMX_BIN(M, false, true); else AMX_BIN(M, false, false); } } while (0)
         if (rc.motion == K_LINEAR) AMX_BIN_M(M_LINEAR);
@@ -1742,6 +2228,7 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
         else AMX_BIN_M(M_NONE);
 #undef AMX_BIN_M
 #undef AMX_BIN
+#undef AMX_BIN2
         E->launches++;
     }
     g_ktime.end(E->stream, 0, nb);
@@ -1757,8 +2244,22 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
         k_tile<S, C><<<grid, 256, T_SMEM_BYTES(S), E->stream>>>(bn, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
     const bool single = E->nchains == 1, counted = rc.density > 1;
     g_ktime.begin(E->stream);
-    if (single) { if (counted) AMX_TILE(true, true); else AMX_TILE(true, false); }
-    else        { if (counted) AMX_TILE(false, true); else AMX_TILE(false, false); }
+    if (single && E->tiled_acc) {
+        // accumulating kernel + the (normally empty) list of tiles it leaves to the ordering kernel
+        if (n_live == 0) cudaMemsetAsync(bn.fix, 0, 4, E->stream);        // k_bin, which clears the list, did not run
+        const uint32_t fix_grid = std::min<uint32_t>(bn.fix_cap, 2u * (uint32_t) E->sm_count);
+        const bool plain = !rc.keep_background && rc.show_blobs == SHOW_TEXTURE;
+#define AMX_ACC(C) do { \
+        if (plain) k_acc<C, true><<<grid, 256, 0, E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); \
+        else       k_acc<C, false><<<grid, 256, 0, E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); \
+        cudaFuncSetAttribute(k_tile_fix<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T_SMEM_BYTES(true)); \
+        k_tile_fix<C><<<fix_grid, 256, T_SMEM_BYTES(true), E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
+        if (counted) AMX_ACC(true); else AMX_ACC(false);
+#undef AMX_ACC
+        E->launches++;
+    }
+    else if (single) { if (counted) AMX_TILE(true, true); else AMX_TILE(true, false); }
+    else             { if (counted) AMX_TILE(false, true); else AMX_TILE(false, false); }
 #undef AMX_TILE
     g_ktime.end(E->stream, 1, nb);
     E->launches++;
