@@ -91,7 +91,6 @@ int amx_create(amx_ctx **out, int device) {
     if (const char *nb = getenv("AMX_RENDER_BATCH")) c->e.render_batch = (uint32_t) std::max(1, atoi(nb));   // tuning knob (frames per launch pair)
     c->e.swap_global_only = getenv("AMX_SWAP_GLOBAL") != nullptr;
     if (const char *lo = getenv("AMX_SWAP_LOCALITY")) c->e.swap_locality = (uint32_t) std::max(0, atoi(lo));   // every n-th tiled epoch pairs spatial neighbours
-    if (const char *b1 = getenv("AMX_BIN_V1")) c->e.bin_v1 = atoi(b1) != 0;
     if (const char *ac = getenv("AMX_RENDER_ACC")) c->e.tiled_acc = atoi(ac) != 0;
     if (const char *tl = getenv("AMX_RENDER_TILED")) { c->e.tiled_enabled = atoi(tl) != 0; c->e.tiled_multi = atoi(tl) >= 2; }   // 0: general A-buffer path only; 2: tiled path for multi-chain morphs too
     if (const char *la = getenv("AMX_LOOKAHEAD")) c->e.lookahead = atoi(la) != 0;

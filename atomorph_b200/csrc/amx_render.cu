@@ -751,84 +751,10 @@ struct Bins {
 __device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls ? T_CAP0 + (cls - 1u) * T_CAP1 : 0u; }
 __device__ __forceinline__ uint32_t bin_cap(uint32_t cls) { return cls == 0u ? T_CAP0 : cls == 3u ? T_CAP3 : T_CAP1; }
 
-// pass 1: per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile.  An atom's
-// key points and end colours are loaded and converted once for all frames of the batch; the claiming atomics of all
-// frames are issued back to back before the first record is stored.
-template <int MOTION, bool PERLIN, bool H2>
-__global__ void __launch_bounds__(256, 2)
-k_bin(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, Bins bn) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t A = rc.A;
-    const double inv256 = 0.00390625;
-    const uint32_t y = rb.f[0].y;
-    const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0u && bn.fix) bn.fix[0] = 0u;                       // the list of this batch's degenerate tiles (k_acc) starts empty
-    RawIn next = RawIn();
-    if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
-    // warp-uniform trip count: claiming bin slots is a warp collective
-    for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
-        const bool valid = i < n_live;
-        const RawIn raw = next;
-        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
-
-        uint32_t key[RBATCH], col[RBATCH], meta[RBATCH];
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) { key[s] = T_KEY_NONE; col[s] = meta[s] = 0u; }
-        const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
-        if (use) {
-            AtomIn in;
-            in.pt1 = raw.pt1; in.pt2 = raw.pt2;
-            in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
-            in.x2 = u2d((uint32_t) pw_x256(raw.pt2)) * inv256; in.y2 = u2d((uint32_t) pw_y256(raw.pt2)) * inv256;
-            in.rc1 = raw.c1; in.rc2 = raw.c2;
-            in.c1 = col_d(raw.c1); in.c2 = col_d(raw.c2);
-            in.lag = raw.lag; in.slope = raw.slope;
-#pragma unroll
-            for (uint32_t s = 0; s < RBATCH; ++s) {
-                if (s >= nb) continue;
-                uint32_t fr, hx, hy;
-                // a home at x >= width or y >= height reaches no pixel of the image
-                if (atom_sample<MOTION, PERLIN, H2>(ri, rc, rb.f[s], in, i, raw.atom, &hx, &hy, &col[s], &fr) && hx < rc.width && hy < rc.height) {
-                    const uint32_t lx = hx & 31u, ly = hy & 31u;
-                    const uint32_t cls = (lx == 31u ? 1u : 0u) | (ly == 31u ? 2u : 0u);
-                    key[s] = (((hy >> 5) * bn.tiles_x + (hx >> 5)) << 2) | cls;
-                    meta[s] = fr | (((ly << 5) | lx) << 16);                // home pixel inside its tile
-                }
-            }
-        }
-        // one atomicAdd per (warp, bin): the lanes that append to the same bin take consecutive slots
-        uint32_t who[RBATCH], base[RBATCH];
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) {
-            base[s] = 0u; who[s] = 0u;
-            if (s >= nb) continue;
-            const uint32_t peers = __match_any_sync(0xffffffffu, key[s]);
-            const uint32_t leader = (uint32_t) __ffs((int) peers) - 1u;
-            who[s] = leader | ((uint32_t) __popc(peers & lt_mask) << 8);
-            if (lane == leader && key[s] != T_KEY_NONE) base[s] = atomicAdd(&bn.cnt[s * ntiles * 4u + key[s]], (uint32_t) __popc(peers));
-        }
-#pragma unroll
-        for (uint32_t s = 0; s < RBATCH; ++s) {
-            if (s >= nb) continue;
-            const uint32_t b = __shfl_sync(0xffffffffu, base[s], (int) (who[s] & 255u));      // the leader's claim
-            if (key[s] == T_KEY_NONE) continue;
-            const uint32_t cls = key[s] & 3u, pos = b + (who[s] >> 8);
-            // capacity and offset of the four bins of a tile, 16 bits each, looked up with one shift
-            const uint32_t cap = (uint32_t) ((((unsigned long long) T_CAP3 << 48) | ((unsigned long long) T_CAP1 << 32) | ((unsigned long long) T_CAP1 << 16) | T_CAP0) >> (cls * 16u)) & 0xffffu;
-            const uint32_t off = (uint32_t) ((((unsigned long long) (T_CAP0 + 2u * T_CAP1) << 48) | ((unsigned long long) (T_CAP0 + T_CAP1) << 32) | ((unsigned long long) T_CAP0 << 16)) >> (cls * 16u)) & 0xffffu;
-            if (pos >= cap) continue;                             // dropped: k_tile sees the counter beyond the capacity and raises the flag
-            const uint32_t o = (s * ntiles + (key[s] >> 2)) * T_STRIDE + off + pos;      // < 2^32 records (ensure_bins)
-            bn.rec[o] = make_uint2(col[s], meta[s]);
-            bn.atom[o] = raw.atom;
-            if (bn.chain) bn.chain[o] = raw.chain;
-        }
-    }
-}
-
-// ---- the binning kernel, second generation.  Same inputs, same bins, fewer instructions per atom and frame (k_bin: 183):
+// pass 1 (k_bin2): per sorted atom and frame of the batch, sample -> record appended to the bin of its home's tile.  An atom's
+// key points and end colours are loaded and converted once for all frames of the batch; the claiming atomics of all frames are
+// issued back to back before the first record is stored.  Second generation (the first needed 183 instructions per atom and
+// frame, this one 145):
 // * one branch-free sample per frame: floor / fraction of a coordinate with round-down adds of 2^52 (the HIGH word of
 //   2^52 + v tells whether v lies in [0, 2^32), so negative or huge spline samples fall out to the generic code without
 //   a double compare), colour bytes packed without masks;
@@ -850,7 +776,7 @@ __device__ __forceinline__ void split_h2(const double v, uint32_t *i, uint32_t *
 }
 
 #ifndef BIN2_CTAS
-#define BIN2_CTAS 2
+#define BIN2_CTAS 3
 #endif
 // FULL: the batch has all RBATCH frames (no per-frame test); LEAN: two key frames, spline, colour weight in [0, 1] for every
 // frame of the batch (checked on the host)
@@ -1391,8 +1317,11 @@ __device__ __forceinline__ void rdiv_correct(uint32_t &q, uint32_t &rem, const u
 }
 
 // PLAIN: keep_background off and show_blobs == SHOW_TEXTURE (the frame is the resolved pixel itself)
+#ifndef ACC_CTAS
+#define ACC_CTAS 5
+#endif
 template <bool COUNTED, bool PLAIN>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, ACC_CTAS)
 k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
       uint32_t *__restrict__ fix, const uint32_t fix_cap,
       const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
@@ -2206,12 +2135,7 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     g_ktime.begin(E->stream);
     if (n_live > 0) {
 #define AMX_BIN(M, P, H) do { \
-        static int per_sm_dev[64] = {0}; \
-        int &per_sm = per_sm_dev[E->device & 63]; \
-        if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<M, P, H>, 256, 0); if (per_sm < 1) per_sm = 1; } \
-        const uint32_t blocks = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm * (uint32_t) E->sm_count); \
-        if (E->bin_v1) k_bin<M, P, H><<<blocks, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); \
-        else if (lean && full) AMX_BIN2(M, P, H, true, true); \
+        if (lean && full) AMX_BIN2(M, P, H, true, true); \
         else if (lean) AMX_BIN2(M, P, H, false, true); \
         else if (full) AMX_BIN2(M, P, H, true, false); \
         else AMX_BIN2(M, P, H, false, false); } while (0)
