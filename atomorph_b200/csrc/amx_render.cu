@@ -720,7 +720,9 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 // array.  Pixels fold the records of the homes that reach them into exact integer sums exactly like k_gather_pixel; ties,
 // several blobs at a pixel and pixels with more than MAXK records take the ordered double replay (resolve_contributions).
 //
-// Capacity: a tile takes T_SREC records per frame (its nine bins together: 4 atoms per pixel; an interior bin holds 3.5).
+// Capacity: the accumulating kernel k_acc streams a tile's records straight from the bins, so a tile takes what its bins hold
+// (interior bin: 7 atoms per pixel); the ordering kernel k_tile stages them in shared memory and takes T_SREC records per tile
+// and frame (4 atoms per pixel).
 // A bin or tile that would need more raises bins.flag; engine_render then renders the frames again through the general
 // path above (the results of the two paths are identical, both being exact).
 #ifndef T_CTAS
@@ -729,10 +731,10 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #define T_TILE   32u
 #define T_SW     33u                    // homes per tile row incl. the halo column (home x = tile_x0 - 1)
 #define T_SREC   4096u                  // (12 B of shared memory per record, 54 KB per CTA: 4 CTAs per SM)
-#define T_CAP0   3584u
+#define T_CAP0   7168u
 // T_SREC: records a tile takes in one frame; T_CAP0 / T_CAP1 / T_CAP3: bin capacities per class (interior / last column or row / corner)
-#define T_CAP1   512u
-#define T_CAP3   128u
+#define T_CAP1   1024u
+#define T_CAP3   256u
 #define T_STRIDE (T_CAP0 + 2u * T_CAP1 + T_CAP3)      // records per (frame slot, tile)
 #define T_KEY_NONE 0xffffffffu
 
@@ -1244,9 +1246,13 @@ k_tile_fix(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, c
 //   splat targets per segment (MASK), no run-time test.
 // * Exact .5 ties (about 0.7 per tile and frame on C2) need the reference's double sums in atom order: the tie pixels are
 //   marked in a 32 x 32 bit mask, the CTA scans the tile's records once more (L2 hits) and collects the contributions of
-//   up to A_TIE_MAX ties, one thread per tie replays them (resolve_fp).  A tile with more ties, or with a pixel whose
-//   sums may have wrapped (sum(n) >= 2^24: more than 257 atoms on one pixel), is put on a list and rendered again by
-//   k_tile_fix (the ordering kernel above): degenerate frames only, e.g. a key frame full of duplicate atoms.
+//   A_TIE_MAX ties per round, one thread per tie replays them (resolve_fp).  A tile with a pixel whose sums may have wrapped
+//   (sum(n) >= 2^24: more than 257 atoms on one pixel) is put on a list and rendered again by k_tile_fix (the ordering
+//   kernel above).
+// * Tried and measured slower: a persistent, warp-specialised variant (some warps accumulate item k + 1 into a second
+//   set of planes while the others resolve item k; 134-188 us against 105) -- the atomics need many warps in flight --, runs of
+//   full warps kept 32-aligned in the bins (no fewer bank conflicts: the atoms of a warp are scattered by the residual noise of
+//   the matching), two streams so that the binning of the next batch overlaps this kernel (1.02 x).
 #ifndef A_STRIDE
 #define A_STRIDE  40u
 #endif
@@ -1260,7 +1266,7 @@ struct AccCtx {
     uint32_t tie_mask[34];               // [1 + row]: tie pixels of a row; rows -1 and 32 are guards (always 0)
     uint32_t tie_rows;                   // bit r: row r has a tie pixel
     uint32_t ntie, fix;
-    uint16_t tie_px[A_TIE_MAX];          // pixel (ly << 5 | lx) of tie t
+    uint16_t tie_px[1024];               // pixel (ly << 5 | lx) of tie t (every pixel of the tile may be one)
     uint32_t con_cnt[A_TIE_MAX];
     uint8_t  tie_of[1024];               // pixel -> tie index (valid where tie_mask has the bit)
 };
@@ -1465,8 +1471,9 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
                 if (tie && inside) {
                     if (stats) atomicAdd(&stats->ties, 1ull);
                     const uint32_t k = atomicAdd(&cx.ntie, 1u);
+                    if (k < 1024u) cx.tie_px[k] = (uint16_t) ((ly << 5) | lx);
                     if (k < A_TIE_MAX) {
-                        cx.tie_px[k] = (uint16_t) ((ly << 5) | lx); cx.tie_of[(ly << 5) | lx] = (uint8_t) k;
+                        cx.tie_of[(ly << 5) | lx] = (uint8_t) k;
                         atomicOr(&cx.tie_mask[1u + ly], 1u << lx); atomicOr(&cx.tie_rows, 1u << ly);
                     }
                 }
@@ -1476,10 +1483,10 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
         if (inside) outf[i] = res;                                      // (a tie pixel is written again below)
     }
     __syncthreads();
-    const uint32_t nt = cx.ntie;
+    const uint32_t nt = min(cx.ntie, 1024u);
     if (nt == 0u && cx.fix == 0u) return;
-    if (nt > A_TIE_MAX || cx.fix != 0u) {
-        // degenerate tile: the ordering kernel renders it again
+    if (cx.fix != 0u) {
+        // a pixel whose sums may have wrapped: the ordering kernel renders the tile again
         if (tid == 0u) {
             const uint32_t e = atomicAdd(fix, 1u);
             if (e < fix_cap) fix[1u + e] = tile | (slot << 28); else atomicOr(bn.flag, 1u);
@@ -1487,9 +1494,26 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
         return;
     }
     // ---- ties: collect the contributions of the marked pixels (second pass over the records, which filters on the rows that
-    // have a tie), replay in atom order.  The lists live in the accumulator planes, which nobody reads any more.
+    // have a tie), replay in atom order.  The lists live in the accumulator planes, which nobody reads any more.  A_TIE_MAX ties
+    // per round; the first round's marks were set by the resolve above, later rounds (degenerate frames only: a key frame full of
+    // duplicate atoms has a tie on every other pixel) mark theirs first.
     uint32_t *con_atom = s_acc, *con_col = s_acc + A_TIE_MAX * A_CON, *con_n = s_acc + 2u * A_TIE_MAX * A_CON;
-    {
+#pragma unroll 1
+    for (uint32_t t0 = 0; t0 < nt; t0 += A_TIE_MAX) {
+        const uint32_t ntr = min(nt - t0, A_TIE_MAX);
+        if (t0 != 0u) {
+            __syncthreads();
+            if (tid < 34u) cx.tie_mask[tid] = 0u;
+            if (tid >= 64u && tid < 64u + A_TIE_MAX) cx.con_cnt[tid - 64u] = 0u;
+            if (tid == 128u) cx.tie_rows = 0u;
+            __syncthreads();
+            if (tid < ntr) {
+                const uint32_t pq = cx.tie_px[t0 + tid];
+                cx.tie_of[pq] = (uint8_t) tid;
+                atomicOr(&cx.tie_mask[1u + (pq >> 5)], 1u << (pq & 31u)); atomicOr(&cx.tie_rows, 1u << (pq >> 5));
+            }
+            __syncthreads();
+        }
         const unsigned long long rows2 = (unsigned long long) cx.tie_rows << 1;      // bit 1 + r
         for (uint32_t j = tid; j < m; j += 256u) {
             uint32_t sgm = 0u, g = cx.seg_first[0] + j;
@@ -1512,25 +1536,25 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
                 if (c < A_CON) { con_atom[t * A_CON + c] = bn.atom[g]; con_col[t * A_CON + c] = r.x; con_n[t * A_CON + c] = nn; }
             }
         }
-    }
-    __syncthreads();
-    // one thread per tie, spread over the warps (tie t: lane t / 8 of warp t % 8)
-    if (lane < A_TIE_MAX / 8u) {
-        const uint32_t t = lane * 8u + band;
-        const uint32_t c = t < nt ? cx.con_cnt[t] : 0u;
-        if (c >= 1u && c <= MAXK) {                                   // beyond MAXK contributions the integer result stands
-            uint32_t key[MAXK], cc[MAXK], cn[MAXK];
-            for (uint32_t e = 0; e < c; ++e) {                        // insertion sort by atom: the reference's summation order
-                const uint32_t at = con_atom[t * A_CON + e];
-                int q = (int) e;
-                while (q > 0 && key[q - 1] > at) { key[q] = key[q - 1]; cc[q] = cc[q - 1]; cn[q] = cn[q - 1]; --q; }
-                key[q] = at; cc[q] = con_col[t * A_CON + e]; cn[q] = con_n[t * A_CON + e];
+        __syncthreads();
+        // one thread per tie, spread over the warps (tie t: lane t / 8 of warp t % 8)
+        if (lane < A_TIE_MAX / 8u) {
+            const uint32_t t = lane * 8u + band;
+            const uint32_t c = t < ntr ? cx.con_cnt[t] : 0u;
+            if (c >= 1u && c <= MAXK) {                                   // beyond MAXK contributions the integer result stands
+                uint32_t key[MAXK], cc[MAXK], cn[MAXK];
+                for (uint32_t e = 0; e < c; ++e) {                        // insertion sort by atom: the reference's summation order
+                    const uint32_t at = con_atom[t * A_CON + e];
+                    int q = (int) e;
+                    while (q > 0 && key[q - 1] > at) { key[q] = key[q - 1]; cc[q] = cc[q - 1]; cn[q] = cn[q - 1]; --q; }
+                    key[q] = at; cc[q] = con_col[t * A_CON + e]; cn[q] = con_n[t * A_CON + e];
+                }
+                const uint32_t pq = cx.tie_px[t0 + t], qx = pq & 31u, qy = pq >> 5;
+                const size_t i = (size_t) (ty * T_TILE + qy) * rc.width + (tx * T_TILE + qx);
+                const uint32_t bgc = (!PLAIN && rc.keep_background) ? bg[(size_t) slot * np + i] : 0u;
+                if (stats) atomicAdd(&stats->generic, 1ull);
+                outf[i] = finish(resolve_fp(cc, cn, 0, (int) c, rc.density), bgc);
             }
-            const uint32_t qx = cx.tie_px[t] & 31u, qy = cx.tie_px[t] >> 5;
-            const size_t i = (size_t) (ty * T_TILE + qy) * rc.width + (tx * T_TILE + qx);
-            const uint32_t bgc = (!PLAIN && rc.keep_background) ? bg[(size_t) slot * np + i] : 0u;
-            if (stats) atomicAdd(&stats->generic, 1ull);
-            outf[i] = finish(resolve_fp(cc, cn, 0, (int) c, rc.density), bgc);
         }
     }
 }

@@ -101,9 +101,9 @@ def test_tiled_path_equals_general_path(reflib, monkeypatch):
 
 
 def test_tiled_path_overflow_falls_back(reflib):
-    """More atoms than a tile's bins take (density 6 = 6 atoms per pixel): the frames are rendered again by the general path."""
-    images = scenes.ellipses(96, 2, seed=17)             # the middle tile is covered completely: 6144 records > 3584
-    params = dict(motion=eng.LINEAR, fading=eng.LINEAR, density=6)
+    """More atoms than a tile's bins take (density 8 = 8 atoms per pixel): the frames are rendered again by the general path."""
+    images = scenes.ellipses(96, 2, seed=17)             # the middle tile is covered completely: 8192 records > 7168
+    params = dict(motion=eng.LINEAR, fading=eng.LINEAR, density=8)
     m = build_ref(reflib, images, seed=1, **params)
     e = engine_from_ref(m, images, seed=1, **params)
     for t in (0.0, 0.4, 0.9):
@@ -111,6 +111,32 @@ def test_tiled_path_overflow_falls_back(reflib):
         assert mx <= 1 and n <= 0.01 * 96 * 96
     paths = e.render_path_frames()
     assert paths["general"] >= 3 and paths["tiled"] <= 1, paths
+
+
+def test_dense_tiles_stay_on_the_tiled_path(reflib, monkeypatch):
+    """Three atoms per pixel that pile up to 5800 records in one tile in mid-morph -- more than the ordering kernel's shared
+    memory takes -- stay on the tiled path: the accumulating kernel streams the records from the bins.  Same frames as the general
+    path and the reference; the ordering kernel (AMX_RENDER_ACC=0) has to fall back here."""
+    images = scenes.ellipses(96, 2, seed=17)
+    params = dict(motion=eng.LINEAR, fading=eng.LINEAR, density=3)
+    m = build_ref(reflib, images, seed=1, **params)
+    ts = [0.0, 0.4, 0.9]
+    e = engine_from_ref(m, images, seed=1, **params)
+    a = e.render(ts)
+    assert e.render_path_frames() == dict(tiled=3, general=0), e.render_path_frames()
+    assert e.render_tiled_stats()["max_tile"] > 4096
+    monkeypatch.setenv("AMX_RENDER_TILED", "0")
+    e0 = engine_from_ref(m, images, seed=1, **params)
+    assert np.array_equal(a, e0.render(ts))
+    assert e0.render_path_frames() == dict(tiled=0, general=3)
+    monkeypatch.setenv("AMX_RENDER_TILED", "1")
+    monkeypatch.setenv("AMX_RENDER_ACC", "0")
+    e1 = engine_from_ref(m, images, seed=1, **params)
+    assert np.array_equal(a, e1.render(ts))
+    assert e1.render_path_frames()["general"] >= 3
+    for k, t in enumerate(ts):
+        n, mx = diff_stats(m.render(t), a[k])
+        assert mx <= 1 and n <= 0.01 * 96 * 96
 
 
 def test_tiled_diagnostics_and_kernel_times():
@@ -128,7 +154,7 @@ def test_tiled_diagnostics_and_kernel_times():
     assert kt[0]["ms"] > 0 and kt[1]["ms"] > 0
     st = e.render_tiled_stats()
     assert st["fallbacks"] == 0 and not st["blocked"]
-    assert 0 < st["max_bin"][0] <= 2560 and st["max_tile"] >= st["max_bin"][0]
+    assert 0 < st["max_bin"][0] <= 7168 and st["max_tile"] >= st["max_bin"][0]
     assert e.render_path_frames() == dict(tiled=16, general=0)
 
 
