@@ -158,8 +158,6 @@ struct Engine {
     uint32_t *tb_atom = nullptr, *tb_chain = nullptr;
     uint32_t *tb_cnt = nullptr;            // two counter buffers (ping-pong), each [RBATCH][tiles][4]
     uint32_t *tb_flag = nullptr;           // raised by the kernels when a bin / tile overflows
-    uint32_t *tb_fix = nullptr;            // (tile, frame slot) pairs the accumulating tile kernel leaves to the ordering one
-    uint32_t  tb_fix_cap = 0;
     bool      tiled_acc = true;            // AMX_RENDER_ACC=0: single-chain morphs through the ordering kernel k_tile (for comparisons)
     uint32_t  tb_tiles_x = 0, tb_tiles_y = 0, tb_parity = 0, tb_dirty[2] = {0, 0};
     bool      tb_has_chain = false;

@@ -744,10 +744,9 @@ struct Bins {
     uint32_t *chain;      // same layout: chain of the atom; nullptr for a single chain
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
     uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
-    uint32_t *flag;       // [0] != 0: something overflowed, the frames must be rendered again by the general path;
+    uint32_t *flag;       // [0] bit 0: a bin or tile overflowed, bit 1: a pixel's 32-bit sums may have wrapped (k_acc) -- the frames of the
+                          // call must be rendered again by the general path (bit 0 also keeps the tiled path off until the next table);
                           // [1..4] largest bin count seen per class, [5] largest tile total (diagnostics)
-    uint32_t *fix;        // [1 + fix_cap] (tile, frame slot) pairs k_acc leaves to k_tile_fix: [0] = count (cleared by k_bin)
-    uint32_t  fix_cap;
     uint32_t  tiles_x, tiles_y;
 };
 __device__ __forceinline__ uint32_t bin_off(uint32_t cls) { return cls ? T_CAP0 + (cls - 1u) * T_CAP1 : 0u; }
@@ -794,7 +793,6 @@ k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const 
     const uint32_t y = rb.f[0].y;
     const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0u && bn.fix) bn.fix[0] = 0u;                       // the list of this batch's degenerate tiles (k_acc) starts empty
     RawIn next = RawIn();
     if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
     // warp-uniform trip count: claiming bin slots is a warp collective
@@ -1211,23 +1209,6 @@ k_tile(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const
     tile_body<SINGLE, COUNTED>(bn, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, stats, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
-// the same, for the (tile, frame slot) pairs the accumulating kernel k_acc could not finish (fix[0] = number of entries,
-// fix[1 + e] = tile | slot << 28): a small persistent grid walks the list, which is empty in all but degenerate frames
-template <bool COUNTED>
-__global__ void __launch_bounds__(256, T_CTAS)
-k_tile_fix(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-           const uint32_t *__restrict__ fix, const uint32_t fix_cap,
-           const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
-           const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-           const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
-    const uint32_t n = min(fix[0], fix_cap);
-    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
-        const uint32_t w = fix[1u + e], tile = w & 0x0fffffffu;
-        tile_body<true, COUNTED>(bn, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, stats, tile % bn.tiles_x, tile / bn.tiles_x, w >> 28);
-        __syncthreads();                                         // the next entry reuses the shared memory
-    }
-}
-
 // ---------------------------------------------------------------------------------------- tiled path, accumulating variant
 // Single chain (C2, C5).  Measured on B200 (profiles/micro_ops.cu): a shared-memory atomicAdd on 32 scattered words costs
 // about 3 SM cycles per warp instruction -- no more than a plain scattered store -- so a tile does not have to ORDER its
@@ -1246,9 +1227,8 @@ k_tile_fix(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, c
 //   splat targets per segment (MASK), no run-time test.
 // * Exact .5 ties (about 0.7 per tile and frame on C2) need the reference's double sums in atom order: the tie pixels are
 //   marked in a 32 x 32 bit mask, the CTA scans the tile's records once more (L2 hits) and collects the contributions of
-//   A_TIE_MAX ties per round, one thread per tie replays them (resolve_fp).  A tile with a pixel whose sums may have wrapped
-//   (sum(n) >= 2^24: more than 257 atoms on one pixel) is put on a list and rendered again by k_tile_fix (the ordering
-//   kernel above).
+//   A_TIE_MAX ties per round, one thread per tie replays them (resolve_fp).  A pixel whose sums may have wrapped (sum(n) >= 2^24:
+//   more than 257 atoms on one pixel) raises flag bit 1: the frames of this call are rendered again by the general path.
 // * Tried and measured slower: a persistent, warp-specialised variant (some warps accumulate item k + 1 into a second
 //   set of planes while the others resolve item k; 134-188 us against 105) -- the atomics need many warps in flight --, runs of
 //   full warps kept 32-aligned in the bins (no fewer bank conflicts: the atoms of a warp are scattered by the residual noise of
@@ -1329,7 +1309,6 @@ __device__ __forceinline__ void rdiv_correct(uint32_t &q, uint32_t &rem, const u
 template <bool COUNTED, bool PLAIN>
 __global__ void __launch_bounds__(256, ACC_CTAS)
 k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-      uint32_t *__restrict__ fix, const uint32_t fix_cap,
       const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
       const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
     constexpr uint32_t NPL = COUNTED ? 6u : 5u;
@@ -1486,11 +1465,8 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
     const uint32_t nt = min(cx.ntie, 1024u);
     if (nt == 0u && cx.fix == 0u) return;
     if (cx.fix != 0u) {
-        // a pixel whose sums may have wrapped: the ordering kernel renders the tile again
-        if (tid == 0u) {
-            const uint32_t e = atomicAdd(fix, 1u);
-            if (e < fix_cap) fix[1u + e] = tile | (slot << 28); else atomicOr(bn.flag, 1u);
-        }
+        // a pixel whose sums may have wrapped: the general path renders the frames of this call again
+        if (tid == 0u) atomicOr(bn.flag, 2u);
         return;
     }
     // ---- ties: collect the contributions of the marked pixels (second pass over the records, which filters on the rows that
@@ -1802,8 +1778,8 @@ void engine_render_free(Engine *E) {
     dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
-    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
-    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
@@ -2111,22 +2087,19 @@ static bool ensure_bins(Engine *E) {
     if (E->tb_rec && E->tb_tiles_x == tx && E->tb_tiles_y == ty && E->tb_has_chain == want_chain) return true;
     const uint64_t ntiles = (uint64_t) tx * ty, nrec = (uint64_t) RBATCH * ntiles * T_STRIDE;
     if (ntiles == 0 || nrec >= (1ull << 32)) return false;               // record indices are 32-bit
-    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
-    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
+    dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+    E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
     const size_t cnt_bytes = (size_t) 2 * RBATCH * ntiles * 4 * sizeof(uint32_t);
-    E->tb_fix_cap = (uint32_t) std::min<uint64_t>(RBATCH * ntiles, 1u << 27);
     if (!dev_alloc(E, (void **) &E->tb_rec, nrec * 8, "bin records") || !dev_alloc(E, (void **) &E->tb_atom, nrec * 4, "bin atoms") ||
         (want_chain && !dev_alloc(E, (void **) &E->tb_chain, nrec * 4, "bin chains")) ||
-        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4 + 8 * 8, "bin flag") ||
-        !dev_alloc(E, (void **) &E->tb_fix, ((size_t) E->tb_fix_cap + 1) * 4, "tile fix list")) {
+        !dev_alloc(E, (void **) &E->tb_cnt, cnt_bytes, "bin counters") || !dev_alloc(E, (void **) &E->tb_flag, 8 * 4 + 8 * 8, "bin flag")) {
         E->err.clear();                                                   // not an error: the general path needs none of this
-        dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag); dev_free(E->tb_fix);
-        E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = E->tb_fix = nullptr;
+        dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
+        E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr;
         return false;
     }
     cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
     cudaMemsetAsync(E->tb_flag, 0, 8 * 4 + 8 * 8, E->stream);
-    cudaMemsetAsync(E->tb_fix, 0, 4, E->stream);
     E->tb_tiles_x = tx; E->tb_tiles_y = ty; E->tb_has_chain = want_chain;
     E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
     return true;
@@ -2139,7 +2112,6 @@ static Bins make_bins(Engine *E) {
     bn.cnt = E->tb_cnt + (size_t) E->tb_parity * per;
     bn.cnt_other = E->tb_cnt + (size_t) (E->tb_parity ^ 1u) * per;
     bn.flag = E->tb_flag;
-    bn.fix = E->tb_fix; bn.fix_cap = E->tb_fix_cap;
     bn.tiles_x = E->tb_tiles_x; bn.tiles_y = E->tb_tiles_y;
     return bn;
 }
@@ -2193,18 +2165,12 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     const bool single = E->nchains == 1, counted = rc.density > 1;
     g_ktime.begin(E->stream);
     if (single && E->tiled_acc) {
-        // accumulating kernel + the (normally empty) list of tiles it leaves to the ordering kernel
-        if (n_live == 0) cudaMemsetAsync(bn.fix, 0, 4, E->stream);        // k_bin, which clears the list, did not run
-        const uint32_t fix_grid = std::min<uint32_t>(bn.fix_cap, 2u * (uint32_t) E->sm_count);
         const bool plain = !rc.keep_background && rc.show_blobs == SHOW_TEXTURE;
 #define AMX_ACC(C) do { \
-        if (plain) k_acc<C, true><<<grid, 256, 0, E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); \
-        else       k_acc<C, false><<<grid, 256, 0, E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); \
-        cudaFuncSetAttribute(k_tile_fix<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T_SMEM_BYTES(true)); \
-        k_tile_fix<C><<<fix_grid, 256, T_SMEM_BYTES(true), E->stream>>>(bn, rc, rb, bn.fix, bn.fix_cap, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
+        if (plain) k_acc<C, true><<<grid, 256, 0, E->stream>>>(bn, rc, rb, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); \
+        else       k_acc<C, false><<<grid, 256, 0, E->stream>>>(bn, rc, rb, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st); } while (0)
         if (counted) AMX_ACC(true); else AMX_ACC(false);
 #undef AMX_ACC
-        E->launches++;
     }
     else if (single) { if (counted) AMX_TILE(true, true); else AMX_TILE(true, false); }
     else             { if (counted) AMX_TILE(false, true); else AMX_TILE(false, false); }
@@ -2373,13 +2339,18 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             E->fail(cudaStreamSynchronize(E->stream), "render")) return AMX_ERR_CUDA;
         for (int k = 0; k < 6; ++k) E->tb_demand[k] = std::max(E->tb_demand[k], flag8[1 + k]);
         if (flag8[0]) {
+            // bit 0: a bin overflowed -- it would again, so the tiled path stays off until the table changes; bit 1 alone: a pixel
+            // with more than 257 atoms in one of these frames -- only this call goes through the general path
+            const bool latch = (flag8[0] & 1u) != 0u;
             E->tiled_fallbacks++;
             const size_t cnt_bytes = (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t);
             cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
             cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
             E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
             E->tiled_blocked = true;
-            return engine_render(E, times, n, out, out_is_device);
+            const int rcode2 = engine_render(E, times, n, out, out_is_device);
+            if (!latch) E->tiled_blocked = false;
+            return rcode2;
         }
     }
     if (rcode == AMX_OK && E->nchains > 1 && E->d_ovf_used && rc.feather > 0) {

@@ -139,6 +139,27 @@ def test_dense_tiles_stay_on_the_tiled_path(reflib, monkeypatch):
         assert mx <= 1 and n <= 0.01 * 96 * 96
 
 
+def test_pixel_with_hundreds_of_atoms_takes_the_general_path_for_that_call(reflib):
+    """300 atoms on one pixel: the 32-bit sums of the accumulating tile kernel could wrap, so it asks for the frames of that call
+    to be rendered again by the general path (64-bit sums) -- without switching the tiled path off for the table."""
+    n = 16
+    images = []
+    for k in range(2):
+        im = np.zeros((n, n, 4), dtype=np.uint8)
+        im[4 + k:8 + k, 5 + k:9 + k, :3] = np.arange(48, dtype=np.uint8).reshape(4, 4, 3) * 5 + 3 * k
+        im[4 + k:8 + k, 5 + k:9 + k, 3] = 255
+        images.append(im)
+    params = dict(motion=eng.LINEAR, fading=eng.LINEAR, density=300)
+    m = build_ref(reflib, images, seed=1, **params)
+    e = engine_from_ref(m, images, seed=1, **params)
+    for t in (0.0, 0.5):
+        n_diff, mx = diff_stats(m.render(t), e.render([t])[0])
+        assert mx <= 1 and n_diff <= 4, (t, n_diff, mx)
+    st, paths = e.render_tiled_stats(), e.render_path_frames()
+    assert st["fallbacks"] >= 1 and not st["blocked"], st
+    assert paths["general"] >= 1 and paths["tiled"] >= 2, paths
+
+
 def test_tiled_diagnostics_and_kernel_times():
     """amx_render_tiled_stats / amx_kernel_times: bin occupancy of a rendered batch and per-kernel device times."""
     images = scenes.square_to_disc(128) if hasattr(scenes, "square_to_disc") else scenes.ellipses(128, 2, seed=5)
