@@ -258,14 +258,17 @@ __device__ __forceinline__ bool atom_sample(const RIn &ri, const RConst &rc, con
 struct RenderStats { unsigned long long generic, ties, overflow; };
 
 // raw render inputs of one sorted atom
-struct RawIn { pword pt1, pt2; uint32_t atom, c1, c2, chain; double lag, slope; };
+struct RawIn { pword pt1, pt2, pt0, pt3; uint32_t atom, c1, c2, chain; double lag, slope; };
 
-template <bool PERLIN>
+// OUTER: also the outer spline controls (columns y - 1 and y + 2; stored when the morph has three key frames or more)
+template <bool PERLIN, bool OUTER = false>
 __device__ __forceinline__ RawIn load_raw(const RIn &ri, size_t A, uint32_t y, size_t i) {
     RawIn r;
     const size_t o = (size_t) y * A + i;
     r.pt1 = ri.pts[((size_t) y * ri.npt + 0) * A + i];
     r.pt2 = ri.pts[((size_t) y * ri.npt + 1) * A + i];
+    r.pt0 = r.pt3 = 0ull;
+    if (OUTER) { r.pt0 = ri.pts[((size_t) y * ri.npt + 2) * A + i]; r.pt3 = ri.pts[((size_t) y * ri.npt + 3) * A + i]; }
     r.atom = ri.atom[o];
     r.c1 = ri.c1[o]; r.c2 = ri.c2[o];
     r.chain = ri.chain ? ri.chain[o] : 0u;
@@ -776,13 +779,25 @@ __device__ __forceinline__ void split_h2(const double v, uint32_t *i, uint32_t *
     *f = d2u_round((v - (t - 4503599627370496.0)) * 255.0);                 // the fraction is exact
 }
 
+// floor(v) and round((v - floor(v)) * 255) for 0 <= v < 2^31; false otherwise (nothing is written then)
+__device__ __forceinline__ bool split_lean(const double v, uint32_t *i, uint32_t *f) {
+    const double t = __dadd_rd(v, 4503599627370496.0);                      // 2^52 + floor(v)
+    const uint32_t ip = (uint32_t) __double2loint(t);
+    if ((((uint32_t) __double2hiint(t) ^ 0x43300000u) | (ip >> 31)) != 0u) return false;
+    *i = ip & 0xffffu;
+    *f = d2u_round((v - (t - 4503599627370496.0)) * 255.0);                 // the fraction is exact
+    return true;
+}
+__device__ __noinline__ void split_spline_slow(double v, uint32_t *i, uint32_t *f) { split_spline_coord(v, i, f); }
+
 #ifndef BIN2_CTAS
 #define BIN2_CTAS 3
 #endif
-// FULL: the batch has all RBATCH frames (no per-frame test); LEAN: two key frames, spline, colour weight in [0, 1] for every
-// frame of the batch (checked on the host)
+// FULL: the batch has all RBATCH frames (no per-frame test); LEAN: spline motion with one colour weight in [0, 1] per frame and,
+// with three key frames or more, every frame's spline interval = the batch's key-frame interval, so that its four controls are
+// the stored columns y - 1, y, y + 1, y + 2 (all checked on the host)
 template <int MOTION, bool PERLIN, bool H2, bool FULL, bool LEAN>
-__global__ void __launch_bounds__(256, BIN2_CTAS)
+__global__ void __launch_bounds__(256, (LEAN && !H2) ? 2 : BIN2_CTAS)      // (the four-control sample needs 8 more registers: no spills at 2 CTAs per SM)
 k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb, const uint32_t n_live, const uint32_t nb_arg, const __grid_constant__ Bins bn) {
     const uint32_t nb = FULL ? RBATCH : nb_arg;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -793,14 +808,20 @@ k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const 
     const uint32_t y = rb.f[0].y;
     const uint32_t ntiles = bn.tiles_x * bn.tiles_y;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr bool OUTER = LEAN && !H2;
     RawIn next = RawIn();
-    if (i < n_live) next = load_raw<PERLIN>(ri, A, y, i);
+    if (i < n_live) next = load_raw<PERLIN, OUTER>(ri, A, y, i);
     // warp-uniform trip count: claiming bin slots is a warp collective
     for (uint32_t i0 = i - lane; i0 < n_live; i0 += stride, i += stride) {
         const bool valid = i < n_live;
         const RawIn raw = next;
-        if (i + stride < n_live) next = load_raw<PERLIN>(ri, A, y, (size_t) i + stride);
+        if (i + stride < n_live) next = load_raw<PERLIN, OUTER>(ri, A, y, (size_t) i + stride);
         const bool use = valid && ((pw_flags(raw.pt1) | pw_flags(raw.pt2)) & F_HAS_PIXEL) != 0;
+        double x0 = 0.0, y0 = 0.0, x3 = 0.0, y3 = 0.0;           // the outer controls (three key frames or more)
+        if (OUTER) {
+            x0 = u2d((uint32_t) pw_x256(raw.pt0)) * inv256; y0 = u2d((uint32_t) pw_y256(raw.pt0)) * inv256;
+            x3 = u2d((uint32_t) pw_x256(raw.pt3)) * inv256; y3 = u2d((uint32_t) pw_y256(raw.pt3)) * inv256;
+        }
         AtomIn in;
         in.pt1 = raw.pt1; in.pt2 = raw.pt2;
         in.x1 = u2d((uint32_t) pw_x256(raw.pt1)) * inv256; in.y1 = u2d((uint32_t) pw_y256(raw.pt1)) * inv256;
@@ -817,7 +838,22 @@ k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const 
             if (!FULL && s >= nb) continue;
             uint32_t fr, hx, hy;
             bool ok;
-            if (LEAN) {
+            if (LEAN && !H2) {
+                const RFrame &rf = rb.f[s];
+                const double vx = cr_eval(x0, in.x1, in.x2, x3, rf.b1, rf.b2, rf.b3, rf.b4);
+                const double vy = cr_eval(y0, in.y1, in.y2, y3, rf.b1, rf.b2, rf.b3, rf.b4);
+                uint32_t xf, yf;
+                // (a spline through four different points overshoots: a negative or huge sample takes the generic split)
+                if (!split_lean(vx, &hx, &xf)) split_spline_slow(vx, &hx, &xf);
+                if (!split_lean(vy, &hy, &yf)) split_spline_slow(vy, &hy, &yf);
+                const double str = rf.str, iw = 1.0 - str;
+                col[s] = pack_bytes(d2u_round(str * in.c1.r + iw * in.c2.r), d2u_round(str * in.c1.g + iw * in.c2.g),
+                                    d2u_round(str * in.c1.b + iw * in.c2.b), d2u_round(str * in.c1.a + iw * in.c2.a));
+                fr = xf + (yf << 8);
+                // clip (morph.cpp:552-555): outside the image the home must lie inside the bounding box -- and reaches no pixel
+                // of the image either way, which is the test below
+                ok = use;
+            } else if (LEAN) {
                 const RFrame &rf = rb.f[s];
                 // the controls alternate between the two end points (spline.cpp:29-38, operation order kept)
                 double vx, vy;
@@ -2124,9 +2160,14 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
     const uint32_t n_live = E->r_live[rb.f[0].y];
     const Bins bn = make_bins(E);
     const bool perlin = rc.fading == K_PERLIN, h2 = E->h == 2;
-    // the lean sample of k_bin2: two key frames, spline, every frame's colour weight inside [0, 1]
-    bool lean = h2 && !perlin && rc.motion == K_SPLINE;
-    for (uint32_t s = 0; s < nb; ++s) lean = lean && rb.f[s].str >= 0.0 && rb.f[s].str <= 1.0;
+    // the lean sample of k_bin2: spline, every frame's colour weight inside [0, 1]; two key frames, or (with the outer
+    // controls stored) every frame's spline interval equal to the batch's key-frame interval
+    bool lean = !perlin && rc.motion == K_SPLINE && (h2 || E->rnpt == 4);
+    for (uint32_t s = 0; s < nb; ++s) {
+        const RFrame &f = rb.f[s];
+        lean = lean && f.str >= 0.0 && f.str <= 1.0;
+        if (!h2) lean = lean && (uint32_t) f.p1 == f.y && (uint32_t) f.p2 == f.yn && (uint32_t) f.p0 == (f.y + E->h - 1u) % E->h && (uint32_t) f.p3 == (f.y + 2u) % E->h;
+    }
     const bool full = nb == RBATCH;
     g_ktime.begin(E->stream);
     if (n_live > 0) {
@@ -2138,9 +2179,9 @@ static void launch_tiled(Engine *E, const RConst &rc, const RBatch &rb, uint32_t
 #define AMX_BIN2(M, P, H, F, L) do { \
         static int per_sm2_dev[64] = {0}; \
         int &per_sm2 = per_sm2_dev[E->device & 63]; \
-        if (!per_sm2) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && (H) && !(P)>, 256, 0); if (per_sm2 < 1) per_sm2 = 1; } \
+        if (!per_sm2) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && !(P)>, 256, 0); if (per_sm2 < 1) per_sm2 = 1; } \
         const uint32_t blocks2 = std::min<uint32_t>(div_up(n_live, 256), (uint32_t) per_sm2 * (uint32_t) E->sm_count); \
-        k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && (H) && !(P)><<<blocks2, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
+        k_bin2<M, P, H, F, (L) && (M) == M_SPLINE && !(P)><<<blocks2, 256, 0, E->stream>>>(ri, rc, rb, n_live, nb, bn); } while (0)
 #define AMX_BIN_M(M) do { if (perlin) { if (h2) AMX_BIN(M, true, true); else AMX_BIN(M, true, false); } \
                           else        { if (h2) AMX_BIN(M, false, true); else AMX_BIN(M, false, false); } } while (0)
         if (rc.motion == K_LINEAR) AMX_BIN_M(M_LINEAR);

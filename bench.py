@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[1]): synthetic 1024x1024 RGBA, 2 key frames (ful
 1 048 576 atoms, spline motion + cosine fading, 64 output frames.
 
 One STEP = one pass of the hot path over one batch:
-    render phase : the 64 output frames of the morph (k_bin + k_tile per batch of 8 frames)
+    render phase : the 64 output frames of the morph (k_bin2 + k_acc per batch of 8 frames)
     swap phase   : SWAP_ROUNDS rounds of disjoint pair-swap proposals on the 1M-atom chain
 Both phases are timed separately with CUDA events on the engine's stream, inputs resident in HBM.
 `value` is the render throughput (frames/s); the swap throughput and its roofline are reported in
@@ -330,7 +330,7 @@ def run_b200(args):
     counted = timed.launches
     e.kernel_times(True)
     timed(render_step, max(1, min(args.steps, 3)), 1)
-    ktimes = e.kernel_times(False)                  # [k_bin, k_tile]
+    ktimes = e.kernel_times(False)                  # [k_bin2, k_acc]
     timed.launches = counted                        # (the diagnostic pass is not part of the timed region)
     # invariants of the sharded matcher, checked on every run at every N: each column stays the same multiset of key
     # points, the cost never rises (thread.cpp:1014-1038), and all replicas of the table are identical afterwards
@@ -434,23 +434,23 @@ def run_b200(args):
 
     render_bytes = A * 24 + P * 4                  # linear or h <= 3 -> 24 B/atom + 4 B/pixel
     swap_bytes = 32                                # h = 2: 4 distinct key points per proposal
-    # roofline of the render batch = the kernel pair k_bin + k_tile (one launch each per batch of frames): algorithmic bytes
+    # roofline of the render batch = the kernel pair k_bin2 + k_acc (one launch each per batch of frames): algorithmic bytes
     # of the frames of a batch / the pair's device time, measured with CUDA events around each launch on the engine's stream
     kb, kt = ktimes
     if kb["launches"] and kt["launches"] and kt["frames"]:
         pair_ms = kb["ms"] / kb["launches"] + kt["ms"] / kt["launches"]
         frames_per_launch = kt["frames"] / float(kt["launches"])
         r_ach = render_bytes * frames_per_launch / (pair_ms / 1000.0) / 1e9
-        kernels = {"k_bin": {"us_per_launch": 1000.0 * kb["ms"] / kb["launches"], "launches": kb["launches"]},
-                   "k_tile": {"us_per_launch": 1000.0 * kt["ms"] / kt["launches"], "launches": kt["launches"]},
+        kernels = {"k_bin2": {"us_per_launch": 1000.0 * kb["ms"] / kb["launches"], "launches": kb["launches"]},
+                   "k_acc": {"us_per_launch": 1000.0 * kt["ms"] / kt["launches"], "launches": kt["launches"]},
                    "frames_per_launch": frames_per_launch}
     else:
         r_ach = render_bytes * (F * args.steps) / (ms_render / 1000.0) / 1e9
         kernels = None
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")) as fh:
-            traffic = json.load(fh).get("k_bin+k_tile_dram_bytes_per_launch_pair")
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r03_traffic.json")) as fh:
+            traffic = json.load(fh).get("k_bin2+k_acc_dram_bytes_per_launch_pair")
     except Exception:
         pass
     s_ach = swap_bytes * (proposals / world) / (ms_swap / 1000.0) / 1e9
@@ -480,7 +480,7 @@ def run_b200(args):
                    "l2": "256 MB buffer written between timed steps", "step": "render %d frames; swap: %d rounds" % (F, SWAP_ROUNDS),
                    "parallelism": "frames: frame-range x%d; swap: atom-range x%d + 1 all-gather/step" % (world, world)},
         "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": traffic,
-                     "peak_kind": peak_kind, "kernel": "k_bin+k_tile (one launch each per batch of frames)",
+                     "peak_kind": peak_kind, "kernel": "k_bin2+k_acc (one launch each per batch of frames)",
                      "bytes_per_unit": render_bytes, "unit_name": "frame", "kernels": kernels},
         "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps, "rounds_per_step": SWAP_ROUNDS,
                  "issue": swap_issue,
@@ -666,7 +666,7 @@ def run_b200_c5(args):
                    "step": "render %d frames per GPU; swap: one sweep = 64 rounds on each of the %d columns" % (b - a, H),
                    "parallelism": "frames: frame-range x%d; swap: key-frame columns of a phase x%d + exchange of the refined columns" % (world, world)},
         "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak, "traffic": None, "peak_kind": peak_kind,
-                     "kernel": "k_bin+k_tile (one launch each per batch of frames)", "bytes_per_unit": render_bytes, "unit_name": "frame", "per": "GPU"},
+                     "kernel": "k_bin2+k_acc (one launch each per batch of frames)", "bytes_per_unit": render_bytes, "unit_name": "frame", "per": "GPU"},
         "swap": {"value": pps, "unit": "proposals/s", "ms_per_step": ms_swap / args.steps,
                  "exchange": ("p2p write-through + flag barrier" if matcher.p2p else "ncclBroadcast per column") if world > 1 else "none"},
         "e2e": {"value": F / s_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int((b - a) * P * 4)},
