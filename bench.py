@@ -192,6 +192,64 @@ def cpu_reference_numbers(m, frames, frame_budget_s=25.0, morph_steps=16, gpu_re
     return dict(fps=fps, frames=n, render_s=t_used, pps=pps, cores=int(cores), morph_s=dt, parity=parity)
 
 
+def other_configs(dev, peak):
+    """BASELINE.json configs 3, 4 and 5 on one GPU, device-resident frames/s (a few seconds each; N = 1 only).  Bytes per frame
+    are SURVEY.md section 8d's: 24 B (linear or <= 3 key frames) / 40 B (spline, >= 4 key frames) per atom + 4 B per pixel; the
+    fluid configuration adds 184 B per particle and MPM step."""
+    import time
+    import torch
+    from atomorph_b200 import engine as eng
+    from atomorph_b200 import scenes
+    res = {}
+
+    def timed_frames(e, times, size, reps):
+        out = torch.empty((len(times), size, size), dtype=torch.int32, device=dev)
+        e.render_into(times, out.data_ptr(), True)
+        e.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e.render_into(times, out.data_ptr(), True)
+        e.sync()
+        dt = (time.perf_counter() - t0) / reps
+        del out
+        return dt
+
+    def entry(name, what, n, dt, bytes_per_frame, e):
+        res[name] = {"workload": what, "frames_per_s": n / dt, "us_per_frame": 1e6 * dt / n, "bytes_per_frame": int(bytes_per_frame),
+                     "roofline_frac": bytes_per_frame * n / dt / 1e9 / peak, "path_frames": e.render_path_frames()}
+
+    try:
+        # C4: 512^2, 2 500 blobs per key frame (one chain per blob group), density 2
+        e = eng.Engine(dev.index, seed=1, motion=eng.LINEAR, fading=eng.COSINE, density=2, blob_rgba_weight=2, blob_size_weight=1, blob_xy_weight=3, threads=0, cycle_length=1000)
+        e.load_images(scenes.rect_blobs(512, 2500, frames=2, seed=11, min_side=2, max_side=20))
+        e.blobify(); e.match_init(); e.match_rounds(2000); e.init_chains(); e.swap_rounds(400); e.render_prepare()
+        A = e.table_device_ptr(0)[1]
+        dt = timed_frames(e, np.array([f / 128.0 for f in range(128)]), 512, 3)
+        entry("c4", "512x512, 2500 blobs per key frame, density 2, linear + cosine, 128 frames (several chains: general A-buffer path)", 128, dt, A * 24 + 512 * 512 * 4, e)
+        del e
+        # C5: 4096^2, 8 cyclic key frames, 16.7 M atoms, 64 of the 512 frames
+        e = eng.Engine(dev.index, seed=1, motion=eng.SPLINE, fading=eng.COSINE, threads=0, cycle_length=1000)
+        e.load_images(scenes.rotating_shapes(4096, 8))
+        e.step(8); e.swap_rounds(256); e.render_prepare()
+        A = e.table_device_ptr(0)[1]
+        dt = timed_frames(e, np.array([f / 512.0 for f in range(64)]), 4096, 2)
+        entry("c5", "4096x4096, 8 cyclic key frames, %d atoms, spline + cosine, 64 of 512 frames (--workload c5 is the multi-GPU run)" % A, 64, dt, A * 40 + 4096 * 4096 * 4, e)
+        del e
+        torch.cuda.empty_cache()
+        # C3: 1024^2, fluid (10 MPM steps per frame) + perlin fading + feather 2
+        e = eng.Engine(dev.index, seed=1, motion=eng.SPLINE, fading=eng.PERLIN, feather=2, fluid=10, threads=0, cycle_length=1000)
+        e.load_images(scenes.square_to_disc(1024))
+        e.step(8); e.swap_rounds(512); e.render_prepare()
+        A = e.table_device_ptr(0)[1]
+        dt = timed_frames(e, np.array([f / 64.0 for f in range(16)]), 1024, 1)
+        entry("c3", "1024x1024, 2 key frames, fluid 10 MPM steps per frame + perlin + feather 2, 16 frames (stateful particle path)", 16, dt, A * 24 + 1024 * 1024 * 4 + 10 * 184 * A, e)
+        del e
+        torch.cuda.empty_cache()
+    except Exception as ex:  # the extra configurations must never take the bench line down
+        res["error"] = repr(ex)
+    return res
+
+
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -526,6 +584,11 @@ def run_b200(args):
         except Exception as ex:  # the baseline must never take the GPU line down
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
+    if rank == 0 and world == 1 and not args.no_configs:
+        # the other BASELINE configurations, device-resident (N = 1): configs[2], [3], [4]
+        del out, flush
+        torch.cuda.empty_cache()
+        line["configs"] = other_configs(dev, peak)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -692,6 +755,7 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 3, 4 and 5 (N = 1)")
     ap.add_argument("--match-rounds", type=int, default=49152, help="untimed pair-swap rounds before rendering (C2: 24576 proposals per atom)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: BASELINE configs[1] (the bench line); c5: configs[4], 4096^2 x 8 key frames, strong scaling")
     args = ap.parse_args()

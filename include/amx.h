@@ -195,7 +195,7 @@ int  amx_lookahead_stats(amx_ctx *ctx, uint64_t stats2[2]);
  * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
  * went to an overflow list */
 int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
-/* device time of the two render kernels of every batch ([0] k_bin or k_scatter, [1] k_tile or k_gather_pixel), measured
+/* device time of the two render kernels of every batch ([0] k_bin2 or k_scatter, [1] k_acc (k_tile) or k_gather_pixel), measured
  * with CUDA event pairs on the engine's stream without synchronising between launches.  Returns the milliseconds,
  * launches and frames accumulated since the previous call, then switches the recording on (enable != 0) or off.
  * Process-wide (one engine per process records). */
