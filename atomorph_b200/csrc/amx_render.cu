@@ -520,6 +520,17 @@ __device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &r
     resolve_contributions<SINGLE>([&](auto f) { visit_contributions(ab, rc, px, py, f); }, rc, chain_of, boc, emit);
 }
 
+// Alpha of a pixel that ONE contribution reaches while `density` asks for more (count 1 < density): count / density times an
+// exact 255 (or any a) is often an exact .5 tie -- with density 2 on every such pixel -- and the reference's result then hangs on
+// the rounding of its doubles, round(wd * ((a * w) / w)) with w = n / 65025 and wd = 1 / density (morph.cpp:598-613).  One
+// contribution needs no ordering, so the doubles are evaluated right here instead of going through the ordered replay.
+__device__ __forceinline__ uint32_t alpha_single(const uint32_t a, const uint32_t n, const uint32_t density) {
+    const double w = (double) n / 65025.0;
+    const double q = ((double) a * w) / w;
+    const double wd = 1.0 / (double) density;
+    return to_u8(round(wd * q));
+}
+
 // exact round(num/den) (half up) for 2*num + den < 2^32, quotient <= 255: float estimate + integer fix-up.
 // *tie is set when num/den is an exact .5 tie (the only place where the reference's double sums can differ).
 __device__ __forceinline__ uint32_t rdiv_small(uint32_t num, uint32_t den, float rcp_d2, bool *tie) {
@@ -559,15 +570,29 @@ __device__ __forceinline__ uint32_t merge_chain(uint32_t a, uint32_t b) {
 
 // fold one record into the sums of a pixel; on == false disables it (record beyond the counter / splat not allowed).
 // Byte extraction is one PRMT each; 255 - fract is fract ^ 255.
+// Several chains: the contributions of the first two blobs that reach the pixel are summed separately (P, Q: each is resolved
+// from its own exact integer sums and the two are composited in blob order); a third blob marks P as PART_GENERIC (ordered replay).
 template <bool SINGLE, bool COUNTED, int DX, int DY>
-__device__ __forceinline__ void fold(Part &P, const uint4 &r, bool on) {
+__device__ __forceinline__ void fold(Part &P, Part &Q, const uint4 &r, bool on) {
     const uint32_t fr = r.y ^ ((DX ? 0u : 0x00ffu) | (DY ? 0u : 0xff00u));      // (DX ? xf : 255 - xf) | (DY ? yf : 255 - yf) << 8
     const uint32_t wx = __byte_perm(fr, 0, 0x4440), wy = on ? __byte_perm(fr, 0, 0x4441) : 0u;
     const uint32_t n = wx * wy;
-    P.R += __byte_perm(r.x, 0, 0x4440) * n; P.G += __byte_perm(r.x, 0, 0x4441) * n;
-    P.B += __byte_perm(r.x, 0, 0x4442) * n; P.A += __byte_perm(r.x, 0, 0x4443) * n; P.N += n;
-    if (COUNTED) P.cnt += (n != 0u);
-    if (!SINGLE) { if (n) P.chain = merge_chain(P.chain, r.y >> 16); }
+    const uint32_t cr = __byte_perm(r.x, 0, 0x4440), cg = __byte_perm(r.x, 0, 0x4441), cb = __byte_perm(r.x, 0, 0x4442), ca = __byte_perm(r.x, 0, 0x4443);
+    if (SINGLE) {
+        P.R += cr * n; P.G += cg * n; P.B += cb * n; P.A += ca * n; P.N += n;
+        if (COUNTED) P.cnt += (n != 0u);
+    } else {
+        const uint32_t tag = r.y >> 16;
+        const bool to_p = n != 0u && (P.chain == PART_NONE || P.chain == tag);
+        const bool to_q = n != 0u && !to_p && P.chain != PART_GENERIC && (Q.chain == PART_NONE || Q.chain == tag);
+        const uint32_t np = to_p ? n : 0u, nq = to_q ? n : 0u;
+        P.R += cr * np; P.G += cg * np; P.B += cb * np; P.A += ca * np; P.N += np;
+        Q.R += cr * nq; Q.G += cg * nq; Q.B += cb * nq; Q.A += ca * nq; Q.N += nq;
+        if (COUNTED) { P.cnt += to_p; Q.cnt += to_q; }
+        if (to_p) P.chain = tag;
+        if (to_q) Q.chain = tag;
+        if (n != 0u && !to_p && !to_q) P.chain = PART_GENERIC;        // a third blob (or P already given up)
+    }
 }
 
 // the ordered double replay of one pixel (ties, several blobs, very long lists): rare, kept out of line so that its
@@ -622,12 +647,13 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
     const size_t i = (size_t) py * rc.width + px;
     const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
 
-    Part P;
+    Part P, Q;
     P.R = P.G = P.B = P.A = P.N = P.cnt = 0; P.chain = PART_NONE;
-    fold<SINGLE, COUNTED, 0, 0>(P, a0, c0 > 0u); fold<SINGLE, COUNTED, 0, 0>(P, b0, c0 > 1u);
-    fold<SINGLE, COUNTED, 1, 0>(P, a1, c1 > 0u); fold<SINGLE, COUNTED, 1, 0>(P, b1, c1 > 1u);
-    fold<SINGLE, COUNTED, 0, 1>(P, a2, c2 > 0u); fold<SINGLE, COUNTED, 0, 1>(P, b2, c2 > 1u);
-    fold<SINGLE, COUNTED, 1, 1>(P, a3, c3 > 0u); fold<SINGLE, COUNTED, 1, 1>(P, b3, c3 > 1u);
+    Q = P;
+    fold<SINGLE, COUNTED, 0, 0>(P, Q, a0, c0 > 0u); fold<SINGLE, COUNTED, 0, 0>(P, Q, b0, c0 > 1u);
+    fold<SINGLE, COUNTED, 1, 0>(P, Q, a1, c1 > 0u); fold<SINGLE, COUNTED, 1, 0>(P, Q, b1, c1 > 1u);
+    fold<SINGLE, COUNTED, 0, 1>(P, Q, a2, c2 > 0u); fold<SINGLE, COUNTED, 0, 1>(P, Q, b2, c2 > 1u);
+    fold<SINGLE, COUNTED, 1, 1>(P, Q, a3, c3 > 0u); fold<SINGLE, COUNTED, 1, 1>(P, Q, b3, c3 > 1u);
     const uint32_t csum = c0 + c1 + c2 + c3;                      // upper bound of the contributions
     bool generic = csum > MAXK;
     const uint32_t cmax = max(max(c0, c1), max(c2, c3));
@@ -639,11 +665,11 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
         if (c1 > 2u) { t1 = ab.pair2[2 * (size_t) h1]; u1 = ab.pair2[2 * (size_t) h1 + 1]; }
         if (c2 > 2u) { t2 = ab.pair2[2 * (size_t) h2]; u2 = ab.pair2[2 * (size_t) h2 + 1]; }
         if (c3 > 2u) { t3 = ab.pair2[2 * (size_t) h3]; u3 = ab.pair2[2 * (size_t) h3 + 1]; }
-        fold<SINGLE, COUNTED, 0, 0>(P, t0, c0 > 2u); fold<SINGLE, COUNTED, 1, 0>(P, t1, c1 > 2u);
-        fold<SINGLE, COUNTED, 0, 1>(P, t2, c2 > 2u); fold<SINGLE, COUNTED, 1, 1>(P, t3, c3 > 2u);
+        fold<SINGLE, COUNTED, 0, 0>(P, Q, t0, c0 > 2u); fold<SINGLE, COUNTED, 1, 0>(P, Q, t1, c1 > 2u);
+        fold<SINGLE, COUNTED, 0, 1>(P, Q, t2, c2 > 2u); fold<SINGLE, COUNTED, 1, 1>(P, Q, t3, c3 > 2u);
         if (max(max(c0, c1), max(c2, c3)) > 3u) {
-            fold<SINGLE, COUNTED, 0, 0>(P, u0, c0 > 3u); fold<SINGLE, COUNTED, 1, 0>(P, u1, c1 > 3u);
-            fold<SINGLE, COUNTED, 0, 1>(P, u2, c2 > 3u); fold<SINGLE, COUNTED, 1, 1>(P, u3, c3 > 3u);
+            fold<SINGLE, COUNTED, 0, 0>(P, Q, u0, c0 > 3u); fold<SINGLE, COUNTED, 1, 0>(P, Q, u1, c1 > 3u);
+            fold<SINGLE, COUNTED, 0, 1>(P, Q, u2, c2 > 3u); fold<SINGLE, COUNTED, 1, 1>(P, Q, u3, c3 > 3u);
         }
         if (!generic && cmax > K_SLOTS) {
             // overflow lists: rare
@@ -655,45 +681,62 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
                 for (uint32_t j = K_SLOTS; j < cc[k]; ++j) {
                     const uint4 r = ab.ovf_rec[ovf_i];
                     ovf_i = r.z;
-                    if (k == 0) fold<SINGLE, COUNTED, 0, 0>(P, r, true);
-                    else if (k == 1) fold<SINGLE, COUNTED, 1, 0>(P, r, true);
-                    else if (k == 2) fold<SINGLE, COUNTED, 0, 1>(P, r, true);
-                    else fold<SINGLE, COUNTED, 1, 1>(P, r, true);
+                    if (k == 0) fold<SINGLE, COUNTED, 0, 0>(P, Q, r, true);
+                    else if (k == 1) fold<SINGLE, COUNTED, 1, 0>(P, Q, r, true);
+                    else if (k == 2) fold<SINGLE, COUNTED, 0, 1>(P, Q, r, true);
+                    else fold<SINGLE, COUNTED, 1, 1>(P, Q, r, true);
                 }
             }
         }
     }
     out += (size_t) rb.f[slot].dst * np;
-    if (!generic && P.N == 0) { out[i] = bgc; return; }           // no contribution with a non-zero weight
-    if (!COUNTED) P.cnt = csum;
+    if (!generic && P.N == 0 && (SINGLE || P.chain == PART_NONE)) { out[i] = bgc; return; }   // no contribution with a non-zero weight
+    if (!COUNTED) P.cnt = Q.cnt = csum;
     if (!SINGLE) generic = generic || P.chain == PART_GENERIC || rc.nchains > 65536u;   // 16-bit chain tags are ambiguous beyond 65536 chains
-    uint32_t pxl = 0;
-    if (!generic) {
-        // integer sums with exact rational rounding: the reference's result unless a quotient is an exact .5 tie
-        // (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits)
-        bool tie = false;
-        const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * P.N));
-        uint32_t cr = rdiv_small(P.R, P.N, rcp_d2, &tie), cg = rdiv_small(P.G, P.N, rcp_d2, &tie), cb = rdiv_small(P.B, P.N, rcp_d2, &tie), ca;
-        if (!COUNTED) ca = rc.density == 0 ? 0u : rdiv_small(P.A, P.N, rcp_d2, &tie);       // density 1: min(1, count/1) = 1
-        else if (P.cnt >= rc.density) ca = rdiv_small(P.A, P.N, rcp_d2, &tie);
+    // integer sums with exact rational rounding: the reference's result unless a quotient is an exact .5 tie
+    // (sum(n) <= 32 * 65025 < 2^21 and sum(c*n) < 2^29, so 2*num + den fits 32 bits)
+    auto resolve_part = [&](const Part &T, bool *tie) -> uint32_t {
+        const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * T.N));
+        uint32_t cr = rdiv_small(T.R, T.N, rcp_d2, tie), cg = rdiv_small(T.G, T.N, rcp_d2, tie), cb = rdiv_small(T.B, T.N, rcp_d2, tie), ca;
+        if (!COUNTED) ca = rc.density == 0 ? 0u : rdiv_small(T.A, T.N, rcp_d2, tie);       // density 1: min(1, count/1) = 1
+        else if (T.cnt >= rc.density) ca = rdiv_small(T.A, T.N, rcp_d2, tie);
+        else if (T.cnt == 1u) ca = alpha_single(T.A / T.N, T.N, rc.density);
         else {
-            unsigned long long num = (unsigned long long) P.A * P.cnt, den = (unsigned long long) P.N * rc.density;   // round(cnt*A / (density*N))
+            unsigned long long num = (unsigned long long) T.A * T.cnt, den = (unsigned long long) T.N * rc.density;   // round(cnt*A / (density*N))
             unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
             unsigned long long q = n2 / d2;
-            tie |= (n2 - q * d2 == 0ull);
+            *tie |= (n2 - q * d2 == 0ull);
             ca = (uint32_t) q;
         }
-        pxl = c_make(cr, cg, cb, ca);
+        return c_make(cr, cg, cb, ca);
+    };
+    uint32_t pxl = 0, pxl2 = 0;
+    const bool two = !SINGLE && !generic && Q.N != 0u;
+    if (!generic) {
+        bool tie = false;
+        pxl = resolve_part(P, &tie);
+        if (two) pxl2 = resolve_part(Q, &tie);
         generic = tie;
         if (tie && stats) atomicAdd(&stats->ties, 1ull);
     }
     if (!generic) {
         const uint32_t chain = SINGLE ? 0u : P.chain;           // the 16-bit tag is the chain itself here (nchains <= 65536)
         uint32_t colr = entry_color(pxl, 255u, chain, rc, y_frame, blob_avg, blob_distinct);
-        if (!rc.keep_background) { out[i] = c_a(colr) ? colr : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
+        if (!two) {
+            if (!rc.keep_background) { out[i] = c_a(colr) ? colr : 0u; return; }   // round((c/255.0)*255.0) == c for every byte c
+            Over ov;
+            ov.add(colr);
+            out[i] = ov.finish(bgc, true);
+            return;
+        }
+        // two blobs at the pixel: composited "over" in ascending blob order (morph.cpp:1342-1380)
+        uint32_t colr2 = entry_color(pxl2, 255u, Q.chain, rc, y_frame, blob_avg, blob_distinct);
+        const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
+        if (boc[Q.chain] < boc[P.chain]) { const uint32_t t = colr; colr = colr2; colr2 = t; }
         Over ov;
         ov.add(colr);
-        out[i] = ov.finish(bgc, true);
+        ov.add(colr2);
+        out[i] = ov.finish(bgc, rc.keep_background != 0);
         return;
     }
     // generic path: several blobs at the position, an exact tie, or a very long list
@@ -1205,6 +1248,7 @@ tile_body(const Bins &bn, const RConst &rc, const RBatch &rb,
             uint32_t cr = rdiv_small(Q.R, Q.N, rcp_d2, &tie), cg = rdiv_small(Q.G, Q.N, rcp_d2, &tie), cb = rdiv_small(Q.B, Q.N, rcp_d2, &tie), ca;
             if (!COUNTED) ca = rc.density == 0 ? 0u : rdiv_small(Q.A, Q.N, rcp_d2, &tie);
             else if (Q.cnt >= rc.density) ca = rdiv_small(Q.A, Q.N, rcp_d2, &tie);
+            else if (Q.cnt == 1u) ca = alpha_single(Q.A / Q.N, Q.N, rc.density);
             else {
                 unsigned long long num = (unsigned long long) Q.A * Q.cnt, den = (unsigned long long) Q.N * rc.density;
                 unsigned long long n2 = 2ull * num + den, d2 = 2ull * den;
@@ -1476,6 +1520,7 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
                 bool tie;
                 if (rc.density == 0u) { qa = 0u; tie = min(min(er, eg), eb) == 0u; }
                 else if (!COUNTED || cnt >= rc.density) tie = min(min(er, eg), min(eb, ea)) == 0u;
+                else if (cnt == 1u) { qa = alpha_single(A / N, N, rc.density); tie = min(min(er, eg), eb) == 0u; }
                 else {
                     const unsigned long long num = (unsigned long long) A * cnt, den = (unsigned long long) N * rc.density;   // round(cnt*A / (density*N))
                     const unsigned long long n2 = 2ull * num + den, dd = 2ull * den, q = n2 / dd;
