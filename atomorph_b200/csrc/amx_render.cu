@@ -831,7 +831,8 @@ __device__ __forceinline__ bool split_lean(const double v, uint32_t *i, uint32_t
     *f = d2u_round((v - (t - 4503599627370496.0)) * 255.0);                 // the fraction is exact
     return true;
 }
-__device__ __noinline__ void split_spline_slow(double v, uint32_t *i, uint32_t *f) { split_spline_coord(v, i, f); }
+// (out of line and returning in registers: pointer arguments would pin the caller's coordinates to local memory)
+__device__ __noinline__ uint2 split_spline_slow(double v) { uint2 r; split_spline_coord(v, &r.x, &r.y); return r; }
 
 #ifndef BIN2_CTAS
 #define BIN2_CTAS 3
@@ -887,8 +888,8 @@ k_bin2(const __grid_constant__ RIn ri, const __grid_constant__ RConst rc, const 
                 const double vy = cr_eval(y0, in.y1, in.y2, y3, rf.b1, rf.b2, rf.b3, rf.b4);
                 uint32_t xf, yf;
                 // (a spline through four different points overshoots: a negative or huge sample takes the generic split)
-                if (!split_lean(vx, &hx, &xf)) split_spline_slow(vx, &hx, &xf);
-                if (!split_lean(vy, &hy, &yf)) split_spline_slow(vy, &hy, &yf);
+                if (!split_lean(vx, &hx, &xf)) { const uint2 q = split_spline_slow(vx); hx = q.x; xf = q.y; }
+                if (!split_lean(vy, &hy, &yf)) { const uint2 q = split_spline_slow(vy); hy = q.x; yf = q.y; }
                 const double str = rf.str, iw = 1.0 - str;
                 col[s] = pack_bytes(d2u_round(str * in.c1.r + iw * in.c2.r), d2u_round(str * in.c1.g + iw * in.c2.g),
                                     d2u_round(str * in.c1.b + iw * in.c2.b), d2u_round(str * in.c1.a + iw * in.c2.a));
