@@ -386,7 +386,7 @@ class Engine:
 
     def kernel_times(self, enable):
         """Per-kernel device times of the render batches since the last call (ms, launches, frames per kernel class:
-        0 = k_bin / k_scatter, 1 = k_tile / k_gather_pixel); then switches the event recording on or off."""
+        0 = k_bin2 / k_scatter, 1 = k_acc (k_tile) / k_gather_pixel); then switches the event recording on or off."""
         ms = np.zeros(2, dtype=np.float64)
         ln = np.zeros(2, dtype=np.uint64)
         fr = np.zeros(2, dtype=np.uint64)

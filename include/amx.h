@@ -201,7 +201,7 @@ int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
  * Process-wide (one engine per process records). */
 int  amx_kernel_times(amx_ctx *ctx, int enable, double ms2[2], uint64_t launches2[2], uint64_t frames2[2]);
 /* frames rendered so far by [0] the tiled path (shared-memory tiles, feather == 0 without fluid) and [1] the general
- * A-buffer path (feather, per-blob fetch, or more than 3.5 atoms per pixel over a 32x32 tile); both are exact */
+ * A-buffer path (feather, per-blob fetch, several chains, or more than 7 atoms per pixel over a 32x32 tile); both are exact */
 int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
 /* tiled-path diagnostics: [0..3] largest record count seen in a bin of class interior / last column / last row / corner,
  * [4] largest record total of a tile, [5] unused (0), [6] render calls repeated on the general path,
