@@ -151,7 +151,14 @@ struct Engine {
     uint32_t *ab_cnt_base = nullptr;       // allocations behind ab_cnt / ab_pair (guard in front)
     uint4    *ab_pair_base = nullptr;
     uint32_t *ab_ovf_head = nullptr;
-    uint4    *ab_ovf_rec = nullptr;
+    uint4    *ab_ovf_rec = nullptr;        // overflow POOL: the records of a home beyond the direct slots, contiguous from ab_ovf_head[home]
+    uint4    *ab_ovf_list = nullptr;       // overflow records in arrival order {colour, meta, atom, claim index} ...
+    uint32_t *ab_ovf_list_home = nullptr;  // ... and their home (slot * canvas + position)
+    uint32_t *ab_ovf_ctrl = nullptr;       // [2][2] {list entries, pool top}; ping-pong between scatters
+    uint32_t  ab_ovf_parity = 0;
+    uint2    *gl_items = nullptr;          // positions the gather leaves to k_resolve_list: {canvas index, batch slot}
+    uint32_t *gl_count = nullptr;          // [2][2] {replays, heavy positions}; ping-pong: a batch's resolve kernel clears the other pair
+    uint32_t  gl_cap = 0;
     uint32_t  render_batch = 8;            // frames per launch pair (clamped to RBATCH on the tiled path, GBATCH on the general one)
     // tiled path (amx_render.cu: Bins): record bins per (frame slot of a batch, 32x32-pixel tile)
     uint2    *tb_rec = nullptr;

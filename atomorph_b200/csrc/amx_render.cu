@@ -84,17 +84,23 @@ struct RBatch {
 
 // Per-pixel A-buffer of one batch slot.  cnt[home] counts the atoms whose top-left splat target is `home`; the first
 // two of them sit side by side in pair[home] (one 32-byte sector per pixel), the next two in pair2[home], the others
-// hang off ovf_head[home] as a list through ovf_rec[atom].z.  Only cnt is ever cleared: a list is walked for exactly
-// cnt - K_SLOTS nodes.
+// lie contiguously in the overflow pool from ovf_rec[ovf_head[home]] on (cnt - K_SLOTS records).  The scatter cannot know how
+// many records a home will get, so it appends the overflow records to a list in arrival order; k_ovf_alloc then reserves a
+// pool range per overflowing home (the final counter is known by then) and k_ovf_place moves every record to
+// range start + claim index - K_SLOTS.  (The first version chained them into a list per home: a chain of dependent loads --
+// 135 us for the 529 records behind one pixel of BASELINE config 4.)  Only cnt is ever cleared.
 // Record: x = colour, y = x_fract | y_fract << 8 | (chain & 0xffff) << 16, z = atom (direct) / next (overflow).
 struct ABuf {
     uint32_t *cnt;
     uint4    *pair;               // [GBATCH][canvas][2]
     uint4    *pair2;              // [GBATCH][canvas][2], sparsely used
-    uint32_t *ovf_head;
-    uint4    *ovf_rec;
+    uint32_t *ovf_head;           // [GBATCH][canvas] first pool index of a home's overflow records
+    uint4    *ovf_rec;            // pool (indices are global over the batch slots)
+    uint4    *ovf_list;           // arrival-order list filled by the scatter {colour, meta, atom, claim index}
+    uint32_t *ovf_list_home;      // home of a list entry: slot * canvas + position
+    uint32_t *ovf_ctrl;           // [0] list entries, [1] pool top
+    uint32_t *ovf_ctrl_other;     // the control block of the next scatter: cleared by k_ovf_alloc
     size_t    canvas;             // stride between batch slots (cnt, pair/2, pair2/2, ovf_head)
-    size_t    A;                  // stride between batch slots (ovf_rec)
 };
 
 // per-(pixel, blob) entries, used by the feather / per-blob paths
@@ -289,9 +295,10 @@ __device__ __forceinline__ void store_pending(const Pending &p, const ABuf &ab, 
         if (p.k[s] < 2u) ab.pair[2 * hp + p.k[s]] = rec;
         else if (p.k[s] < 4u) ab.pair2[2 * hp + (p.k[s] - 2u)] = rec;
         else {
-            // overflow: list through ovf_rec, indexed by the ORIGINAL atom (unique per frame)
-            uint32_t next = atomicExch(&ab.ovf_head[hp], p.who);
-            ab.ovf_rec[(size_t) s * ab.A + p.who] = make_uint4(p.col[s], p.meta[s], next, 0u);
+            // overflow: appended in arrival order, moved to the home's pool range by k_ovf_place
+            const uint32_t e = atomicAdd(&ab.ovf_ctrl[0], 1u);
+            ab.ovf_list[e] = make_uint4(p.col[s], p.meta[s], p.who, p.k[s]);
+            ab.ovf_list_home[e] = (uint32_t) hp;
             if (stats) atomicAdd(&stats->overflow, 1ull);
         }
     }
@@ -353,6 +360,25 @@ k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, R
     store_pending(pend, ab, stats);
 }
 
+// pool ranges of the overflowing homes: the entry that claimed index K_SLOTS (exactly one per such home) reserves
+// cnt - K_SLOTS pool slots.  `ab.cnt` is the batch's counter buffer, final once the scatter has finished.
+__global__ void __launch_bounds__(256) k_ovf_alloc(const ABuf ab) {
+    if (blockIdx.x == 0u && threadIdx.x < 2u) ab.ovf_ctrl_other[threadIdx.x] = 0u;
+    const uint32_t n = ab.ovf_ctrl[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (ab.ovf_list[i].w != K_SLOTS) continue;
+        const uint32_t hp = ab.ovf_list_home[i];
+        ab.ovf_head[hp] = atomicAdd(&ab.ovf_ctrl[1], ab.cnt[hp] - K_SLOTS);
+    }
+}
+__global__ void __launch_bounds__(256) k_ovf_place(const ABuf ab) {
+    const uint32_t n = ab.ovf_ctrl[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 e = ab.ovf_list[i];
+        ab.ovf_rec[ab.ovf_head[ab.ovf_list_home[i]] + (e.w - K_SLOTS)] = make_uint4(e.x, e.y, e.z, 0u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------- gather
 // Visit every contribution to pixel (px, py): f(atom, colour, n, chain16) with n the integer bilinear numerator.
 // Splat targets and their edge rules: morph.cpp:558-588.  `ab` is already offset to the batch slot.  (Generic path.)
@@ -379,18 +405,20 @@ __device__ __forceinline__ void visit_contributions(const ABuf &ab, const RConst
         if (cn > 2) { uint4 r = ab.pair2[2 * hp]; emit(r.z, r); }
         if (cn > 3) { uint4 r = ab.pair2[2 * hp + 1]; emit(r.z, r); }
         if (cn > K_SLOTS) {
-            uint32_t i = ab.ovf_head[hp];
-            for (uint32_t j = K_SLOTS; j < cn; ++j) { uint4 r = ab.ovf_rec[i]; emit(i, r); i = r.z; }
+            const uint4 *o = ab.ovf_rec + ab.ovf_head[hp];
+            for (uint32_t j = K_SLOTS; j < cn; ++j) { const uint4 r = o[j - K_SLOTS]; emit(r.z, r); }
         }
     }
 }
 
 // the reference's per-position normalisation, contributions already in atom order (morph.cpp:598-613)
-__device__ __forceinline__ uint32_t resolve_fp(const uint32_t *cc, const uint32_t *cn, int first, int last, uint32_t density) {
+// (getc(i), getn(i): colour and bilinear numerator of the i-th contribution in the reference's order)
+template <typename GC, typename GN>
+__device__ __forceinline__ uint32_t resolve_fp_of(GC getc, GN getn, int first, int last, uint32_t density) {
     double r = 0.0, g = 0.0, b = 0.0, a = 0.0, weight_sum = 0.0;
     for (int i = first; i < last; ++i) {
-        double w = (double) cn[i] / 65025.0;
-        uint32_t c = cc[i];
+        double w = (double) getn(i) / 65025.0;
+        uint32_t c = getc(i);
         weight_sum += w;
         r += (double) c_r(c) * w;
         g += (double) c_g(c) * w;
@@ -404,6 +432,9 @@ __device__ __forceinline__ uint32_t resolve_fp(const uint32_t *cc, const uint32_
     b = round(b / weight_sum);
     a = round(wd * (a / weight_sum));
     return c_make(to_u8(r), to_u8(g), to_u8(b), to_u8(a));
+}
+__device__ __forceinline__ uint32_t resolve_fp(const uint32_t *cc, const uint32_t *cn, int first, int last, uint32_t density) {
+    return resolve_fp_of([&](int i) { return cc[i]; }, [&](int i) { return cn[i]; }, first, last, density);
 }
 
 // exact round-half-up of num/den for non-negative integers (fallback for pixels with > MAXK contributions)
@@ -461,20 +492,70 @@ struct Over {
 
 // Emits the resolved blob pixels of one position in ascending blob order: emit(chain, px).  visit(f) calls
 // f(atom, colour, n, chain16) for every contribution to the position (it may be invoked several times).
-template <bool SINGLE, typename V, typename E>
+// TAGGED: the visitor's fourth argument is the low 16 bits of the atom's chain (the A-buffer records carry it) -- with at most
+// 65536 chains that IS the chain, and chain_of[atom], a scattered load per contribution on the critical path of the walk (it
+// was 70 % of the general path's time on BASELINE config 4), is never read.
+template <bool SINGLE, bool TAGGED, typename V, typename E>
 __device__ __forceinline__ void resolve_contributions(V visit, const RConst &rc,
                                                       const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc, E emit) {
-    unsigned long long key[MAXK];
-    uint32_t cc[MAXK], cn[MAXK];
+    // the first MAXK contributions, kept sorted by (blob order, atom): {key low, key high, colour, n | chain tag << 16} in ONE
+    // 16-byte element, so that a step of the insertion sort is one local load and one local store (it was 42 % of the replay's
+    // instructions with three separate arrays)
+    uint4 el[MAXK];
     int count = 0;
-    visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
+    const bool tags = !SINGLE && TAGGED && rc.nchains <= 65536u;
+    auto chain_at = [&](uint32_t a, uint32_t tag) -> uint32_t { return SINGLE ? 0u : tags ? tag : chain_of[a]; };
+    // Heavy position (more than MAXK contributions: atoms of shrinking or volatile blobs piling up, lists of dependent loads behind
+    // the homes): exact integer sums per chain, emitted in ascending blob order.  The sums of up to HEAVY_NC chains are kept during
+    // the SAME walk -- seeded from the MAXK stored contributions the moment one more arrives --, so a heavy position costs one
+    // walk; only a position that more chains reach takes a walk per chain (below).
+    constexpr int HEAVY_NC = 16;
+    unsigned long long hs[HEAVY_NC][6];
+    uint32_t hchain[HEAVY_NC];
+    long long hkey[HEAVY_NC];
+    int nh = 0, hcur = -1;
+    bool hfull = false;
+    // the sums of the chain the walk is at live in registers (a heavy position is nearly always ONE blob piling up); they move to
+    // hs[] only when the chain changes
+    unsigned long long sR = 0, sG = 0, sB = 0, sA = 0, sN = 0, sC = 0;
+    uint32_t cur_chain = 0;
+    auto heavy_flush = [&]() {
+        if (hcur < 0) return;
+        hs[hcur][0] = sR; hs[hcur][1] = sG; hs[hcur][2] = sB; hs[hcur][3] = sA; hs[hcur][4] = sN; hs[hcur][5] = sC;
+    };
+    auto heavy_add = [&](uint32_t ch, uint32_t col, uint32_t n) {
+        if (hcur < 0 || ch != cur_chain) {
+            heavy_flush();
+            int j = 0;
+            while (j < nh && hchain[j] != ch) ++j;
+            if (j == nh) {
+                if (nh == HEAVY_NC) { hfull = true; hcur = -1; return; }
+                hchain[j] = ch; hkey[j] = SINGLE ? 0 : (long long) boc[ch];
+                for (int q = 0; q < 6; ++q) hs[j][q] = 0ull;
+                ++nh;
+            }
+            hcur = j; cur_chain = ch;
+            sR = hs[j][0]; sG = hs[j][1]; sB = hs[j][2]; sA = hs[j][3]; sN = hs[j][4]; sC = hs[j][5];
+        }
+        sR += c_r(col) * n; sG += c_g(col) * n; sB += c_b(col) * n; sA += c_a(col) * n; sN += n; sC += 1ull;
+    };
+    visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t tag) {
         if (count < MAXK) {
             unsigned long long k = a;
-            if (!SINGLE) k |= (unsigned long long) (uint32_t) boc[chain_of[a]] << 32;
+            if (!SINGLE) k |= (unsigned long long) (uint32_t) boc[chain_at(a, tag)] << 32;
             // insertion sort by (blob order, atom)
             int i = count;
-            while (i > 0 && key[i - 1] > k) { key[i] = key[i - 1]; cc[i] = cc[i - 1]; cn[i] = cn[i - 1]; --i; }
-            key[i] = k; cc[i] = col; cn[i] = n;
+            while (i > 0) {
+                const uint4 e = el[i - 1];
+                if ((((unsigned long long) e.y << 32) | e.x) <= k) break;
+                el[i] = e; --i;
+            }
+            el[i] = make_uint4((uint32_t) k, (uint32_t) (k >> 32), col, n | (tags ? tag << 16 : 0u));      // n <= 255 * 255 < 2^16
+        } else {
+            if (count == MAXK)
+                for (int i = 0; i < MAXK; ++i)
+                    heavy_add(SINGLE ? 0u : tags ? el[i].w >> 16 : chain_of[el[i].x], el[i].z, el[i].w & 0xffffu);
+            heavy_add(chain_at(a, tag), col, n);
         }
         ++count;
     });
@@ -483,29 +564,40 @@ __device__ __forceinline__ void resolve_contributions(V visit, const RConst &rc,
         int first = 0;
         while (first < count) {
             int last = first + 1;
-            if (!SINGLE) while (last < count && (key[last] >> 32) == (key[first] >> 32)) ++last;
+            if (!SINGLE) while (last < count && el[last].y == el[first].y) ++last;
             else last = count;
-            uint32_t chain = SINGLE ? 0u : chain_of[(uint32_t) key[first]];
-            emit(chain, resolve_fp(cc, cn, first, last, rc.density));
+            uint32_t chain = SINGLE ? 0u : tags ? el[first].w >> 16 : chain_of[el[first].x];
+            emit(chain, resolve_fp_of([&](int i) { return el[i].z; }, [&](int i) { return el[i].w & 0xffffu; }, first, last, rc.density));
             first = last;
         }
         return;
     }
-    // heavy position: exact integer sums, one chain at a time in ascending blob order
+    if (!hfull) {
+        heavy_flush();
+        long long prev = -1;
+        for (;;) {
+            int b = -1;
+            for (int j = 0; j < nh; ++j) if (hkey[j] > prev && (b < 0 || hkey[j] < hkey[b])) b = j;
+            if (b < 0) return;
+            emit(hchain[b], resolve_int(hs[b][0], hs[b][1], hs[b][2], hs[b][3], hs[b][4], hs[b][5], rc.density));
+            prev = hkey[b];
+        }
+    }
+    // (more than HEAVY_NC chains at a heavy position: one walk per chain)
     long long prev = -1;
     for (;;) {
         long long best = LLONG_MAX;
         uint32_t bchain = 0;
         if (SINGLE) { if (prev < 0) best = 0; }
-        else visit([&](uint32_t a, uint32_t, uint32_t, uint32_t) {
-            uint32_t c = chain_of[a];
+        else visit([&](uint32_t a, uint32_t, uint32_t, uint32_t tag) {
+            uint32_t c = chain_at(a, tag);
             long long k = boc[c];
             if (k > prev && k < best) { best = k; bchain = c; }
         });
         if (best == LLONG_MAX) break;
         unsigned long long R = 0, G = 0, B = 0, Av = 0, N = 0, cnt = 0;
-        visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t) {
-            if (!SINGLE && chain_of[a] != bchain) return;
+        visit([&](uint32_t a, uint32_t col, uint32_t n, uint32_t tag) {
+            if (!SINGLE && chain_at(a, tag) != bchain) return;
             R += c_r(col) * n; G += c_g(col) * n; B += c_b(col) * n; Av += c_a(col) * n; N += n; ++cnt;
         });
         emit(bchain, resolve_int(R, G, B, Av, N, cnt, rc.density));
@@ -517,7 +609,7 @@ template <bool SINGLE, typename E>
 __device__ __forceinline__ void resolve_position(const ABuf &ab, const RConst &rc,
                                                  const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ boc,
                                                  uint32_t px, uint32_t py, E emit) {
-    resolve_contributions<SINGLE>([&](auto f) { visit_contributions(ab, rc, px, py, f); }, rc, chain_of, boc, emit);
+    resolve_contributions<SINGLE, true>([&](auto f) { visit_contributions(ab, rc, px, py, f); }, rc, chain_of, boc, emit);
 }
 
 // Alpha of a pixel that ONE contribution reaches while `density` asks for more (count 1 < density): count / density times an
@@ -545,7 +637,7 @@ __device__ __forceinline__ uint32_t rdiv_small(uint32_t num, uint32_t den, float
 // the A-buffer of batch slot `slot`
 __device__ __forceinline__ ABuf ab_at(ABuf ab, uint32_t slot) {
     size_t o = (size_t) slot * ab.canvas;
-    ab.cnt += o; ab.pair += 2 * o; ab.pair2 += 2 * o; ab.ovf_head += o; ab.ovf_rec += (size_t) slot * ab.A;
+    ab.cnt += o; ab.pair += 2 * o; ab.pair2 += 2 * o; ab.ovf_head += o;
     return ab;
 }
 
@@ -611,12 +703,23 @@ __device__ __noinline__ uint32_t resolve_generic(const ABuf *abuf, uint32_t slot
     return ov.finish(bgc, rc.keep_background != 0);
 }
 
+// positions whose ordered replay is deferred to k_resolve_list
+struct GList {
+    uint2    *items;              // {canvas index, batch slot}: [0, cap) replays, [cap, 2 cap) heavy positions (more than MAXK records)
+    uint32_t *count;              // [0] replays, [1] heavy positions appended by this batch's gather (may exceed cap: the surplus was
+                                  // resolved in place)
+    uint32_t *count_other;        // the other batch parity's counters: cleared by k_resolve_list
+    uint32_t  cap;
+};
+#ifndef GATHER_BY
+#define GATHER_BY 8
+#endif
 template <bool SINGLE, bool COUNTED>
 __global__ void __launch_bounds__(256)
 k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_clean, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
                const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
                const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-               const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats) {
+               const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, RenderStats *__restrict__ stats, const GList gl) {
     const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= rc.cw || py >= rc.ch) return;
     const uint32_t slot = blockIdx.z, y_frame = rb.f[slot].y;
@@ -677,10 +780,9 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (cc[k] <= K_SLOTS) continue;
-                uint32_t ovf_i = ab.ovf_head[hh[k]];
+                const uint4 *o = ab.ovf_rec + ab.ovf_head[hh[k]];
                 for (uint32_t j = K_SLOTS; j < cc[k]; ++j) {
-                    const uint4 r = ab.ovf_rec[ovf_i];
-                    ovf_i = r.z;
+                    const uint4 r = o[j - K_SLOTS];
                     if (k == 0) fold<SINGLE, COUNTED, 0, 0>(P, Q, r, true);
                     else if (k == 1) fold<SINGLE, COUNTED, 1, 0>(P, Q, r, true);
                     else if (k == 2) fold<SINGLE, COUNTED, 0, 1>(P, Q, r, true);
@@ -739,9 +841,201 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
         out[i] = ov.finish(bgc, rc.keep_background != 0);
         return;
     }
-    // generic path: several blobs at the position, an exact tie, or a very long list
+    // generic path: several blobs at the position, an exact tie, or a very long list.  The ordered replay is a few thousand
+    // dependent instructions for ONE lane of this warp (config 4: 2.6 % of the pixels, 83 % of this kernel's time when resolved
+    // here), so the position goes onto a list that k_resolve_list works off with every lane busy.
     if (stats) atomicAdd(&stats->generic, 1ull);
+    if (gl.cap != 0u) {
+        const uint32_t heavy = csum > MAXK ? 1u : 0u;
+        const uint32_t k = atomicAdd(gl.count + heavy, 1u);
+        if (k < gl.cap) { gl.items[heavy * gl.cap + k] = make_uint2(ci, slot); return; }
+    }
     out[i] = resolve_generic<SINGLE>(&abuf, slot, &rc, chain_of, blob_of_chain + (size_t) y_frame * rc.nchains, blob_avg, blob_distinct, y_frame, px, py, bgc);
+}
+
+// A listed position with at most MAXK contributions, resolved WITHOUT the ordered replay when no quotient is an exact .5 tie:
+// integer sums per blob (exact rational rounding = the reference's doubles away from ties, like the one- and two-blob cases of
+// k_gather_pixel), the blobs composited in ascending blob order.  false: a tie, more than NB blobs, two blobs of equal order or
+// ambiguous chain tags -- the caller takes the replay.
+template <bool SINGLE>
+__device__ __forceinline__ bool resolve_blobs_int(const ABuf &ab, const RConst &rc, const int32_t *__restrict__ boc, uint32_t px, uint32_t py,
+                                                  uint32_t y_frame, const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+                                                  uint32_t bgc, uint32_t *res) {
+    constexpr int NB = 8;
+    if (!SINGLE && rc.nchains > 65536u) return false;
+    Part T[NB];
+    int nb = 0;
+    bool give_up = false;
+    visit_contributions(ab, rc, px, py, [&](uint32_t, uint32_t col, uint32_t n, uint32_t tag) {
+        int j = 0;
+        while (j < nb && T[j].chain != tag) ++j;
+        if (j == nb) {
+            if (nb == NB) { give_up = true; return; }
+            T[j].R = T[j].G = T[j].B = T[j].A = T[j].N = T[j].cnt = 0u; T[j].chain = tag;
+            ++nb;
+        }
+        T[j].R += c_r(col) * n; T[j].G += c_g(col) * n; T[j].B += c_b(col) * n; T[j].A += c_a(col) * n; T[j].N += n; T[j].cnt += 1u;
+    });
+    if (give_up || nb == 0) return false;
+    uint32_t pxl[NB];
+    long long key[NB];
+    bool tie = false;
+    for (int j = 0; j < nb; ++j) {
+        const Part &P = T[j];
+        const float rcp_d2 = __frcp_rz(__uint2float_ru(2u * P.N));
+        const uint32_t cr = rdiv_small(P.R, P.N, rcp_d2, &tie), cg = rdiv_small(P.G, P.N, rcp_d2, &tie), cb = rdiv_small(P.B, P.N, rcp_d2, &tie);
+        uint32_t ca;
+        if (rc.density == 0u) ca = 0u;
+        else if (P.cnt >= rc.density) ca = rdiv_small(P.A, P.N, rcp_d2, &tie);
+        else if (P.cnt == 1u) ca = alpha_single(P.A / P.N, P.N, rc.density);
+        else {
+            const unsigned long long num = (unsigned long long) P.A * P.cnt, den = (unsigned long long) P.N * rc.density;   // round(cnt*A / (density*N))
+            const unsigned long long n2 = 2ull * num + den, d2 = 2ull * den, q = n2 / d2;
+            tie |= (n2 - q * d2 == 0ull);
+            ca = (uint32_t) q;
+        }
+        pxl[j] = c_make(cr, cg, cb, ca);
+        key[j] = SINGLE ? 0 : (long long) boc[P.chain];
+    }
+    if (tie) return false;
+    Over ov;
+    long long prev = LLONG_MIN;
+    for (int r = 0; r < nb; ++r) {
+        int b = -1;
+        for (int j = 0; j < nb; ++j) if (key[j] > prev && (b < 0 || key[j] < key[b])) b = j;
+        if (b < 0) return false;                                    // two blobs of equal order
+        ov.add(entry_color(pxl[b], 255u, SINGLE ? 0u : T[b].chain, rc, y_frame, blob_avg, blob_distinct));
+        prev = key[b];
+    }
+    *res = ov.finish(bgc, rc.keep_background != 0);
+    return true;
+}
+
+// the deferred replays of one batch: one thread per listed position
+#ifndef LIST_LANES
+#define LIST_LANES 8u
+#endif
+template <bool SINGLE>
+__global__ void __launch_bounds__(32)
+k_resolve_list(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+               const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+               const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+               const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList gl) {
+    const uint32_t n = min(gl.count[0], gl.cap);
+    if (blockIdx.x == 0u && threadIdx.x < 2u) gl.count_other[threadIdx.x] = 0u;
+    const size_t np = (size_t) rc.width * rc.height;
+    // LIST_LANES lanes of a warp take a position each: the replay is a chain of dependent instructions whose length differs from
+    // position to position, so a warp runs as long as the union of its lanes' paths -- few lanes per warp and many warps hide
+    // that latency
+    if (threadIdx.x % (32u / LIST_LANES) != 0u) return;
+    const uint32_t per_cta = LIST_LANES;
+    for (uint32_t k = blockIdx.x * per_cta + threadIdx.x / (32u / LIST_LANES); k < n; k += gridDim.x * per_cta) {
+        const uint2 it = gl.items[k];
+        const uint32_t slot = it.y, px = it.x % rc.cw, py = it.x / rc.cw, y_frame = rb.f[slot].y;
+        const size_t i = (size_t) py * rc.width + px;
+        const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+        const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
+        uint32_t res;
+        if (!resolve_blobs_int<SINGLE>(ab_at(abuf, slot), rc, boc, px, py, y_frame, blob_avg, blob_distinct, bgc, &res))
+            res = resolve_generic<SINGLE>(&abuf, slot, &rc, chain_of, boc, blob_avg, blob_distinct, y_frame, px, py, bgc);
+        out[(size_t) rb.f[slot].dst * np + i] = res;
+    }
+}
+
+// Heavy positions (more than MAXK records behind the four homes: atoms of shrinking or volatile blobs piling up -- 612 at one pixel
+// of BASELINE config 4): beyond MAXK contributions the result is the exact integer quotient per blob, blobs composited in ascending
+// blob order -- no order inside a blob.  One WARP per position: the lanes stride over the homes' records (direct slots, then the
+// contiguous pool range) and reduce with shuffles -- one pass to count, then per blob one pass that finds the next blob in order
+// (ties between blobs of equal order go to the record visited first, as in resolve_contributions) and one that sums it.  A
+// position that turns out to have at most MAXK contributions with a non-zero weight goes through the serial replay on lane 0.
+template <bool SINGLE>
+__global__ void __launch_bounds__(128)
+k_resolve_heavy(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+                const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+                const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+                const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList gl) {
+    const uint32_t n = min(gl.count[1], gl.cap);
+    const uint32_t lane = threadIdx.x & 31u, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const size_t np = (size_t) rc.width * rc.height;
+    const bool tags_ok = SINGLE || rc.nchains <= 65536u;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nwarps) {
+        const uint2 it = gl.items[gl.cap + e];
+        const uint32_t slot = it.y, px = it.x % rc.cw, py = it.x / rc.cw, y_frame = rb.f[slot].y;
+        const size_t i = (size_t) py * rc.width + px;
+        const ABuf ab = ab_at(abuf, slot);
+        const int32_t *boc = blob_of_chain + (size_t) y_frame * rc.nchains;
+        // f(record, weight, visit index): every contribution with a non-zero weight, lane-strided; the visit index orders them as
+        // visit_contributions does (home, then slot)
+        auto stream = [&](auto f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // splat targets and their edge rules as in visit_contributions (morph.cpp:558-588)
+                const uint32_t dx = k & 1, dy = k >> 1;
+                bool ok = px >= dx && py >= dy;
+                const uint32_t hx = px - dx, hy = py - dy;
+                if (k == 1) ok = ok && (hx < rc.bx2 || hx + 1 < rc.width);
+                else if (k == 2) ok = ok && (hy < rc.by2 || hy + 1 < rc.height);
+                else if (k == 3) ok = ok && ((hy < rc.by2 && hx < rc.bx2) || (hy + 1 < rc.height && hx + 1 < rc.width));
+                if (!ok) continue;
+                const size_t hp = (size_t) hy * rc.cw + hx;
+                const uint32_t cn = ab.cnt[hp];
+                const uint4 *pool = ab.ovf_rec + (cn > K_SLOTS ? ab.ovf_head[hp] : 0u);
+                for (uint32_t j = lane; j < cn; j += 32u) {
+                    const uint4 r = j < 2u ? ab.pair[2 * hp + j] : j < K_SLOTS ? ab.pair2[2 * hp + (j - 2u)] : pool[j - K_SLOTS];
+                    const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
+                    const uint32_t w = (dx ? xf : 255u - xf) * (dy ? yf : 255u - yf);
+                    if (w != 0u) f(r, w, ((uint32_t) k << 28) | j);
+                }
+            }
+        };
+        uint32_t cnt = 0;
+        stream([&](const uint4 &, uint32_t, uint32_t) { ++cnt; });
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        const uint32_t bgc = rc.keep_background ? bg[(size_t) slot * np + i] : 0u;
+        if (cnt <= MAXK || !tags_ok) {
+            if (lane == 0u)
+                out[(size_t) rb.f[slot].dst * np + i] = resolve_generic<SINGLE>(&abuf, slot, &rc, chain_of, boc, blob_avg, blob_distinct, y_frame, px, py, bgc);
+            continue;
+        }
+        Over ov;
+        long long prev = -1;
+        for (;;) {
+            // the next blob in order: smallest (blob order, visit index) with blob order > prev
+            unsigned long long best = ~0ull;
+            uint32_t btag = 0u;
+            if (SINGLE) { if (prev < 0) best = 0ull; }
+            else stream([&](const uint4 &r, uint32_t, uint32_t vi) {
+                const uint32_t tag = r.y >> 16;
+                const long long k = boc[tag];
+                const unsigned long long key = ((unsigned long long) (uint32_t) k << 32) | vi;
+                if (k > prev && key < best) { best = key; btag = tag; }
+            });
+            unsigned long long wbest = best;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, wbest, d); wbest = o < wbest ? o : wbest; }
+            if (wbest == ~0ull) break;
+            uint32_t bchain = 0u;
+            if (!SINGLE) {
+                const uint32_t owner = __ballot_sync(0xffffffffu, best == wbest);
+                bchain = __shfl_sync(0xffffffffu, btag, __ffs((int) owner) - 1);
+            }
+            unsigned long long R = 0, G = 0, B = 0, A = 0, N = 0;
+            uint32_t c = 0;
+            stream([&](const uint4 &r, uint32_t w, uint32_t) {
+                if (!SINGLE && (r.y >> 16) != bchain) return;
+                R += c_r(r.x) * w; G += c_g(r.x) * w; B += c_b(r.x) * w; A += c_a(r.x) * w; N += w; ++c;
+            });
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                R += __shfl_xor_sync(0xffffffffu, R, d); G += __shfl_xor_sync(0xffffffffu, G, d); B += __shfl_xor_sync(0xffffffffu, B, d);
+                A += __shfl_xor_sync(0xffffffffu, A, d); N += __shfl_xor_sync(0xffffffffu, N, d); c += __shfl_xor_sync(0xffffffffu, c, d);
+            }
+            ov.add(entry_color(resolve_int(R, G, B, A, N, c, rc.density), 255u, bchain, rc, y_frame, blob_avg, blob_distinct));
+            prev = SINGLE ? 0 : (long long) (int32_t) (uint32_t) (wbest >> 32);
+        }
+        if (lane == 0u) out[(size_t) rb.f[slot].dst * np + i] = ov.finish(bgc, rc.keep_background != 0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------- tiled path (feather == 0)
@@ -1054,7 +1348,7 @@ __device__ __noinline__ uint32_t resolve_generic_tile(const unsigned char *smem,
         }
     };
     Over ov;
-    resolve_contributions<SINGLE>(visit, rc, chain_of, boc, [&](uint32_t ch, uint32_t p) {
+    resolve_contributions<SINGLE, false>(visit, rc, chain_of, boc, [&](uint32_t ch, uint32_t p) {
         ov.add(entry_color(p, 255u, ch, rc, y_frame, blob_avg, blob_distinct));
     });
     return ov.finish(bgc, rc.keep_background != 0);
@@ -1421,6 +1715,10 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
         for (uint32_t d = 1; d < 8u; d <<= 1) { const uint32_t u = __shfl_up_sync(0x1ffu, e, d); if (tid >= d) e += u; }
         cx.rest_end[tid] = e;
     }
+    // the first record of every thread is requested before the bin counters are known (the bins have a fixed stride, so the
+    // address needs no load; a slot beyond the count holds stale bytes and is discarded below): one global round trip less
+    // on the critical path of a CTA
+    const uint2 spec = __ldcs(bn.rec + (slot * ntiles + tile) * T_STRIDE + tid);
     if (tid >= 32u && tid < 36u) bn.cnt_other[((size_t) slot * ntiles + tile) * 4u + (tid - 32u)] = 0u;
     if (tid >= 64u && tid < 98u) cx.tie_mask[tid - 64u] = 0u;
     if (tid >= 128u && tid < 128u + A_TIE_MAX) cx.con_cnt[tid - 128u] = 0u;
@@ -1454,7 +1752,7 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
         const uint2 none = make_uint2(0xff000000u, 0u);
         const uint2 *rec = bn.rec + cx.seg_first[0];
         uint32_t i = tid;
-        uint2 nxt = i < n0 ? __ldcs(rec + i) : none;
+        uint2 nxt = i < n0 ? spec : none;
         for (uint32_t i0 = tid - lane; i0 < n0; i0 += 256u, i += 256u) {
             const uint2 r = nxt;
             const bool valid = i < n0;
@@ -1573,13 +1871,10 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
             __syncthreads();
         }
         const unsigned long long rows2 = (unsigned long long) cx.tie_rows << 1;      // bit 1 + r
-        for (uint32_t j = tid; j < m; j += 256u) {
-            uint32_t sgm = 0u, g = cx.seg_first[0] + j;
-            if (j >= n0) { sgm = acc_rest_segment(cx, j - n0); g = cx.seg_first[sgm] + (j - n0 - cx.rest_end[sgm - 1u]); }
-            const uint2 r = bn.rec[g];
+        auto collect = [&](const uint2 r, const uint32_t sgm, const uint32_t g) {
             const uint32_t v = r.y >> 16;
             const int hy = (int) (v >> 5) + (sgm >= 6u ? -32 : 0);                   // home row in this tile's pixel coordinates, -1 .. 31
-            if (((rows2 >> (hy + 1)) & 3ull) == 0ull) continue;                      // neither row hy nor hy + 1 has a tie
+            if (((rows2 >> (hy + 1)) & 3ull) == 0ull) return;                        // neither row hy nor hy + 1 has a tie
             const int hx = (int) (v & 31u) + ((sgm == 4u || sgm == 5u || sgm == 8u) ? -32 : 0);
             const uint32_t xf = r.y & 255u, yf = (r.y >> 8) & 255u;
 #pragma unroll
@@ -1592,6 +1887,14 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
                 const uint32_t t = cx.tie_of[(qy << 5) | qx];
                 const uint32_t c = atomicAdd(&cx.con_cnt[t], 1u);
                 if (c < A_CON) { con_atom[t * A_CON + c] = bn.atom[g]; con_col[t * A_CON + c] = r.x; con_n[t * A_CON + c] = nn; }
+            }
+        };
+        {
+            const uint32_t first0 = cx.seg_first[0];
+            for (uint32_t j = tid; j < n0; j += 256u) collect(bn.rec[first0 + j], 0u, first0 + j);
+            for (uint32_t j = tid; j < nrest; j += 256u) {
+                const uint32_t sgm = acc_rest_segment(cx, j), g = cx.seg_first[sgm] + (j - cx.rest_end[sgm - 1u]);
+                collect(bn.rec[g], sgm, g);
             }
         }
         __syncthreads();
@@ -1857,12 +2160,12 @@ void engine_render_free(Engine *E) {
     dev_free(E->acc_owner); dev_free(E->acc_hasovf); dev_free(E->ovf_key);
     dev_free(E->d_ovf_used); dev_free(E->blob_px);
     dev_free(E->d_pix); E->d_pix = nullptr; E->d_pix_cap = 0;
-    dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->d_bg);
+    dev_free(E->ab_cnt_base); dev_free(E->d_render_stats); dev_free(E->ab_pair_base); dev_free(E->ab_pair2); dev_free(E->ab_ovf_head); dev_free(E->ab_ovf_rec); dev_free(E->ab_ovf_list); dev_free(E->ab_ovf_list_home); dev_free(E->ab_ovf_ctrl); dev_free(E->gl_items); dev_free(E->gl_count); dev_free(E->d_bg);
     E->acc_owner = nullptr; E->acc_hasovf = nullptr; E->ovf_key = nullptr;
     E->d_ovf_used = nullptr; E->blob_px = nullptr; E->ovf_cap = 0;
     dev_free(E->tb_rec); dev_free(E->tb_atom); dev_free(E->tb_chain); dev_free(E->tb_cnt); dev_free(E->tb_flag);
     E->tb_rec = nullptr; E->tb_atom = E->tb_chain = E->tb_cnt = E->tb_flag = nullptr; E->tb_tiles_x = E->tb_tiles_y = 0;
-    E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->d_bg = nullptr; E->d_bg_cap = 0;
+    E->ab_cnt = E->ab_cnt_base = nullptr; E->d_render_stats = nullptr; E->ab_pair = E->ab_pair_base = E->ab_pair2 = nullptr; E->ab_ovf_head = nullptr; E->ab_ovf_rec = nullptr; E->ab_ovf_list = nullptr; E->ab_ovf_list_home = nullptr; E->ab_ovf_ctrl = nullptr; E->gl_items = nullptr; E->gl_count = nullptr; E->gl_cap = 0; E->d_bg = nullptr; E->d_bg_cap = 0;
     E->render_ready = false;
 }
 
@@ -1931,8 +2234,19 @@ int engine_render_prepare(Engine *E) {
             !dev_alloc(E, (void **) &E->ab_pair_base, ((size_t) 2 * GBATCH * cv + 2 * guard) * 16, "abuf record pairs") ||
             !dev_alloc(E, (void **) &E->ab_pair2, (size_t) 2 * GBATCH * cv * 16, "abuf second record pairs") ||
             !dev_alloc(E, (void **) &E->ab_ovf_head, GBATCH * cv * 4, "abuf overflow heads") ||
-            !dev_alloc(E, (void **) &E->ab_ovf_rec, GBATCH * E->A * 16, "abuf overflow records"))
+            !dev_alloc(E, (void **) &E->ab_ovf_rec, GBATCH * E->A * 16, "abuf overflow pool") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_list, GBATCH * E->A * 16, "abuf overflow list") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_list_home, GBATCH * E->A * 4, "abuf overflow list homes") ||
+            !dev_alloc(E, (void **) &E->ab_ovf_ctrl, 16, "abuf overflow control"))
             return AMX_ERR_NOMEM;
+        if ((uint64_t) GBATCH * cv >= (1ull << 32)) { E->err = "canvas too large for the A-buffer"; return AMX_ERR_ARG; }
+        cudaMemsetAsync(E->ab_ovf_ctrl, 0, 16, E->stream);
+        E->ab_ovf_parity = 0;
+        // positions left to the list kernel (ordered replay): a quarter of the batch's positions, the rest is resolved in place
+        E->gl_cap = (uint32_t) std::min<size_t>(GBATCH * cv / 8 + 1024, 1u << 25);
+        if (!dev_alloc(E, (void **) &E->gl_items, (size_t) 2 * E->gl_cap * 8, "replay lists") || !dev_alloc(E, (void **) &E->gl_count, 16, "replay list counters"))
+            return AMX_ERR_NOMEM;
+        cudaMemsetAsync(E->gl_count, 0, 16, E->stream);
         // two counter buffers: the gather of a batch clears the one the previous batch used, so no memset per batch
         E->ab_cnt = E->ab_cnt_base + guard;
         E->ab_pair = E->ab_pair_base + 2 * guard;
@@ -2129,7 +2443,9 @@ static ABuf make_abuf(Engine *E) {
     ABuf ab;
     size_t cv = E->canvas();
     ab.cnt = E->ab_cnt + (size_t) E->ab_parity * GBATCH * cv; ab.pair = E->ab_pair; ab.pair2 = E->ab_pair2; ab.ovf_head = E->ab_ovf_head; ab.ovf_rec = E->ab_ovf_rec;
-    ab.canvas = cv; ab.A = E->A;
+    ab.ovf_list = E->ab_ovf_list; ab.ovf_list_home = E->ab_ovf_list_home;
+    ab.ovf_ctrl = E->ab_ovf_ctrl + 2u * E->ab_ovf_parity; ab.ovf_ctrl_other = E->ab_ovf_ctrl + 2u * (E->ab_ovf_parity ^ 1u);
+    ab.canvas = cv;
     return ab;
 }
 
@@ -2158,8 +2474,16 @@ static void launch_scatter(Engine *E, const RConst &rc, const RBatch &rb, uint32
     else AMX_SCATTER_M(M_NONE);
 #undef AMX_SCATTER_M
 #undef AMX_SCATTER
+    // overflow records (beyond K_SLOTS per home) from the arrival-order list into contiguous pool ranges
+    {
+        const ABuf ab = make_abuf(E);
+        const unsigned blocks = (unsigned) E->sm_count * 2u;
+        k_ovf_alloc<<<blocks, 256, 0, E->stream>>>(ab);
+        k_ovf_place<<<blocks, 256, 0, E->stream>>>(ab);
+        E->ab_ovf_parity ^= 1u;
+    }
     g_ktime.end(E->stream, 0, nb);
-    E->launches++;
+    E->launches += 3;
 }
 
 // ---- tiled path: bins for RBATCH frames of the current resolution; false when the path cannot be used
@@ -2360,16 +2684,23 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         uint32_t *cnt_other = E->ab_cnt + (size_t) q * GBATCH * cv;
         // the gather clears slots [0, nb) of the other counter buffer; a longer dirty tail (previous batch was larger) is memset
         if (E->ab_dirty[q] > nb) cudaMemsetAsync(cnt_other + (size_t) nb * cv, 0, (size_t) (E->ab_dirty[q] - nb) * cv * 4, E->stream);
-        dim3 grid(div_up(rc.cw, 32), div_up(rc.ch, 8), nb);
+        dim3 grid(div_up(rc.cw, 32), div_up(rc.ch, GATHER_BY), nb);
         RenderStats *st = (RenderStats *) E->d_render_stats;
-#define AMX_GATHER(S, C) k_gather_pixel<S, C><<<grid, dim3(32, 8), 0, E->stream>>>(make_abuf(E), cnt_other, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st)
+        GList gl;
+        gl.items = E->gl_items; gl.count = E->gl_count + 2u * p; gl.count_other = E->gl_count + 2u * q; gl.cap = E->gl_cap;
+#define AMX_GATHER(S, C) k_gather_pixel<S, C><<<grid, dim3(32, GATHER_BY), 0, E->stream>>>(make_abuf(E), cnt_other, rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, st, gl)
         const bool counted = rc.density > 1;
         g_ktime.begin(E->stream);
         if (single) { if (counted) AMX_GATHER(true, true); else AMX_GATHER(true, false); }
         else        { if (counted) AMX_GATHER(false, true); else AMX_GATHER(false, false); }
 #undef AMX_GATHER
+        // the listed positions (ties, three blobs or more, long lists): one warp per CTA so that a short list still spreads over the SMs
+        if (single) k_resolve_list<true><<<(unsigned) E->sm_count * 32u, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
+        else        k_resolve_list<false><<<(unsigned) E->sm_count * 32u, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
+        if (single) k_resolve_heavy<true><<<(unsigned) E->sm_count * 4u, 128, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
+        else        k_resolve_heavy<false><<<(unsigned) E->sm_count * 4u, 128, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
         g_ktime.end(E->stream, 1, nb);
-        E->launches++;
+        E->launches += 3;
         E->ab_dirty[q] = 0; E->ab_dirty[p] = nb; E->ab_parity = q;
         nb = 0;
     };
