@@ -365,10 +365,20 @@ k_scatter(RIn ri, RConst rc, RBatch rb, uint32_t n_live, uint32_t nb, ABuf ab, R
 __global__ void __launch_bounds__(256) k_ovf_alloc(const ABuf ab) {
     if (blockIdx.x == 0u && threadIdx.x < 2u) ab.ovf_ctrl_other[threadIdx.x] = 0u;
     const uint32_t n = ab.ovf_ctrl[0];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (ab.ovf_list[i].w != K_SLOTS) continue;
-        const uint32_t hp = ab.ovf_list_home[i];
-        ab.ovf_head[hp] = atomicAdd(&ab.ovf_ctrl[1], ab.cnt[hp] - K_SLOTS);
+    const uint32_t lane = threadIdx.x & 31u;
+    // one atomicAdd per warp: the lanes' ranges follow each other (warp-uniform trip count)
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        uint32_t hp = 0u, need = 0u;
+        if (i < n && ab.ovf_list[i].w == K_SLOTS) { hp = ab.ovf_list_home[i]; need = ab.cnt[hp] - K_SLOTS; }
+        uint32_t incl = need;
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0u;
+        if (lane == 0u && total != 0u) base = atomicAdd(&ab.ovf_ctrl[1], total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need != 0u) ab.ovf_head[hp] = base + incl - need;
     }
 }
 __global__ void __launch_bounds__(256) k_ovf_place(const ABuf ab) {

@@ -235,3 +235,39 @@ def test_full_size_frame_tiled_path_matches_reference(reflib):
     assert mx <= 1, "channel diff %d" % mx
     assert n <= 0.005 * size * size, "%d pixels differ" % n
     print("1024^2 frame: %d of %d pixels differ by 1 LSB (max %d)" % (n, size * size, mx))
+
+
+def test_general_path_piles_and_many_blobs(reflib):
+    """Several chains without feather: the general path's fused gather with its three follow-up kernels.  Big rectangles matched to
+    small ones pile dozens of atoms onto a pixel near the small key frame (density 2 doubles them): positions behind more than
+    MAXK records are summed by a warp each (k_resolve_heavy), positions that three or more blobs reach are resolved from integer
+    sums per blob or replayed in order (k_resolve_list), and the homes' overflow records lie in contiguous pool ranges."""
+    rng = np.random.default_rng(3)
+    size = 72
+    big = np.zeros((size, size, 4), dtype=np.uint8)
+    small = np.zeros((size, size, 4), dtype=np.uint8)
+    for k, (x, y) in enumerate(((4, 4), (38, 6), (6, 40), (40, 40))):
+        big[y:y + 26, x:x + 26, :3] = rng.integers(0, 256, size=(26, 26, 3), dtype=np.uint8)
+        big[y:y + 26, x:x + 26, 3] = 255 - 40 * (k & 1)
+        sx, sy = 30 + 5 * (k & 1), 30 + 5 * (k >> 1)                   # the small ones lie close together: their morphs cross
+        small[sy:sy + 3, sx:sx + 3, :3] = rng.integers(0, 256, size=(3, 3, 3), dtype=np.uint8)
+        small[sy:sy + 3, sx:sx + 3, 3] = 255
+    images = [big, small]
+    params = dict(motion=eng.LINEAR, fading=eng.COSINE, density=2)
+    m = build_ref(reflib, images, seed=4, match_steps=100, **params)
+    e = engine_from_ref(m, images, seed=4, **params)
+    assert e.chain_count() >= 4
+    ts = [0.0, 0.2, 0.35, 0.45, 0.49, 0.499, 0.5, 0.6, 0.9]
+    got = e.render(ts)
+    total = ndiff = 0
+    for i, t in enumerate(ts):
+        n, mx = diff_stats(m.render(t), got[i])
+        assert mx <= 1, "t=%g: channel diff %d" % (t, mx)
+        ndiff += n
+        total += got[i].size
+    assert ndiff <= 0.01 * total
+    st = e.render_stats()
+    assert st["overflow"] > 2000 and st["generic"] > 100, st         # piles behind single homes, and replayed / listed positions
+    assert e.render_path_frames() == dict(tiled=0, general=len(ts))
+    for i in (3, 5):
+        assert np.array_equal(got[i], e.render([ts[i]])[0])
