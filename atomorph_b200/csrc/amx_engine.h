@@ -170,7 +170,9 @@ struct Engine {
     bool      tb_has_chain = false;
     bool      tiled_enabled = true;        // AMX_RENDER_TILED=0: general A-buffer path only (for comparisons)
     bool      tiled_multi = false;         // AMX_RENDER_TILED=2: tiled path for morphs with several chains as well
-    bool      tiled_blocked = false;       // a bin overflowed with the current table: general path until the next refresh
+    bool      tiled_blocked = false;       // this call only: everything through the general path (re-render after a wrapped pixel)
+    uint32_t  tiled_blocked_mask = 0;      // bit (interval & 31): a bin overflowed there with the current table -- general path for that
+                                           // key-frame interval until the next refresh
     uint64_t  tiled_frames = 0, general_frames = 0;   // diagnostics (amx_render_path_frames)
     uint32_t  tb_demand[6] = {0, 0, 0, 0, 0, 0};       // largest bin counts per class, tile total, overflow list seen (amx_render_tiled_stats)
     uint64_t  tiled_fallbacks = 0;                    // render calls that were repeated on the general path

@@ -1095,7 +1095,8 @@ struct Bins {
     uint32_t *cnt;        // [RBATCH][tiles][4] records claimed per bin in this batch (clean on entry)
     uint32_t *cnt_other;  // the counters of the previous batch: cleared by k_tile
     uint32_t *flag;       // [0] bit 0: a bin or tile overflowed, bit 1: a pixel's 32-bit sums may have wrapped (k_acc) -- the frames of the
-                          // call must be rendered again by the general path (bit 0 also keeps the tiled path off until the next table);
+                          // call must be rendered again by the general path (bit 0 also keeps the tiled path off for that key-frame interval
+                          // until the next table: [7] has bit (interval & 31) of every overflow);
                           // [1..4] largest bin count seen per class, [5] largest tile total (diagnostics)
     uint32_t  tiles_x, tiles_y;
 };
@@ -1397,7 +1398,7 @@ tile_body(const Bins &bn, const RConst &rc, const RBatch &rb,
             const uint32_t t2 = (uint32_t) ((int) ty + dty) * bn.tiles_x + (uint32_t) ((int) tx + dtx);
             n = bn.cnt[((size_t) slot * ntiles + t2) * 4u + cls];
             if (tid < 4u && n > bn.flag[1u + cls]) atomicMax(&bn.flag[1u + cls], n);
-            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); }
+            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); atomicOr(bn.flag + 7, 1u << (rb.f[slot].y & 31u)); }
             first = (slot * ntiles + t2) * T_STRIDE + bin_off(cls);
         }
         cx->segstart[tid + 1u] = n;                              // lengths first, prefix sums below
@@ -1417,7 +1418,7 @@ tile_body(const Bins &bn, const RConst &rc, const RBatch &rb,
     for (uint32_t s = 1; s <= 9u; ++s) seg[s] = seg[s - 1u] + cx->segstart[s];
     if (tid == 0u) {
         if (seg[9] > bn.flag[5]) atomicMax(&bn.flag[5], seg[9]);
-        if (seg[9] > T_SREC) atomicOr(bn.flag, 1u);             // more records than the tile's shared memory takes: rendered again
+        if (seg[9] > T_SREC) { atomicOr(bn.flag, 1u); atomicOr(bn.flag + 7, 1u << (rb.f[slot].y & 31u)); }      // more records than the tile's shared memory takes: rendered again
     }
 #pragma unroll
     for (uint32_t s = 1; s <= 9u; ++s) seg[s] = min(seg[s], T_SREC);   // (truncated for memory safety)
@@ -1714,7 +1715,7 @@ k_acc(const __grid_constant__ Bins bn, const __grid_constant__ RConst rc, const 
             const uint32_t t2 = (uint32_t) ((int) ty + dty) * bn.tiles_x + (uint32_t) ((int) tx + dtx);
             n = bn.cnt[((size_t) slot * ntiles + t2) * 4u + cls];
             if (tid < 4u && n > bn.flag[1u + cls]) atomicMax(&bn.flag[1u + cls], n);
-            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); }
+            if (n > bin_cap(cls)) { n = bin_cap(cls); atomicOr(bn.flag, 1u); atomicOr(bn.flag + 7, 1u << (rb.f[slot].y & 31u)); }
             first = (slot * ntiles + t2) * T_STRIDE + bin_off(cls);
         }
         cx.seg_n[tid] = n;
@@ -2334,7 +2335,7 @@ int engine_render_prepare(Engine *E) {
     if (bad) return okay ? AMX_ERR_CUDA : AMX_ERR_NOMEM;
     E->render_ready = true;
     E->prepare_count++;
-    E->tiled_blocked = false;                 // a new table gets a new chance on the tiled path
+    E->tiled_blocked = false; E->tiled_blocked_mask = 0u;      // a new table gets a new chance on the tiled path
     return AMX_OK;
 }
 
@@ -2687,7 +2688,8 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
     auto flush_batch = [&]() {
         // feather == 0: nb frames share one scatter and one fused gather/composite launch
         if (nb == 0) return;
-        if (tiled) { launch_tiled(E, rc, rb, nb, d_bg, d_dst); tiled_used = true; nb = 0; return; }
+        // (a key-frame interval whose bins overflowed with this table stays on the general path; the others keep the tiled one)
+        if (tiled && !((E->tiled_blocked_mask >> (rb.f[0].y & 31u)) & 1u)) { launch_tiled(E, rc, rb, nb, d_bg, d_dst); tiled_used = true; nb = 0; return; }
         E->general_frames += nb;
         launch_scatter(E, rc, rb, nb);
         const uint32_t p = E->ab_parity, q = p ^ 1u;
@@ -2739,7 +2741,8 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             if (nb > 0 && rb.f[0].y != rf.y) flush_batch();           // a batch stays inside one key-frame interval
             if (E->p.keep_background) launch_background(E, rc, rf, d_bg + (size_t) nb * np);
             rb.f[nb++] = rf;
-            if (nb == NB) { flush_batch(); if (i + 1 - shipped >= ship_every) ship(i + 1); }
+            const uint32_t nb_cap = (tiled && ((E->tiled_blocked_mask >> (rf.y & 31u)) & 1u)) ? std::min<uint32_t>(NB, GBATCH) : NB;
+            if (nb >= nb_cap) { flush_batch(); if (i + 1 - shipped >= ship_every) ship(i + 1); }
             continue;
         }
         if (E->p.keep_background) launch_background(E, rc, rf, d_bg);
@@ -2773,11 +2776,21 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
             E->tiled_fallbacks++;
             const size_t cnt_bytes = (size_t) 2 * RBATCH * E->tb_tiles_x * E->tb_tiles_y * 4 * sizeof(uint32_t);
             cudaMemsetAsync(E->tb_flag, 0, 4, E->stream);
+            cudaMemsetAsync(E->tb_flag + 7, 0, 4, E->stream);
             cudaMemsetAsync(E->tb_cnt, 0, cnt_bytes, E->stream);
             E->tb_parity = 0; E->tb_dirty[0] = E->tb_dirty[1] = 0;
+            if (latch) {
+                // the intervals that overflowed leave the tiled path until the table changes; this call is rendered again -- its other
+                // intervals through the tiled path once more (a pixel that may have wrapped in one of them: everything general)
+                E->tiled_blocked_mask |= flag8[7] ? flag8[7] : 0xffffffffu;
+                if (flag8[0] & 2u) E->tiled_blocked = true;
+                const int rcode2 = engine_render(E, times, n, out, out_is_device);
+                E->tiled_blocked = false;
+                return rcode2;
+            }
             E->tiled_blocked = true;
             const int rcode2 = engine_render(E, times, n, out, out_is_device);
-            if (!latch) E->tiled_blocked = false;
+            E->tiled_blocked = false;
             return rcode2;
         }
     }
@@ -3127,7 +3140,7 @@ int amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]) {
     }
 #endif
     for (int k = 0; k < 6; ++k) stats8[k] = ctx->e.tb_demand[k];
-    stats8[6] = ctx->e.tiled_fallbacks; stats8[7] = ctx->e.tiled_blocked ? 1 : 0;
+    stats8[6] = ctx->e.tiled_fallbacks; stats8[7] = ctx->e.tiled_blocked_mask != 0u ? 1 : 0;
     return AMX_OK;
 }
 int amx_background(amx_ctx *ctx, double t, uint32_t *out, int out_is_device) {

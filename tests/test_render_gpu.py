@@ -110,7 +110,7 @@ def test_tiled_path_overflow_falls_back(reflib):
         n, mx = diff_stats(m.render(t), e.render([t])[0])
         assert mx <= 1 and n <= 0.01 * 96 * 96
     paths = e.render_path_frames()
-    assert paths["general"] >= 3 and paths["tiled"] <= 1, paths
+    assert paths["general"] >= 3 and paths["tiled"] <= 2, paths        # one attempt per key-frame interval (two here), then general
 
 
 def test_dense_tiles_stay_on_the_tiled_path(reflib, monkeypatch):
@@ -271,3 +271,45 @@ def test_general_path_piles_and_many_blobs(reflib):
     assert e.render_path_frames() == dict(tiled=0, general=len(ts))
     for i in (3, 5):
         assert np.array_equal(got[i], e.render([ts[i]])[0])
+
+
+def test_bin_overflow_blocks_only_its_interval(monkeypatch):
+    """Three key frames, one chain: big -> big -> small.  The atoms of a covered 96 x 96 canvas (density 3) pile onto a 20 x 20
+    square in the second and third interval -- more than a tile's bins hold --, while the first interval never has more than three
+    atoms per pixel.  After the overflow only the piling intervals leave the tiled path; the frames equal the general path's."""
+    rng = np.random.default_rng(9)
+    n = 96
+    images = []
+    for k in range(3):
+        im = np.zeros((n, n, 4), dtype=np.uint8)
+        lo, hi = (0, n) if k < 2 else (38, 58)
+        im[lo:hi, lo:hi, :3] = rng.integers(0, 256, size=(hi - lo, hi - lo, 3), dtype=np.uint8)
+        im[lo:hi, lo:hi, 3] = 255
+        images.append(im)
+    params = dict(seed=2, motion=eng.LINEAR, fading=eng.LINEAR, density=3, threads=0, cycle_length=1000)
+    ts = [0.05, 0.2, 0.3, 0.4, 0.6, 0.65, 0.7, 0.9]                   # intervals 0 0 0 1 1 1 2 2
+
+    def run(tiled):
+        monkeypatch.setenv("AMX_RENDER_TILED", tiled)
+        e = eng.Engine(0, **params)
+        e.load_images(images)
+        e.step(8)
+        assert e.state() == eng.STATE_ATOM_MORPHING and e.chain_count() == 1
+        e.swap_rounds(64, want_stats=False)
+        return e
+    e1 = run("1")
+    a = e1.render(ts)
+    st = e1.render_tiled_stats()
+    assert st["fallbacks"] == 1 and st["blocked"], st
+    p1 = e1.render_path_frames()
+    a2 = e1.render(ts)                                                # no second fallback: the blocked intervals go straight to the general path
+    p2 = e1.render_path_frames()
+    assert e1.render_tiled_stats()["fallbacks"] == 1
+    assert p2["tiled"] - p1["tiled"] == 3 and p2["general"] - p1["general"] == 5, (p1, p2)
+    assert np.array_equal(a, a2)
+    # same table, general path only
+    e0 = run("0")
+    e0.import_chains(e1.chains())
+    b = e0.render(ts)
+    assert e0.render_path_frames()["tiled"] == 0
+    assert np.array_equal(a, b)
