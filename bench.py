@@ -507,7 +507,7 @@ def run_b200(args):
         kernels = None
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r03_traffic.json")) as fh:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r04_traffic.json")) as fh:
             traffic = json.load(fh).get("k_bin2+k_acc_dram_bytes_per_launch_pair")
     except Exception:
         pass

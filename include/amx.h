@@ -192,10 +192,12 @@ int  amx_render_pixels(amx_ctx *ctx, double t, uint64_t *pixels_out);
 int  amx_set_lookahead(amx_ctx *ctx, int enable);
 int  amx_lookahead_stats(amx_ctx *ctx, uint64_t stats2[2]);
 /* renderer diagnostics, cumulative since the render buffers were (re)built: [0] pixels resolved by the ordered double
- * replay of morph.cpp:598-613 instead of exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records that
- * went to an overflow list */
+ * replay of morph.cpp:598-613 or left to the list kernels (three blobs or more, more than 32 records) instead of the fused
+ * gather's exact integer sums, [1] of those the exact .5 ties, [2] A-buffer records beyond the four direct slots of their
+ * home pixel (they go to the home's range of the overflow pool) */
 int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
-/* device time of the two render kernels of every batch ([0] k_bin2 or k_scatter, [1] k_acc (k_tile) or k_gather_pixel), measured
+/* device time of the render kernels of every batch ([0] k_bin2, or k_scatter + k_ovf_alloc + k_ovf_place; [1] k_acc (k_tile), or
+ * k_gather_pixel + k_resolve_list + k_resolve_heavy), measured
  * with CUDA event pairs on the engine's stream without synchronising between launches.  Returns the milliseconds,
  * launches and frames accumulated since the previous call, then switches the recording on (enable != 0) or off.
  * Process-wide (one engine per process records). */
@@ -205,7 +207,8 @@ int  amx_kernel_times(amx_ctx *ctx, int enable, double ms2[2], uint64_t launches
 int  amx_render_path_frames(amx_ctx *ctx, uint64_t frames2[2]);
 /* tiled-path diagnostics: [0..3] largest record count seen in a bin of class interior / last column / last row / corner,
  * [4] largest record total of a tile, [5] unused (0), [6] render calls repeated on the general path,
- * [7] 1 while the tiled path is blocked for the current table */
+ * [7] 1 while a key-frame interval is kept off the tiled path for the current table (a bin overflowed there; the other
+ * intervals stay on it) */
 int  amx_render_tiled_stats(amx_ctx *ctx, uint64_t stats8[8]);
 /* one blob of the frame active at time t (morph::get_pixels(size_t,double,vector*), morph.cpp:452-678):
  * returns count via *n (pixels in reference emission order), -1 in *n when the blob index is out of range */
