@@ -713,12 +713,12 @@ __device__ __noinline__ uint32_t resolve_generic(const ABuf *abuf, uint32_t slot
     return ov.finish(bgc, rc.keep_background != 0);
 }
 
-// positions whose ordered replay is deferred to k_resolve_list
+// positions whose resolution is deferred to k_resolve
 struct GList {
     uint2    *items;              // {canvas index, batch slot}: [0, cap) replays, [cap, 2 cap) heavy positions (more than MAXK records)
     uint32_t *count;              // [0] replays, [1] heavy positions appended by this batch's gather (may exceed cap: the surplus was
                                   // resolved in place)
-    uint32_t *count_other;        // the other batch parity's counters: cleared by k_resolve_list
+    uint32_t *count_other;        // the other batch parity's counters: cleared by k_resolve
     uint32_t  cap;
 };
 #ifndef GATHER_BY
@@ -853,7 +853,7 @@ k_gather_pixel(const __grid_constant__ ABuf abuf, uint32_t *__restrict__ cnt_cle
     }
     // generic path: several blobs at the position, an exact tie, or a very long list.  The ordered replay is a few thousand
     // dependent instructions for ONE lane of this warp (config 4: 2.6 % of the pixels, 83 % of this kernel's time when resolved
-    // here), so the position goes onto a list that k_resolve_list works off with every lane busy.
+    // here), so the position goes onto a list that k_resolve works off.
     if (stats) atomicAdd(&stats->generic, 1ull);
     if (gl.cap != 0u) {
         const uint32_t heavy = csum > MAXK ? 1u : 0u;
@@ -926,20 +926,20 @@ __device__ __forceinline__ bool resolve_blobs_int(const ABuf &ab, const RConst &
 #define LIST_LANES 8u
 #endif
 template <bool SINGLE>
-__global__ void __launch_bounds__(32)
-k_resolve_list(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-               const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
-               const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-               const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList gl) {
+__device__ __forceinline__ void
+resolve_list_role(const ABuf &abuf, const RConst &rc, const RBatch &rb,
+                  const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+                  const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+                  const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList &gl, const uint32_t bid, const uint32_t nblocks) {
     const uint32_t n = min(gl.count[0], gl.cap);
-    if (blockIdx.x == 0u && threadIdx.x < 2u) gl.count_other[threadIdx.x] = 0u;
+    if (bid == 0u && threadIdx.x < 2u) gl.count_other[threadIdx.x] = 0u;
     const size_t np = (size_t) rc.width * rc.height;
     // LIST_LANES lanes of a warp take a position each: the replay is a chain of dependent instructions whose length differs from
     // position to position, so a warp runs as long as the union of its lanes' paths -- few lanes per warp and many warps hide
     // that latency
     if (threadIdx.x % (32u / LIST_LANES) != 0u) return;
     const uint32_t per_cta = LIST_LANES;
-    for (uint32_t k = blockIdx.x * per_cta + threadIdx.x / (32u / LIST_LANES); k < n; k += gridDim.x * per_cta) {
+    for (uint32_t k = bid * per_cta + threadIdx.x / (32u / LIST_LANES); k < n; k += nblocks * per_cta) {
         const uint2 it = gl.items[k];
         const uint32_t slot = it.y, px = it.x % rc.cw, py = it.x / rc.cw, y_frame = rb.f[slot].y;
         const size_t i = (size_t) py * rc.width + px;
@@ -959,16 +959,16 @@ k_resolve_list(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst
 // (ties between blobs of equal order go to the record visited first, as in resolve_contributions) and one that sums it.  A
 // position that turns out to have at most MAXK contributions with a non-zero weight goes through the serial replay on lane 0.
 template <bool SINGLE>
-__global__ void __launch_bounds__(128)
-k_resolve_heavy(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
-                const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
-                const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
-                const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList gl) {
+__device__ __forceinline__ void
+resolve_heavy_role(const ABuf &abuf, const RConst &rc, const RBatch &rb,
+                   const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+                   const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+                   const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList &gl, const uint32_t warp, const uint32_t nwarps) {
     const uint32_t n = min(gl.count[1], gl.cap);
-    const uint32_t lane = threadIdx.x & 31u, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     const size_t np = (size_t) rc.width * rc.height;
     const bool tags_ok = SINGLE || rc.nchains <= 65536u;
-    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nwarps) {
+    for (uint32_t e = warp; e < n; e += nwarps) {
         const uint2 it = gl.items[gl.cap + e];
         const uint32_t slot = it.y, px = it.x % rc.cw, py = it.x / rc.cw, y_frame = rb.f[slot].y;
         const size_t i = (size_t) py * rc.width + px;
@@ -1046,6 +1046,21 @@ k_resolve_heavy(const __grid_constant__ ABuf abuf, const __grid_constant__ RCons
         }
         if (lane == 0u) out[(size_t) rb.f[slot].dst * np + i] = ov.finish(bgc, rc.keep_background != 0);
     }
+}
+
+// Both lists of a batch in ONE launch of one-warp CTAs: the first `heavy_blocks` CTAs take a heavy position each, the others
+// LIST_LANES listed positions each.  The two kinds of work are latency chains that leave most warp slots idle (4-14 % active when
+// they ran as two kernels one after the other: 24.6 + 38.0 us per batch of BASELINE config 4), so they share the SMs.
+template <bool SINGLE>
+__global__ void __launch_bounds__(32)
+k_resolve(const __grid_constant__ ABuf abuf, const __grid_constant__ RConst rc, const __grid_constant__ RBatch rb,
+          const uint32_t *__restrict__ chain_of, const int32_t *__restrict__ blob_of_chain,
+          const uint32_t *__restrict__ blob_avg, const uint32_t *__restrict__ blob_distinct,
+          const uint32_t *__restrict__ bg, uint32_t *__restrict__ out, const GList gl, const uint32_t heavy_blocks) {
+    if (blockIdx.x < heavy_blocks)
+        resolve_heavy_role<SINGLE>(abuf, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, gl, blockIdx.x, heavy_blocks);
+    else
+        resolve_list_role<SINGLE>(abuf, rc, rb, chain_of, blob_of_chain, blob_avg, blob_distinct, bg, out, gl, blockIdx.x - heavy_blocks, gridDim.x - heavy_blocks);
 }
 
 // ---------------------------------------------------------------------------------------- tiled path (feather == 0)
@@ -2706,13 +2721,14 @@ int engine_render(Engine *E, const double *times, uint32_t n, uint32_t *out, int
         if (single) { if (counted) AMX_GATHER(true, true); else AMX_GATHER(true, false); }
         else        { if (counted) AMX_GATHER(false, true); else AMX_GATHER(false, false); }
 #undef AMX_GATHER
-        // the listed positions (ties, three blobs or more, long lists): one warp per CTA so that a short list still spreads over the SMs
-        if (single) k_resolve_list<true><<<(unsigned) E->sm_count * 32u, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
-        else        k_resolve_list<false><<<(unsigned) E->sm_count * 32u, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
-        if (single) k_resolve_heavy<true><<<(unsigned) E->sm_count * 4u, 128, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
-        else        k_resolve_heavy<false><<<(unsigned) E->sm_count * 4u, 128, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl);
+        // the listed positions (ties, three blobs or more) and the heavy ones (more than MAXK records)
+        {
+            const unsigned hb = (unsigned) E->sm_count * 8u, lb = (unsigned) E->sm_count * 24u;      // 32 one-warp CTAs per SM
+            if (single) k_resolve<true><<<hb + lb, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl, hb);
+            else        k_resolve<false><<<hb + lb, 32, 0, E->stream>>>(make_abuf(E), rc, rb, E->chain_of, E->d_blob_of_chain, E->d_blob_avg, E->d_blob_distinct, d_bg, d_dst, gl, hb);
+        }
         g_ktime.end(E->stream, 1, nb);
-        E->launches += 3;
+        E->launches += 2;
         E->ab_dirty[q] = 0; E->ab_dirty[p] = nb; E->ab_parity = q;
         nb = 0;
     };

@@ -197,7 +197,7 @@ int  amx_lookahead_stats(amx_ctx *ctx, uint64_t stats2[2]);
  * home pixel (they go to the home's range of the overflow pool) */
 int  amx_render_stats(amx_ctx *ctx, uint64_t stats3[3]);
 /* device time of the render kernels of every batch ([0] k_bin2, or k_scatter + k_ovf_alloc + k_ovf_place; [1] k_acc (k_tile), or
- * k_gather_pixel + k_resolve_list + k_resolve_heavy), measured
+ * k_gather_pixel + k_resolve), measured
  * with CUDA event pairs on the engine's stream without synchronising between launches.  Returns the milliseconds,
  * launches and frames accumulated since the previous call, then switches the recording on (enable != 0) or off.
  * Process-wide (one engine per process records). */

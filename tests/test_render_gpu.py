@@ -240,8 +240,8 @@ def test_full_size_frame_tiled_path_matches_reference(reflib):
 def test_general_path_piles_and_many_blobs(reflib):
     """Several chains without feather: the general path's fused gather with its three follow-up kernels.  Big rectangles matched to
     small ones pile dozens of atoms onto a pixel near the small key frame (density 2 doubles them): positions behind more than
-    MAXK records are summed by a warp each (k_resolve_heavy), positions that three or more blobs reach are resolved from integer
-    sums per blob or replayed in order (k_resolve_list), and the homes' overflow records lie in contiguous pool ranges."""
+    MAXK records are summed by a warp each (k_resolve, heavy role), positions that three or more blobs reach are resolved from integer
+    sums per blob or replayed in order (k_resolve, list role), and the homes' overflow records lie in contiguous pool ranges."""
     rng = np.random.default_rng(3)
     size = 72
     big = np.zeros((size, size, 4), dtype=np.uint8)
