@@ -53,7 +53,10 @@ namespace amx {
 #define MAXK 32
 #define K_SLOTS 4          // direct A-buffer slots per pixel (two 32-byte pairs)
 #define RBATCH 8           // frames per launch of the tiled path (all of one key-frame interval)
-#define GBATCH 2           // frames per launch of the general A-buffer path (its buffers are per canvas position and frame)
+#ifndef GBATCH
+#define GBATCH 4           // frames per launch of the general A-buffer path (its buffers are per canvas position and frame; 2 until the
+                           // end of round 2: the list work of a batch is latency, not throughput -- C4 13.2 k -> 14.7 k frames/s)
+#endif
 
 struct RConst {
     uint32_t width, height, cw, ch;
