@@ -4,7 +4,9 @@
  * Reference: morph::get_pixels(t) -> draw_atoms -> get_pixels(blob,t)  (morph.cpp:452-678,
  * 1302-1421), get_background (1431-1465).  The reference is a scatter into per-pixel std::map
  * lists followed by per-pixel normalisation IN ATOM ORDER, per-blob feather peeling and
- * cross-blob "over" compositing.  Here a frame is two kernels:
+ * cross-blob "over" compositing.  Two paths, both exact (identical frames): the TILED path (one chain,
+ * no feather: k_bin2 + k_acc, records binned per 32 x 32-pixel tile and accumulated with shared-memory
+ * atomics -- described where those kernels are defined) and the GENERAL path below, a per-pixel A-buffer:
  *
  *   prepare  (once per table refresh)  per atom & interval: end colours with the one-sided
  *            alpha rule resolved, Perlin lag/slope  -> coalesced SoA, 24 B/atom/interval
@@ -13,17 +15,18 @@
  *            order), colour fade; ONE 32-bit atomicAdd on the counter of the atom's HOME pixel
  *            (top-left splat target) hands out a slot, and the 16-byte record {colour, fract |
  *            chain, atom} goes straight into that slot of the per-pixel A-buffer (K_SLOTS
- *            direct slots per pixel, SoA; the rare pixel with more atoms chains the rest
- *            through an overflow list whose length is known from the counter, so nothing but
- *            the counters is ever cleared)
+ *            direct slots per pixel, SoA; a pixel with more atoms gets a contiguous range of
+ *            the overflow pool for the rest -- k_ovf_alloc / k_ovf_place, once its counter is
+ *            final -- so nothing but the counters is ever cleared)
  *   gather   per pixel: read counter + slots of the 4 homes that can reach the pixel (no
  *            pointer chasing), exact integer sums sum(c*n)/sum(n) with exact rational rounding
  *            -- provably the reference's double result unless the quotient is an exact .5 tie;
- *            ties and pixels shared by several blobs sort their contributions by (blob order,
- *            atom) and replay the reference's double sums in ITS order (morph.cpp:598-613):
- *            bit-exact.  Without feather the same thread composites the blobs "over" each other
- *            and blends the background (morph.cpp:1357-1401) and writes the RGBA pixel: no
- *            accumulator ever touches HBM.
+ *            ties sort their contributions by (blob order, atom) and replay the reference's
+ *            double sums in ITS order (morph.cpp:598-613): bit-exact.  Without feather the same
+ *            thread composites the blobs "over" each other and blends the background
+ *            (morph.cpp:1357-1401) and writes the RGBA pixel: no accumulator ever touches HBM.
+ *            What a thread cannot finish from two sets of sums (a tie, three blobs or more, more
+ *            than MAXK records) goes onto a list that k_resolve works off after the gather.
  *   feather  (only when feather > 0) per-(pixel, blob) entries, 4-neighbour erosion layers
  *            (morph.cpp:625-674), then a composite kernel.
  *
